@@ -1,0 +1,94 @@
+#!/usr/bin/env python3
+"""Create the *hooked* variant of the reference for the tests.
+
+Reads the five reference files that carry a B2 hook site from
+/root/reference/libde265, inserts the one-line hook calls at anchored positions and writes the
+patched copies to oracle/_ref/patched/libde265/ (git-ignored build output — reference sources are
+never committed).  All other reference files are compiled from where they lie.
+
+TEST INFRASTRUCTURE ONLY (see oracle/hevc_oracle.h).
+"""
+import os
+import re
+import sys
+
+
+def sub_once(text, pattern, repl, what):
+    new, n = re.subn(pattern, repl, text, count=1, flags=re.S)
+    if n != 1:
+        raise SystemExit(f"patch_ref.py: anchor not found for {what}")
+    return new
+
+
+def main():
+    ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(__file__), "_ref", "patched")
+    src = os.path.join(ref, "libde265")
+    dst = os.path.join(out, "libde265")
+    os.makedirs(dst, exist_ok=True)
+    inc = '#include "libde265_hooks.h"\n'
+    # Every other file is a symlink into the reference tree, so that `#include "decctx.h"` from any
+    # translation unit resolves to the patched header (quote-includes search the includer's directory).
+    patched = {"slice.cc", "motion.cc", "decctx.cc", "decctx.h"}
+    for name in os.listdir(src):
+        if name in patched:
+            continue
+        link = os.path.join(dst, name)
+        if os.path.islink(link) or os.path.exists(link):
+            os.remove(link) if not os.path.isdir(link) or os.path.islink(link) else None
+        if not os.path.exists(link):
+            os.symlink(os.path.join(src, name), link)
+
+    # --- slice.cc: decode_TU + PCM ---
+    t = open(os.path.join(src, "slice.cc")).read()
+    t = sub_once(t, r'(#include "slice.h"\n)', r"\1" + inc, "slice.cc include")
+    t = sub_once(
+        t,
+        r"(static void decode_TU\(thread_context\* tctx,[^{]*\{\n)",
+        r"\1  if (b200_hook_decode_TU(tctx, x0, y0, nT, cIdx, (int)cuPredMode, cbf)) return;\n",
+        "decode_TU",
+    )
+    t = sub_once(
+        t,
+        r"(ptr\[y \* stride \+ x\] = value << shift;\n\s*\}\n)",
+        r"\1  b200_hook_pcm(tctx, x0, y0, w, h, cIdx);\n",
+        "read_pcm_samples_internal",
+    )
+    open(os.path.join(dst, "slice.cc"), "w").write(t)
+
+    # --- motion.cc: generate_inter_prediction_samples ---
+    t = open(os.path.join(src, "motion.cc")).read()
+    t = sub_once(t, r'(#include "motion.h"\n)', r"\1" + inc, "motion.cc include")
+    t = sub_once(
+        t,
+        r"(void generate_inter_prediction_samples\(base_context\* ctx,[^{]*\{\n)",
+        r"\1  if (b200_hook_inter_pred(ctx, shdr, img, xC + xB, yC + yB, nPbW, nPbH, vi)) return;\n",
+        "generate_inter_prediction_samples",
+    )
+    open(os.path.join(dst, "motion.cc"), "w").write(t)
+
+    # --- decctx.cc: post-processing filters -> picture done ---
+    t = open(os.path.join(src, "decctx.cc")).read()
+    t = sub_once(t, r'(#include "decctx.h"\n)', r"\1" + inc, "decctx.cc include")
+    t = sub_once(
+        t,
+        r"(\n\s*)(if \(img->decctx->num_worker_threads\)\s*\n\s*run_postprocessing_filters_parallel\(imgunit\);)",
+        r"\1if (b200_hook_picture_done(this, imgunit->img)) { } else\1\2",
+        "decode_some post-processing",
+    )
+    open(os.path.join(dst, "decctx.cc"), "w").write(t)
+
+    # --- decctx.h: per-context hook state ---
+    t = open(os.path.join(src, "decctx.h")).read()
+    t = sub_once(
+        t,
+        r"(struct acceleration_functions acceleration;[^\n]*\n)",
+        r"\1  void* b200_state = nullptr; // B200 reconstruction backend (libde265_hooks.h)\n",
+        "base_context member",
+    )
+    open(os.path.join(dst, "decctx.h"), "w").write(t)
+    print("patched:", dst)
+
+
+if __name__ == "__main__":
+    main()
