@@ -134,7 +134,7 @@ def load(path=None):
     if not os.path.exists(p):
         raise OSError(f"{p} not found: run `python -c 'import __graft_entry__ as g; g.build()'` first "
                       "(there is no CPU fallback for the reconstruction engine)")
-    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(p)
     vp = C.c_void_p
     lib.b200_engine_create.argtypes = [C.POINTER(vp), C.c_int]
     lib.b200_engine_destroy.argtypes = [vp]

@@ -1,0 +1,525 @@
+// engine.cu — host side of the B200 reconstruction engine (b200hevc.h part 2) + kernel launches.
+//
+// Per picture: group TUs by CTB, cut PUs into MC tiles, pack everything into one pinned staging
+// buffer, ONE host->device copy, then  k_inter_pred -> k_recon -> k_deblock<V> -> k_deblock<H> -> k_sao
+// on the engine's stream.  Reference pictures never leave the device (DPB slots are device surfaces).
+// There is no CPU fallback: without a CUDA device b200_engine_create fails with B200_ERR_NO_DEVICE.
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "b200hevc.h"
+#include "dev_common.cuh"
+#include "kernels_filter.cuh"
+#include "kernels_mc.cuh"
+#include "kernels_recon.cuh"
+
+// ---- error reporting -----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char* b200_last_error(void) { return g_err; }
+
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return set_err(B200_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- surfaces ------------------------------------------------------------------------------------
+struct Surface {
+  uint8_t* plane[3] = {nullptr, nullptr, nullptr};
+  int pitch[3] = {0, 0, 0};
+  int w = 0, h = 0, cw = 0, ch = 0, chroma = 0, bd_y = 0, bd_c = 0;
+  bool valid = false;  // holds a picture
+};
+
+static void surface_free(Surface& s)
+{
+  for (int c = 0; c < 3; c++) {
+    if (s.plane[c]) cudaFree(s.plane[c]);
+    s.plane[c] = nullptr;
+  }
+  s.w = s.h = 0;
+  s.valid = false;
+}
+
+static int bytes_per_sample(int bd) { return bd > 8 ? 2 : 1; }
+
+static int surface_ensure(Surface& s, const b200_pic_params& p)
+{
+  const int cw = p.chroma_format_idc ? p.width / 2 : 0, ch = p.chroma_format_idc ? p.height / 2 : 0;
+  if (s.plane[0] && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc &&
+      bytes_per_sample(s.bd_y) == bytes_per_sample(p.bit_depth_luma) && bytes_per_sample(s.bd_c) == bytes_per_sample(p.bit_depth_chroma)) {
+    s.bd_y = p.bit_depth_luma;
+    s.bd_c = p.bit_depth_chroma;
+    return B200_OK;
+  }
+  surface_free(s);
+  s.w = p.width; s.h = p.height; s.cw = cw; s.ch = ch; s.chroma = p.chroma_format_idc;
+  s.bd_y = p.bit_depth_luma; s.bd_c = p.bit_depth_chroma;
+  // rows padded to 256 bytes: every CTB row segment starts 16-byte aligned and vector accesses may overshoot
+  // the picture width inside the padding
+  s.pitch[0] = (int)align_up((size_t)p.width * bytes_per_sample(p.bit_depth_luma) + 16, 256);
+  s.pitch[1] = s.pitch[2] = cw ? (int)align_up((size_t)cw * bytes_per_sample(p.bit_depth_chroma) + 16, 256) : 0;
+  CU(cudaMalloc(&s.plane[0], (size_t)s.pitch[0] * p.height));
+  CU(cudaMemset(s.plane[0], 0, (size_t)s.pitch[0] * p.height));
+  for (int c = 1; c < 3 && cw; c++) {
+    CU(cudaMalloc(&s.plane[c], (size_t)s.pitch[c] * ch));
+    CU(cudaMemset(s.plane[c], 0, (size_t)s.pitch[c] * ch));
+  }
+  return B200_OK;
+}
+
+// ---- engine --------------------------------------------------------------------------------------
+struct StagingSet {
+  uint8_t* host = nullptr;  // pinned
+  uint8_t* dev = nullptr;
+  size_t cap = 0;
+  cudaEvent_t done = nullptr;  // recorded after the last kernel that reads `dev`
+  bool in_flight = false;
+};
+
+struct b200_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Surface slot[B200_MAX_SLOTS];
+  Surface scratch;
+  StagingSet stage[2];
+  int cur_stage = 0;
+  unsigned int* sync_buf = nullptr;  // [1 + n_ctb] ticket + done flags
+  size_t sync_cap = 0;
+  bool timing = false;
+  cudaEvent_t ev[7] = {};
+  float last_ms[6] = {};
+  bool have_timing = false;
+  uint64_t launches = 0;
+  // host scratch reused across pictures
+  std::vector<uint32_t> ctb_count, tiles;
+};
+
+static bool g_tables_ready[64] = {};
+
+static int init_tables(int device)
+{
+  if (device < 64 && g_tables_ready[device]) return B200_OK;
+  // HEVC core transform: mat[k][n] = +-T((2n+1)k mod 128) with T = first matrix column (cosine symmetry);
+  // the 32 base magnitudes are the transform's definition (fallback-dct.cc:512-545 column 0).
+  static const int8_t T[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                               61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9,  4,  0};
+  int8_t m[32][32];
+  for (int k = 0; k < 32; k++)
+    for (int n = 0; n < 32; n++) {
+      int j = ((2 * n + 1) * k) % 128, sign = 1;
+      if (j > 64) j = 128 - j;
+      if (j > 32) { j = 64 - j; sign = -1; }
+      m[k][n] = (int8_t)(sign * T[j]);
+    }
+  CU(cudaMemcpyToSymbol(c_dct, m, sizeof(m)));
+  if (device < 64) g_tables_ready[device] = true;
+  return B200_OK;
+}
+
+extern "C" int b200_engine_create(b200_engine** out, int device)
+{
+  if (!out) return set_err(B200_ERR_INVALID, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_err(B200_ERR_NO_DEVICE, "no CUDA device available (%s); the B200 engine has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return set_err(B200_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  CU(cudaSetDevice(device));
+  b200_engine* en = new (std::nothrow) b200_engine();
+  if (!en) return set_err(B200_ERR_NOMEM, "out of memory");
+  en->device = device;
+  int rc = init_tables(device);
+  if (rc) { delete en; return rc; }
+  CU(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&en->stage[i].done, cudaEventDisableTiming));
+  for (int i = 0; i < 7; i++) CU(cudaEventCreate(&en->ev[i]));
+  CU(cudaFuncSetAttribute(k_recon<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint8_t>)));
+  CU(cudaFuncSetAttribute(k_recon<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint16_t>)));
+  *out = en;
+  return B200_OK;
+}
+
+extern "C" void b200_engine_destroy(b200_engine* en)
+{
+  if (!en) return;
+  cudaSetDevice(en->device);
+  if (en->stream) cudaStreamSynchronize(en->stream);
+  for (auto& s : en->slot) surface_free(s);
+  surface_free(en->scratch);
+  for (auto& st : en->stage) {
+    if (st.host) cudaFreeHost(st.host);
+    if (st.dev) cudaFree(st.dev);
+    if (st.done) cudaEventDestroy(st.done);
+  }
+  if (en->sync_buf) cudaFree(en->sync_buf);
+  for (auto& e : en->ev)
+    if (e) cudaEventDestroy(e);
+  if (en->stream) cudaStreamDestroy(en->stream);
+  delete en;
+}
+
+extern "C" void* b200_engine_stream(b200_engine* en) { return en ? (void*)en->stream : nullptr; }
+extern "C" uint64_t b200_engine_launch_count(const b200_engine* en) { return en ? en->launches : 0; }
+
+extern "C" int b200_engine_enable_timing(b200_engine* en, int on)
+{
+  if (!en) return set_err(B200_ERR_INVALID, "null engine");
+  en->timing = on != 0;
+  en->have_timing = false;
+  return B200_OK;
+}
+
+extern "C" int b200_engine_last_timing(b200_engine* en, float ms[6])
+{
+  if (!en || !ms) return set_err(B200_ERR_INVALID, "null argument");
+  if (!en->have_timing) return set_err(B200_ERR_INVALID, "no timed picture yet");
+  CU(cudaSetDevice(en->device));
+  CU(cudaEventSynchronize(en->ev[6]));
+  float total = 0;
+  for (int i = 0; i < 5; i++) {
+    CU(cudaEventElapsedTime(&ms[i], en->ev[i], en->ev[i + 1]));
+  }
+  CU(cudaEventElapsedTime(&total, en->ev[0], en->ev[6]));
+  ms[5] = total;
+  return B200_OK;
+}
+
+static int check_params(const b200_pic_params& p)
+{
+  if (p.width == 0 || p.height == 0) return set_err(B200_ERR_INVALID, "empty picture");
+  if (p.log2_ctb_size < 4 || p.log2_ctb_size > 6) return set_err(B200_ERR_INVALID, "log2_ctb_size %d", p.log2_ctb_size);
+  if (p.dst_slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "dst_slot %d", p.dst_slot);
+  if (p.chroma_format_idc > 1) return set_err(B200_ERR_UNSUPPORTED, "chroma_format_idc %d: the device path implements 4:0:0 and 4:2:0", p.chroma_format_idc);
+  if (p.bit_depth_luma < 8 || p.bit_depth_luma > 12 || p.bit_depth_chroma < 8 || p.bit_depth_chroma > 12)
+    return set_err(B200_ERR_UNSUPPORTED, "bit depth %d/%d (8..12 supported)", p.bit_depth_luma, p.bit_depth_chroma);
+  if ((p.bit_depth_luma > 8) != (p.bit_depth_chroma > 8)) return set_err(B200_ERR_UNSUPPORTED, "mixed 8-bit / high-bit-depth planes");
+  if ((p.width & 7) || (p.height & 7)) return set_err(B200_ERR_INVALID, "picture size must be a multiple of the minimum CB size (8)");
+  return B200_OK;
+}
+
+static DevPic make_devpic(const b200_pic_params& p, const Surface& cur, const Surface& out)
+{
+  DevPic d{};
+  d.w = p.width; d.h = p.height;
+  d.cw = cur.cw; d.ch = cur.ch;
+  d.bd_y = p.bit_depth_luma; d.bd_c = p.bit_depth_chroma;
+  d.log2ctb = p.log2_ctb_size;
+  const int S = 1 << d.log2ctb;
+  d.wctb = (p.width + S - 1) / S; d.hctb = (p.height + S - 1) / S;
+  d.w4 = (p.width + 3) / 4; d.h4 = (p.height + 3) / 4;
+  d.w8 = (p.width + 7) / 8; d.h8 = (p.height + 7) / 8;
+  d.chroma = p.chroma_format_idc;
+  d.cb_qp_off = p.pps_cb_qp_offset; d.cr_qp_off = p.pps_cr_qp_offset;
+  d.flags = p.flags;
+  for (int c = 0; c < 3; c++) { d.cur[c] = cur.plane[c]; d.out[c] = out.plane[c]; d.pitch[c] = cur.pitch[c]; }
+  return d;
+}
+
+template <typename P>
+static int launch_picture(b200_engine* en, const b200_picture* pic, const DevPic& dp, const RefTable& refs, const uint8_t* dbase,
+                          const size_t* off, int n_tiles, bool run_deblock, bool run_sao)
+{
+  cudaStream_t st = en->stream;
+  const int n_ctb = dp.wctb * dp.hctb;
+  if (en->timing) CU(cudaEventRecord(en->ev[1], st));
+  if (n_tiles > 0) {
+    k_inter_pred<P><<<(n_tiles + 3) / 4, 128, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
+                                                         (const uint32_t*)(dbase + off[12]), n_tiles);
+    en->launches++;
+  }
+  if (en->timing) CU(cudaEventRecord(en->ev[2], st));
+  if (pic->n_tu > 0 && pic->params.stop_after_stage != B200_STAGE_INTER_PRED) {
+    ReconArgs ra;
+    ra.tus = (const b200_tu*)(dbase + off[2]);
+    ra.ctb_tu_start = (const uint32_t*)(dbase + off[3]);
+    ra.ctb_has_intra = dbase + off[4];
+    ra.coeffs = (const b200_coeff*)(dbase + off[5]);
+    ra.scaling = pic->scaling_factors ? dbase + off[11] : nullptr;
+    ra.ticket = en->sync_buf;
+    ra.ctb_done = en->sync_buf + 1;
+    CU(cudaMemsetAsync(en->sync_buf, 0, sizeof(unsigned int) * (size_t)(1 + n_ctb), st));
+    k_recon<P><<<n_ctb, RC_THREADS, sizeof(ReconSmem<P>), st>>>(dp, ra);
+    en->launches++;
+  }
+  if (en->timing) CU(cudaEventRecord(en->ev[3], st));
+  FilterArgs fa;
+  fa.bs_map = dbase + off[8];
+  fa.qp_map = (const int8_t*)(dbase + off[9]);
+  fa.nofilt_map = dbase + off[10];
+  fa.slices = (const b200_slice_info*)(dbase + off[6]);
+  fa.ctbs = (const b200_ctb_info*)(dbase + off[7]);
+  if (run_deblock) {
+    const int nseg = ((dp.w4 + 1) / 2) * dp.h4 > dp.w4 * ((dp.h4 + 1) / 2) ? ((dp.w4 + 1) / 2) * dp.h4 : dp.w4 * ((dp.h4 + 1) / 2);
+    dim3 grid((nseg + 127) / 128, dp.chroma ? 2 : 1);
+    k_deblock<P, true><<<grid, 128, 0, st>>>(dp, fa);
+    k_deblock<P, false><<<grid, 128, 0, st>>>(dp, fa);
+    en->launches += 2;
+  }
+  if (en->timing) CU(cudaEventRecord(en->ev[4], st));
+  if (run_sao) {
+    dim3 grid((dp.w + 255) / 256, dp.h, dp.chroma ? 3 : 1);
+    k_sao<P><<<grid, 256, 0, st>>>(dp, fa);
+    en->launches++;
+  }
+  if (en->timing) CU(cudaEventRecord(en->ev[5], st));
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* pic)
+{
+  if (!en || !pic) return set_err(B200_ERR_INVALID, "null argument");
+  const b200_pic_params& p = pic->params;
+  int rc = check_params(p);
+  if (rc) return rc;
+  CU(cudaSetDevice(en->device));
+  if ((pic->n_pu && !pic->pus) || (pic->n_tu && !pic->tus) || (pic->n_coeff && !pic->coeffs) || !pic->slices || !pic->ctbs || !pic->qp_map ||
+      !pic->nofilt_map || pic->n_slices == 0)
+    return set_err(B200_ERR_INVALID, "missing record arrays");
+  if (pic->n_pu >= (1u << 20)) return set_err(B200_ERR_INVALID, "too many PUs");
+
+  const int S = 1 << p.log2_ctb_size;
+  const int wctb = (p.width + S - 1) / S, hctb = (p.height + S - 1) / S, n_ctb = wctb * hctb;
+  const int w4 = (p.width + 3) / 4, h4 = (p.height + 3) / 4, w8 = (p.width + 7) / 8, h8 = (p.height + 7) / 8;
+
+  const bool run_deblock = !(p.flags & B200_PIC_SKIP_DEBLOCK) && pic->bs_map &&
+                           (p.stop_after_stage == B200_STAGE_ALL || p.stop_after_stage == B200_STAGE_DEBLOCK);
+  const bool run_sao = (p.flags & B200_PIC_SAO_ENABLED) && !(p.flags & B200_PIC_SKIP_SAO) && p.stop_after_stage == B200_STAGE_ALL;
+
+  // ---- surfaces ----
+  Surface& dst = en->slot[p.dst_slot];
+  rc = surface_ensure(dst, p);
+  if (rc) return rc;
+  Surface* cur = &dst;
+  if (run_sao) {
+    rc = surface_ensure(en->scratch, p);
+    if (rc) return rc;
+    cur = &en->scratch;
+  }
+  RefTable refs;
+  memset(&refs, 0, sizeof(refs));
+  for (int i = 0; i < B200_MAX_SLOTS; i++) {
+    const Surface& s = en->slot[i];
+    if (i != p.dst_slot && s.valid && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc && s.bd_y == p.bit_depth_luma &&
+        s.bd_c == p.bit_depth_chroma)
+      for (int c = 0; c < 3; c++) refs.plane[i][c] = s.plane[c];
+  }
+
+  // ---- host preparation: TU grouping by CTB (stable), MC tiles ----
+  // section order: 0 pus, 1 weights, 2 tus(sorted), 3 ctb_tu_start, 4 ctb_has_intra, 5 coeffs, 6 slices, 7 ctbs,
+  //                8 bs_map, 9 qp_map, 10 nofilt_map, 11 scaling, 12 tiles
+  std::vector<uint32_t>& tiles = en->tiles;
+  tiles.clear();
+  for (uint32_t i = 0; i < pic->n_pu; i++) {
+    const b200_pu& pu = pic->pus[i];
+    if (pu.w == 0 || pu.h == 0 || pu.w > 64 || pu.h > 64 || (pu.w & 3) || (pu.h & 3) || (pu.x & 3) || (pu.y & 3) ||
+        pu.x + pu.w > p.width || pu.y + pu.h > p.height)
+      return set_err(B200_ERR_INVALID, "PU %u out of range", i);
+    if ((pu.flags & B200_PU_WEIGHTED) && pu.wt_idx >= pic->n_weights) return set_err(B200_ERR_INVALID, "PU %u weight index", i);
+    if (!(pu.flags & (B200_PU_PRED_L0 | B200_PU_PRED_L1))) continue;
+    for (int ty = 0; ty * MC_TILE < pu.h; ty++)
+      for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
+  }
+  const int n_tiles = (int)tiles.size();
+
+  size_t sz[13], off[13];
+  sz[0] = sizeof(b200_pu) * pic->n_pu;
+  sz[1] = sizeof(b200_weight_entry) * pic->n_weights;
+  sz[2] = sizeof(b200_tu) * pic->n_tu;
+  sz[3] = sizeof(uint32_t) * (size_t)(n_ctb + 1);
+  sz[4] = (size_t)n_ctb;
+  sz[5] = sizeof(b200_coeff) * pic->n_coeff;
+  sz[6] = sizeof(b200_slice_info) * pic->n_slices;
+  sz[7] = sizeof(b200_ctb_info) * (size_t)n_ctb;
+  sz[8] = run_deblock ? (size_t)w4 * h4 : 0;
+  sz[9] = (size_t)w8 * h8;
+  sz[10] = (size_t)w8 * h8;
+  sz[11] = pic->scaling_factors ? B200_SCALING_FACTOR_BYTES : 0;
+  sz[12] = sizeof(uint32_t) * (size_t)n_tiles;
+  size_t total = 0;
+  for (int i = 0; i < 13; i++) { off[i] = total; total += align_up(sz[i], 256); }
+  if (total == 0) total = 256;
+
+  StagingSet& ss = en->stage[en->cur_stage];
+  en->cur_stage ^= 1;
+  if (ss.in_flight) { CU(cudaEventSynchronize(ss.done)); ss.in_flight = false; }
+  if (ss.cap < total) {
+    if (ss.host) cudaFreeHost(ss.host);
+    if (ss.dev) cudaFree(ss.dev);
+    ss.host = nullptr; ss.dev = nullptr;
+    ss.cap = align_up(total + total / 2, 1 << 20);
+    CU(cudaMallocHost(&ss.host, ss.cap));
+    CU(cudaMalloc(&ss.dev, ss.cap));
+  }
+  if (en->sync_cap < (size_t)(1 + n_ctb)) {
+    if (en->sync_buf) cudaFree(en->sync_buf);
+    en->sync_buf = nullptr;
+    CU(cudaMalloc(&en->sync_buf, sizeof(unsigned int) * (size_t)(1 + n_ctb)));
+    en->sync_cap = (size_t)(1 + n_ctb);
+  }
+  uint8_t* hb = ss.host;
+  if (sz[0]) memcpy(hb + off[0], pic->pus, sz[0]);
+  if (sz[1]) memcpy(hb + off[1], pic->weights, sz[1]);
+  {
+    // counting sort of TUs by CTB address, keeping decode order inside each CTB
+    uint32_t* start = (uint32_t*)(hb + off[3]);
+    uint8_t* has_intra = hb + off[4];
+    memset(start, 0, sz[3]);
+    memset(has_intra, 0, sz[4]);
+    std::vector<uint32_t>& cnt = en->ctb_count;
+    cnt.assign((size_t)n_ctb, 0);
+    for (uint32_t i = 0; i < pic->n_tu; i++) {
+      const b200_tu& tu = pic->tus[i];
+      const int sh = tu.cidx ? 1 : 0;
+      const int nT = 1 << tu.log2_size;
+      const int pw = tu.cidx ? p.width / 2 : p.width, ph = tu.cidx ? p.height / 2 : p.height;
+      if (tu.log2_size < 2 || tu.log2_size > 5 || tu.cidx > 2 || (tu.cidx && !p.chroma_format_idc) || tu.x + nT > pw || tu.y + nT > ph ||
+          (tu.x & 3) || (tu.y & 3))
+        return set_err(B200_ERR_INVALID, "TU %u out of range", i);
+      if ((size_t)tu.coeff_off + tu.n_coeff > pic->n_coeff || tu.n_coeff > nT * nT) return set_err(B200_ERR_INVALID, "TU %u coefficient range", i);
+      if ((tu.flags & B200_TU_INTRA) && tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
+      const int cx = (tu.x << sh) >> p.log2_ctb_size, cy = (tu.y << sh) >> p.log2_ctb_size;
+      if ((((tu.x + nT - 1) << sh) >> p.log2_ctb_size) != cx || (((tu.y + nT - 1) << sh) >> p.log2_ctb_size) != cy)
+        return set_err(B200_ERR_INVALID, "TU %u crosses a CTB boundary", i);
+      cnt[(size_t)cx + (size_t)cy * wctb]++;
+    }
+    uint32_t acc = 0;
+    for (int i = 0; i < n_ctb; i++) { start[i] = acc; acc += cnt[i]; cnt[i] = start[i]; }
+    start[n_ctb] = acc;
+    b200_tu* sorted = (b200_tu*)(hb + off[2]);
+    for (uint32_t i = 0; i < pic->n_tu; i++) {
+      const b200_tu& tu = pic->tus[i];
+      const int sh = tu.cidx ? 1 : 0;
+      const size_t ctb = (size_t)((tu.x << sh) >> p.log2_ctb_size) + (size_t)((tu.y << sh) >> p.log2_ctb_size) * wctb;
+      sorted[cnt[ctb]++] = tu;
+      if (tu.flags & B200_TU_INTRA) has_intra[ctb] = 1;
+    }
+  }
+  if (sz[5]) memcpy(hb + off[5], pic->coeffs, sz[5]);
+  memcpy(hb + off[6], pic->slices, sz[6]);
+  for (int i = 0; i < n_ctb; i++)
+    if (pic->ctbs[i].slice_idx >= pic->n_slices) return set_err(B200_ERR_INVALID, "CTB %d slice index", i);
+  memcpy(hb + off[7], pic->ctbs, sz[7]);
+  if (sz[8]) memcpy(hb + off[8], pic->bs_map, sz[8]);
+  memcpy(hb + off[9], pic->qp_map, sz[9]);
+  memcpy(hb + off[10], pic->nofilt_map, sz[10]);
+  if (sz[11]) memcpy(hb + off[11], pic->scaling_factors, sz[11]);
+  if (sz[12]) memcpy(hb + off[12], tiles.data(), sz[12]);
+
+  // ---- device work ----
+  cudaStream_t st = en->stream;
+  if (en->timing) CU(cudaEventRecord(en->ev[0], st));
+  CU(cudaMemcpyAsync(ss.dev, ss.host, total, cudaMemcpyHostToDevice, st));
+  const DevPic dp = make_devpic(p, *cur, dst);
+  if (p.bit_depth_luma > 8) rc = launch_picture<uint16_t>(en, pic, dp, refs, ss.dev, off, n_tiles, run_deblock, run_sao);
+  else rc = launch_picture<uint8_t>(en, pic, dp, refs, ss.dev, off, n_tiles, run_deblock, run_sao);
+  if (rc) return rc;
+  if (en->timing) { CU(cudaEventRecord(en->ev[6], st)); en->have_timing = true; }
+  CU(cudaEventRecord(ss.done, st));
+  ss.in_flight = true;
+  dst.valid = true;
+  return B200_OK;
+}
+
+extern "C" int b200_engine_sync(b200_engine* en)
+{
+  if (!en) return set_err(B200_ERR_INVALID, "null engine");
+  CU(cudaSetDevice(en->device));
+  CU(cudaStreamSynchronize(en->stream));
+  return B200_OK;
+}
+
+template <typename P>
+__global__ void k_fill(uint8_t* base, int pitch, int w, int h, int value)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < w && y < h) row_ptr<P>(base, pitch, y)[x] = (P)value;
+}
+
+extern "C" int b200_engine_fill_slot(b200_engine* en, int slot, const b200_pic_params* p, int vy, int vc)
+{
+  if (!en || !p || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
+  int rc = check_params(*p);
+  if (rc) return rc;
+  CU(cudaSetDevice(en->device));
+  Surface& s = en->slot[slot];
+  rc = surface_ensure(s, *p);
+  if (rc) return rc;
+  for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
+    const int w = c ? s.cw : s.w, h = c ? s.ch : s.h;
+    dim3 grid((w + 255) / 256, h);
+    if (p->bit_depth_luma > 8) k_fill<uint16_t><<<grid, 256, 0, en->stream>>>(s.plane[c], s.pitch[c], w, h, c ? vc : vy);
+    else k_fill<uint8_t><<<grid, 256, 0, en->stream>>>(s.plane[c], s.pitch[c], w, h, c ? vc : vy);
+    en->launches++;
+  }
+  CU(cudaGetLastError());
+  s.valid = true;
+  return B200_OK;
+}
+
+extern "C" int b200_engine_upload_slot(b200_engine* en, int slot, const b200_pic_params* p, const void* const planes[3], const size_t strides[3])
+{
+  if (!en || !p || !planes || !strides || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
+  int rc = check_params(*p);
+  if (rc) return rc;
+  CU(cudaSetDevice(en->device));
+  Surface& s = en->slot[slot];
+  rc = surface_ensure(s, *p);
+  if (rc) return rc;
+  for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
+    const int w = c ? s.cw : s.w, h = c ? s.ch : s.h, bps = bytes_per_sample(c ? s.bd_c : s.bd_y);
+    if (!planes[c]) return set_err(B200_ERR_INVALID, "plane %d missing", c);
+    CU(cudaMemcpy2DAsync(s.plane[c], s.pitch[c], planes[c], strides[c], (size_t)w * bps, h, cudaMemcpyHostToDevice, en->stream));
+  }
+  CU(cudaStreamSynchronize(en->stream));  // the source may be pageable / reused by the caller
+  s.valid = true;
+  return B200_OK;
+}
+
+extern "C" int b200_engine_read_slot_async(b200_engine* en, int slot, void* const planes[3], const size_t strides[3])
+{
+  if (!en || !planes || !strides || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
+  const Surface& s = en->slot[slot];
+  if (!s.valid) return set_err(B200_ERR_INVALID, "slot %d holds no picture", slot);
+  CU(cudaSetDevice(en->device));
+  for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
+    if (!planes[c]) continue;
+    const int w = c ? s.cw : s.w, h = c ? s.ch : s.h, bps = bytes_per_sample(c ? s.bd_c : s.bd_y);
+    CU(cudaMemcpy2DAsync(planes[c], strides[c], s.plane[c], s.pitch[c], (size_t)w * bps, h, cudaMemcpyDeviceToHost, en->stream));
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_engine_read_slot(b200_engine* en, int slot, void* const planes[3], const size_t strides[3])
+{
+  int rc = b200_engine_read_slot_async(en, slot, planes, strides);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(en->stream));
+  return B200_OK;
+}
+
+extern "C" int b200_engine_slot_device_planes(b200_engine* en, int slot, void* planes[3], size_t strides[3])
+{
+  if (!en || !planes || !strides || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
+  const Surface& s = en->slot[slot];
+  if (!s.valid) return set_err(B200_ERR_INVALID, "slot %d holds no picture", slot);
+  for (int c = 0; c < 3; c++) { planes[c] = s.plane[c]; strides[c] = (size_t)s.pitch[c]; }
+  return B200_OK;
+}

@@ -1,0 +1,202 @@
+// kernels_filter.cuh — in-loop filters for one picture.
+//
+// k_deblock<P, VERT>: one thread per 4-line edge segment (luma on the 8x8 grid, Cb and Cr on the
+//   chroma 8x8 grid), decisions + filtering fused.  Replaces edge_filtering_luma_internal
+//   (deblock.cc:412-605), edge_filtering_chroma_internal (:635-761) and the deblock_luma/chroma
+//   kernels (fallback-deblk.h:32-124).  Launched twice per picture: all vertical edges, then all
+//   horizontal edges (deblock.cc:908-946).  Edge flags / boundary strengths arrive in bs_map.
+// k_sao<P>: one thread per sample, reads the deblocked surface, writes the DPB surface (out-of-place
+//   exactly like sao.cc:327-382), copying samples that SAO leaves untouched.  Replaces apply_sao_internal
+//   (sao.cc:28-263).
+#pragma once
+#include "dev_common.cuh"
+
+struct FilterArgs {
+  const uint8_t* bs_map;
+  const int8_t* qp_map;
+  const uint8_t* nofilt_map;
+  const b200_slice_info* slices;
+  const b200_ctb_info* ctbs;
+};
+
+__constant__ uint8_t k_tab_beta[52] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  6,  7,
+                                       8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 22, 24, 26, 28, 30, 32,
+                                       34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64};
+__constant__ uint8_t k_tab_tc[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  0,  0,  1,  1,  1,  1,  1,  1,  1,  1,  1,
+                                     2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8,  9,  10, 11, 13, 14, 16, 18, 20, 22, 24};
+__constant__ uint8_t k_tab_qpc[13] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37};
+
+__device__ __forceinline__ int qpy_at(const DevPic& pic, const FilterArgs& a, int x, int y) { return a.qp_map[(x >> 3) + (y >> 3) * pic.w8]; }
+__device__ __forceinline__ int nofilt_at(const DevPic& pic, const FilterArgs& a, int x, int y) { return a.nofilt_map[(x >> 3) + (y >> 3) * pic.w8] & 1; }
+__device__ __forceinline__ const b200_slice_info& slice_at(const DevPic& pic, const FilterArgs& a, int x, int y)
+{
+  return a.slices[a.ctbs[(x >> pic.log2ctb) + (y >> pic.log2ctb) * pic.wctb].slice_idx];
+}
+
+template <typename P, bool VERT>
+__global__ void __launch_bounds__(128) k_deblock(DevPic pic, FilterArgs a)
+{
+  // blockIdx.y: 0 luma, 1 chroma (both Cb and Cr per thread)
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.y == 0) {
+    // luma segments: VERT: x even (8-px grid), every y;  HORZ: every x, y even   [units of 4 samples]
+    const int nx = VERT ? (pic.w4 + 1) / 2 : pic.w4;
+    const int ny = VERT ? pic.h4 : (pic.h4 + 1) / 2;
+    if (id >= nx * ny) return;
+    const int ux = VERT ? (id % nx) * 2 : id % nx, uy = VERT ? id / nx : (id / nx) * 2;
+    const int b = a.bs_map[ux + uy * pic.w4];
+    const int bS = VERT ? B200_BS_V(b) : B200_BS_H(b);
+    if (bS == 0) return;
+    const int xd = ux << 2, yd = uy << 2;
+    const int pitch = pic.pitch[0];
+    const ptrdiff_t sa = VERT ? 1 : pitch / (int)sizeof(P), sb = VERT ? pitch / (int)sizeof(P) : 1;  // across / along the edge, in samples
+    P* ptr = row_ptr<P>(pic.cur[0], pitch, yd) + xd;
+    const int bd = pic.bd_y;
+    int p[4][4], q[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        q[k][i] = ptr[k * sb + i * sa];
+        p[k][i] = ptr[k * sb - (i + 1) * sa];
+      }
+    const int qp_q = qpy_at(pic, a, xd, yd);
+    const int qp_p = VERT ? qpy_at(pic, a, xd - 1, yd) : qpy_at(pic, a, xd, yd - 1);
+    const int qpl = (qp_q + qp_p + 1) >> 1;
+    const b200_slice_info sl = slice_at(pic, a, xd, yd);
+    const int beta = k_tab_beta[clip3i(0, 51, qpl + sl.beta_offset)] * (1 << (bd - 8));
+    const int tc = k_tab_tc[clip3i(0, 53, qpl + 2 * (bS - 1) + sl.tc_offset)] * (1 << (bd - 8));
+    const int dp0 = abs(p[0][2] - 2 * p[0][1] + p[0][0]), dp3 = abs(p[3][2] - 2 * p[3][1] + p[3][0]);
+    const int dq0 = abs(q[0][2] - 2 * q[0][1] + q[0][0]), dq3 = abs(q[3][2] - 2 * q[3][1] + q[3][0]);
+    const int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3, d = dpq0 + dpq3;
+    if (d >= beta) return;
+    const bool s0 = 2 * dpq0 < (beta >> 2) && abs(p[0][3] - p[0][0]) + abs(q[0][0] - q[0][3]) < (beta >> 3) && abs(p[0][0] - q[0][0]) < ((5 * tc + 1) >> 1);
+    const bool s3 = 2 * dpq3 < (beta >> 2) && abs(p[3][3] - p[3][0]) + abs(q[3][0] - q[3][3]) < (beta >> 3) && abs(p[3][0] - q[3][0]) < ((5 * tc + 1) >> 1);
+    const bool strong = s0 && s3;
+    const bool dEp = dp < ((beta + (beta >> 1)) >> 3), dEq = dq < ((beta + (beta >> 1)) >> 3);
+    const bool fP = !(VERT ? nofilt_at(pic, a, xd - 1, yd) : nofilt_at(pic, a, xd, yd - 1));
+    const bool fQ = !nofilt_at(pic, a, xd, yd);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int p0 = p[k][0], p1 = p[k][1], p2 = p[k][2], p3 = p[k][3], q0 = q[k][0], q1 = q[k][1], q2 = q[k][2], q3 = q[k][3];
+      P* c = ptr + k * sb;
+      if (strong) {
+        if (fP) {
+          c[-sa] = (P)clip3i(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+          c[-2 * sa] = (P)clip3i(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0 + 2) >> 2);
+          c[-3 * sa] = (P)clip3i(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+        }
+        if (fQ) {
+          c[0] = (P)clip3i(q0 - 2 * tc, q0 + 2 * tc, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+          c[sa] = (P)clip3i(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0 + q1 + q2 + 2) >> 2);
+          c[2 * sa] = (P)clip3i(q2 - 2 * tc, q2 + 2 * tc, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+        }
+      } else {
+        int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+        if (abs(delta) < tc * 10) {
+          delta = clip3i(-tc, tc, delta);
+          if (fP) c[-sa] = (P)clip_bd(p0 + delta, bd);
+          if (fQ) c[0] = (P)clip_bd(q0 - delta, bd);
+          if (dEp && fP) c[-2 * sa] = (P)clip_bd(p1 + clip3i(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + delta) >> 1), bd);
+          if (dEq && fQ) c[sa] = (P)clip_bd(q1 + clip3i(-(tc >> 1), tc >> 1, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1), bd);
+        }
+      }
+    }
+  } else {
+    if (!pic.chroma) return;
+    // chroma (4:2:0): edges on the chroma 8x8 grid = every 16 luma samples across, 4 chroma lines = 8 luma lines along
+    // [units of 4 luma samples]: VERT: x step 4, y step 2;  HORZ: x step 2, y step 4   (deblock.cc:650-663)
+    const int xs = VERT ? 4 : 2, ys = VERT ? 2 : 4;
+    const int nx = (pic.w4 + xs - 1) / xs, ny = (pic.h4 + ys - 1) / ys;
+    if (id >= nx * ny) return;
+    const int ux = (id % nx) * xs, uy = (id / nx) * ys;
+    const int b = a.bs_map[ux + uy * pic.w4];
+    const int bS = VERT ? B200_BS_V(b) : B200_BS_H(b);
+    if (bS < 2) return;
+    const int xl = ux << 2, yl = uy << 2, xd = xl >> 1, yd = yl >> 1;
+    const int qp_q = qpy_at(pic, a, xl, yl);
+    const int qp_p = VERT ? qpy_at(pic, a, xl - 1, yl) : qpy_at(pic, a, xl, yl - 1);
+    const b200_slice_info sl = slice_at(pic, a, xl, yl);
+    const bool fP = !(VERT ? nofilt_at(pic, a, xl - 1, yl) : nofilt_at(pic, a, xl, yl - 1));
+    const bool fQ = !nofilt_at(pic, a, xl, yl);
+    const int bd = pic.bd_c;
+#pragma unroll
+    for (int c = 1; c <= 2; c++) {
+      const int qpi = ((qp_q + qp_p + 1) >> 1) + (c == 1 ? pic.cb_qp_off : pic.cr_qp_off);
+      const int qpc = (qpi < 30) ? qpi : (qpi >= 43) ? qpi - 6 : k_tab_qpc[qpi - 30];  // table8_22, transform.h:29-34
+      const int tc = k_tab_tc[clip3i(0, 53, qpc + 2 * (bS - 1) + sl.tc_offset)] * (1 << (bd - 8));
+      const int pitch = pic.pitch[c];
+      const ptrdiff_t sa = VERT ? 1 : pitch / (int)sizeof(P), sb = VERT ? pitch / (int)sizeof(P) : 1;
+      P* ptr = row_ptr<P>(pic.cur[c], pitch, yd) + xd;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        P* e = ptr + k * sb;
+        const int p0 = e[-sa], p1 = e[-2 * sa], q0 = e[0], q1 = e[sa];
+        const int delta = clip3i(-tc, tc, ((((q0 - p0) * 4) + p1 - q1 + 4) >> 3));
+        if (fP) e[-sa] = (P)clip_bd(p0 + delta, bd);
+        if (fQ) e[0] = (P)clip_bd(q0 - delta, bd);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+template <typename P>
+__global__ void __launch_bounds__(256) k_sao(DevPic pic, FilterArgs a)
+{
+  const int c = blockIdx.z;  // colour plane
+  const int sh = c ? 1 : 0;
+  const int width = c ? pic.cw : pic.w, height = c ? pic.ch : pic.h;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= width || y >= height) return;
+  const P* in = row_ptr<P>(pic.cur[c], pic.pitch[c], y);
+  P* out = row_ptr<P>(pic.out[c], pic.pitch[c], y);
+  const int v = in[x];
+  int res = v;
+  const int ctbshift = pic.log2ctb - sh;
+  const int xCtb = x >> ctbshift, yCtb = y >> ctbshift;
+  const b200_ctb_info& ci = a.ctbs[xCtb + yCtb * pic.wctb];
+  const b200_slice_info& sl = a.slices[ci.slice_idx];
+  const bool on = c ? (sl.flags & B200_SLICE_SAO_CHROMA) : (sl.flags & B200_SLICE_SAO_LUMA);
+  const int type = (ci.sao_type >> (2 * c)) & 3;
+  if (on && type != 0 && !nofilt_at(pic, a, x << sh, y << sh)) {
+    const int bd = c ? pic.bd_c : pic.bd_y, maxv = (1 << bd) - 1;
+    if (type == 2) {
+      const int cls = (ci.sao_eo_class >> (2 * c)) & 3;
+      const int hx0 = (cls == 1) ? 0 : (cls == 3) ? 1 : -1, hx1 = -hx0;
+      const int vy0 = (cls == 0) ? 0 : -1, vy1 = -vy0;
+      const int S = 1 << ctbshift;
+      const int xC = xCtb << ctbshift, yC = yCtb << ctbshift;
+      const int ctbW = min(S, width - xC), ctbH = min(S, height - yC);
+      const int i = x - xC, j = y - yC;
+      bool skip = false;
+      if (i == 0 || j == 0 || i == ctbW - 1 || j == ctbH - 1) {
+        // sao.cc:49: slice address of the CTB looked up with COMPONENT coordinates (reference quirk, kept)
+        const int ctb_addr = (int)slice_at(pic, a, min(xC, pic.w - 1), min(yC, pic.h - 1)).slice_addr_rs;
+        const b200_slice_info& sc = slice_at(pic, a, x << sh, y << sh);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int xS = x + (k ? hx1 : hx0), yS = y + (k ? vy1 : vy0);
+          if (xS < 0 || yS < 0 || xS >= width || yS >= height) { skip = true; break; }
+          const b200_ctb_info& cn = a.ctbs[((xS << sh) >> pic.log2ctb) + ((yS << sh) >> pic.log2ctb) * pic.wctb];
+          const b200_slice_info& sn = a.slices[cn.slice_idx];
+          if ((int)sn.slice_addr_rs < ctb_addr && !(sc.flags & B200_SLICE_LF_ACROSS_SLICES)) { skip = true; break; }
+          if ((int)sn.slice_addr_rs > ctb_addr && !(sn.flags & B200_SLICE_LF_ACROSS_SLICES)) { skip = true; break; }
+          if (!(pic.flags & B200_PIC_LF_ACROSS_TILES) && cn.tile_id != ci.tile_id) { skip = true; break; }
+        }
+      }
+      if (!skip) {
+        const int na = row_ptr<P>(pic.cur[c], pic.pitch[c], y + vy0)[x + hx0];
+        const int nb = row_ptr<P>(pic.cur[c], pic.pitch[c], y + vy1)[x + hx1];
+        const int e = ((v > na) - (v < na)) + ((v > nb) - (v < nb));
+        const int off = (e == 0) ? 0 : ci.sao_offset[c][e < 0 ? e + 2 : e + 1];  // [-2,-1,1,2] -> offsets 0,1,2,3 (sao.cc:95-100)
+        res = clip3i(0, maxv, v + off);
+      }
+    } else {
+      const int band = clip3i(0, maxv, v) >> (bd - 5);
+      const int k = (band - ci.sao_band_pos[c]) & 31;
+      if (k < 4) res = clip3i(0, maxv, v + ci.sao_offset[c][k]);
+    }
+  }
+  out[x] = (P)res;
+}

@@ -56,7 +56,7 @@ class Image:
 
 class Decoder:
     def __init__(self, libpath):
-        self.lib = lib = C.CDLL(libpath, mode=C.RTLD_GLOBAL)
+        self.lib = lib = C.CDLL(libpath)  # RTLD_LOCAL: several libde265 builds may coexist in one process
         vp = C.c_void_p
         lib.de265_new_decoder.restype = vp
         lib.de265_free_decoder.argtypes = [vp]

@@ -40,3 +40,42 @@ def oracle():
 def ref_path(name):
     p = os.path.join(REF_DIR, name)
     return p if os.path.exists(p) else None
+
+
+class Oracle:
+    """Python wrapper of the CPU restatement's picture replay (orc_*)."""
+
+    def __init__(self):
+        self.lib = oracle()
+        self.ctx = self.lib.orc_create()
+
+    def close(self):
+        if self.ctx:
+            self.lib.orc_destroy(self.ctx)
+            self.ctx = None
+
+    def reconstruct(self, pic):
+        cp = getattr(pic, "c", pic)
+        rc = self.lib.orc_reconstruct(self.ctx, C.byref(cp))
+        if rc:
+            raise RuntimeError(f"orc_reconstruct failed: {rc}")
+
+    def upload_slot(self, slot, params, planes):
+        pa = capi.PlaneArray(*[p.ctypes.data for p in planes])
+        sa = capi.StrideArray(*[p.strides[0] for p in planes])
+        assert self.lib.orc_upload_slot(self.ctx, slot, C.byref(params), pa, sa) == 0
+
+    def fill_slot(self, slot, params, vy, vc):
+        assert self.lib.orc_fill_slot(self.ctx, slot, C.byref(params), vy, vc) == 0
+
+    def read_slot(self, slot, params):
+        import numpy as np
+        dt = np.uint16 if params.bit_depth_luma > 8 else np.uint8
+        shapes = [(params.height, params.width)]
+        if params.chroma_format_idc:
+            shapes += [(params.height // 2, params.width // 2)] * 2
+        out = [np.empty(s, dt) for s in shapes]
+        ptrs = [o.ctypes.data for o in out] + [None] * (3 - len(out))
+        strides = [o.strides[0] for o in out] + [0] * (3 - len(out))
+        assert self.lib.orc_read_slot(self.ctx, slot, capi.PlaneArray(*ptrs), capi.StrideArray(*strides)) == 0
+        return out
