@@ -1,0 +1,326 @@
+#!/usr/bin/env python3
+"""bench.py — decoded frames/s of the reconstruction hot path on BASELINE.json's 4K Main random-access config.
+
+A "step" is one intra period of 32 pictures at 3840x2160 8-bit 4:2:0 in decode order (1 I + 3 P + 28 B,
+hierarchical-B GOP 8, deblocking + SAO on) replayed from synthetic command records (no HEVC encoder exists
+offline).  Lines printed (one JSON object, rank 0):
+  value     frames/s with the records already resident in HBM (b200_engine_run_prepared), device-timed
+  e2e       frames/s through the C-ABI with HOST buffers: b200_engine_submit_picture (pack + H2D of the records)
+            and a D2H read of every finished picture into pinned host memory inside the timed region
+  roofline  the dominant kernel (and the MC kernel, the one BASELINE's roofline target names) vs measured HBM peak
+  cpu_baseline  the same records replayed on the host cores by the CPU restatement (bounded sample)
+--impl reference times the CPU arm alone with all host threads.
+N GPUs (torchrun): every rank decodes its own independent stream (BASELINE config 5) - no data-path collective.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, BD = 3840, 2160, 8
+GOP = [8, 4, 2, 6, 1, 3, 5, 7]  # decode order inside a hierarchical-B GOP (POC offsets)
+GOP_REFS = {8: (0, None), 4: (0, 8), 2: (0, 4), 6: (4, 8), 1: (0, 2), 3: (2, 4), 5: (4, 6), 7: (6, 8)}
+
+
+def build_workload(width, height, bd, seed0=1000):
+    """32 pictures in decode order from 6 generated base pictures (slots are patched per use)."""
+    from libde265_b200 import synth
+    t0 = time.time()
+    base = {
+        "I": synth.make_picture(width, height, "I", seed=seed0, bit_depth=bd),
+        "P": synth.make_picture(width, height, "P", seed=seed0 + 1, bit_depth=bd, ref_slots=(0,)),
+    }
+    for i in range(4):
+        base[f"B{i}"] = synth.make_picture(width, height, "B", seed=seed0 + 2 + i, bit_depth=bd, ref_slots=(0, 1), weighted=(i == 3))
+    seq = []
+    bcount = 0
+    for g in range(4):  # pocs g*8+1 .. g*8+8, previous key picture at g*8
+        for off in GOP:
+            poc = g * 8 + off
+            r0, r1 = GOP_REFS[off]
+            ref_a = (g * 8 + r0) % 16
+            ref_b = (g * 8 + (r1 if r1 is not None else r0)) % 16
+            if off == 8:
+                kind = "I" if g == 3 else "P"  # one intra picture per 32
+            else:
+                kind = f"B{bcount % 4}"
+                bcount += 1
+            b = base[kind]
+            pus = b.pus.copy()
+            if len(pus):
+                lut = np.array([ref_a, ref_b], np.int8)
+                rs = pus["ref_slot"]
+                pus["ref_slot"] = np.where(rs >= 0, lut[np.clip(rs, 0, 1)], rs)
+            params = type(b.params).from_buffer_copy(b.params)
+            params.dst_slot = poc % 16
+            params.poc = poc
+            seq.append(synth.SynthPicture(params, pus, b.weights, b.tus, b.coeffs, b.slices, b.ctbs, b.bs_map, b.qp_map, b.nofilt_map))
+    return seq, time.time() - t0
+
+
+def algorithmic_bytes(seq, bd):
+    """SURVEY §8(d) per-kernel algorithmic bytes, summed over the step's pictures."""
+    bps = 2 if bd > 8 else 1
+    out = {"inter_pred": 0, "recon": 0, "deblock": 0, "sao": 0}
+    for p in seq:
+        pic_bytes = (p.params.width * p.params.height * 3 // 2) * bps
+        out["inter_pred"] += p.algorithmic_mc_bytes()
+        tu = p.tus
+        if len(tu):
+            px = (1 << (2 * tu["log2_size"].astype(np.int64)))
+            intra = (tu["flags"] & 1) != 0
+            cbf = (tu["flags"] & 2) != 0
+            # residual: 4 B per coefficient + 1 R + 1 W of the touched samples; intra: 1 W per sample + 4nT+1 border reads; + record
+            out["recon"] += int(4 * len(p.coeffs) + (2 * px * cbf).sum() * bps + (px * intra).sum() * bps +
+                                ((4 * (1 << tu["log2_size"].astype(np.int64)) + 1) * intra).sum() * bps + 24 * len(tu))
+        out["deblock"] += 2 * (2 * pic_bytes) + len(p.bs_map) + 2 * len(p.qp_map)
+        out["sao"] += 2 * pic_bytes + 24 * len(p.ctbs)
+    return out
+
+
+class ClockSampler:
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+def cpu_replay_worker(args):
+    """One host core: generates one 4K B picture and replays it `reps` times with the CPU restatement; returns (pictures, seconds)."""
+    seed0, width, height, bd, reps = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib  # CPU baseline leg: the only place bench.py touches the oracle
+    from libde265_b200 import synth
+    orc = oracle_lib.Oracle()
+    pic = synth.make_picture(width, height, "B", seed=seed0, bit_depth=bd, ref_slots=(0, 1), dst_slot=2)
+    for s in (0, 1):
+        orc.upload_slot(s, pic.params, synth.random_planes(width, height, bd, s + 1))
+    t0 = time.time()
+    for _ in range(reps):
+        orc.reconstruct(pic)
+    dt = time.time() - t0
+    orc.close()
+    return reps, dt
+
+
+def cpu_baseline_parallel(width, height, bd, cores, reps):
+    """All host cores, one independent stream per core (the CPU analogue of one stream per GPU)."""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(cpu_replay_worker, [(1002 + i % 4, width, height, bd, reps) for i in range(cores)])
+    wall = max(r[1] for r in res)  # replay time of the slowest worker (generation excluded)
+    n = sum(r[0] for r in res)
+    return {"value": round(n / wall, 3), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} replays of synthetic 4K B pictures ({reps}/core, {cores} processes) by the CPU restatement oracle/hevc_oracle.c (scalar C, -O2)"}
+
+
+def cpu_baseline_inline(seq, ref0, n_pics):
+    """Rank 0, one core: replays the first pictures of the very workload the GPU ran."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib  # CPU baseline leg: the only place bench.py touches the oracle
+    orc = oracle_lib.Oracle()
+    orc.upload_slot(0, seq[0].params, ref0)
+    t0 = time.time()
+    for p in seq[:n_pics]:
+        orc.reconstruct(p)
+    dt = time.time() - t0
+    orc.close()
+    return {"value": round(n_pics / dt, 3), "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"first {n_pics} pictures of the step (decode order: P,B,B,...) replayed by the CPU restatement oracle/hevc_oracle.c (scalar C, -O2)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=W)
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--bit-depth", type=int, default=BD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"{a.width}x{a.height} {a.bit_depth}-bit 4:2:0 synthetic command records, hierarchical-B GOP8, intra period 32 "
+                          "(1 I + 3 P + 28 B per step), deblock+SAO on, one independent stream per GPU",
+              "pictures_per_step": 32, "l2_policy": "per-step working set (16 DPB surfaces x 12.4 MB + records) exceeds the 126 MB L2"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        reps = 8 if a.width * a.height > 1920 * 1080 else 32
+        vals = []
+        for _ in range(max(1, min(a.steps, 2))):
+            vals.append(cpu_baseline_parallel(a.width, a.height, a.bit_depth, cores, reps))
+        best = max(vals, key=lambda v: v["value"])
+        line = {"impl": "reference", "metric": "decoded frames/sec at 4K Main profile, bit-exact YUV", "value": best["value"], "unit": "frames/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1000.0 * 32 / best["value"], 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if a.bit_depth == 8 else "u16", "data": "synthetic",
+                "config": config, "cpu_baseline": best,
+                "e2e": {"value": best["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from libde265_b200 import capi, synth
+    from libde265_b200.engine import Engine
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    eng = Engine(local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+
+    seq, gen_s = build_workload(a.width, a.height, a.bit_depth, seed0=1000 + 100 * rank)
+    params = seq[0].params
+    ref0 = synth.random_planes(a.width, a.height, a.bit_depth, 7 + rank)
+    eng.upload_slot(0, params, ref0)  # POC 0 reference
+    prepared = [eng.prepare(p) for p in seq]
+    h2d_bytes = sum(int(p.pus.nbytes + p.weights.nbytes + p.tus.nbytes + p.coeffs.nbytes + p.slices.nbytes + p.ctbs.nbytes + p.bs_map.nbytes +
+                        p.qp_map.nbytes + p.nofilt_map.nbytes) for p in seq)
+    bps = 2 if a.bit_depth > 8 else 1
+    pic_bytes = a.width * a.height * 3 // 2 * bps
+    # pinned host output buffers for the e2e leg (two, alternating)
+    outs = [[torch.empty((a.height, a.width), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory(),
+             torch.empty((a.height // 2, a.width // 2), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory(),
+             torch.empty((a.height // 2, a.width // 2), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory()] for _ in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident():
+        for h in prepared:
+            eng.run_prepared(h)
+
+    def step_e2e():
+        for i, p in enumerate(seq):
+            eng.submit(p)
+            o = outs[i & 1]
+            capi.check(eng.lib.b200_engine_read_slot_async(eng.handle, p.params.dst_slot, capi.PlaneArray(*[t.data_ptr() for t in o]),
+                                                           capi.StrideArray(*[t.stride(0) * bps for t in o])), "read_slot_async")
+
+    for _ in range(max(3, a.warmup)):
+        step_resident()
+    eng.sync()
+    # ---- value: records resident in HBM, kernels only; per-stage CUDA-event timing on the launching stream ----
+    eng.enable_timing(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = eng.launch_count()
+    ms_res = timed(step_resident, a.steps)
+    launches = eng.launch_count() - l0
+    clk = clocks.stop()
+    stage_ms, n_timed = eng.timing_sum(reset=True)
+    eng.enable_timing(False)
+    # ---- e2e: host records in, pictures out ----
+    for _ in range(2):
+        step_e2e()
+    eng.sync()
+    ms_e2e = timed(step_e2e, a.steps)
+
+    if rank == 0:
+        frames = 32 * a.steps * world
+        fps = frames / (ms_res / 1000.0)
+        fps_e2e = frames / (ms_e2e / 1000.0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        alg = algorithmic_bytes(seq, a.bit_depth)
+        per_stage = {}
+        for k in ("inter_pred", "recon", "deblock", "sao"):
+            ms = stage_ms[k] / max(1, n_timed) * 32  # per step
+            gbs = (alg[k] / 1e9) / (ms / 1000.0) if ms > 0 else 0.0
+            per_stage[k] = {"ms_per_step": round(ms, 4), "algorithmic_MB_per_step": round(alg[k] / 1e6, 2), "achieved_gbs": round(gbs, 1),
+                            "frac": round(gbs / peak, 4)}
+        dominant = max(per_stage, key=lambda k: per_stage[k]["ms_per_step"])
+        traffic = {}
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic_per_launch.json")))
+        except (OSError, ValueError):
+            pass
+
+        def roof(k):
+            launches_per_step = {"inter_pred": 31, "recon": 32, "deblock": 64, "sao": 32}[k]
+            return {"kernel": {"inter_pred": "k_inter_pred", "recon": "k_recon", "deblock": "k_deblock<V>+<H>", "sao": "k_sao"}[k],
+                    "bound": "hbm", "achieved": per_stage[k]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_stage[k]["frac"],
+                    "traffic": traffic.get(k), "peak_source": peak_src, "avg_launch_ms": round(per_stage[k]["ms_per_step"] / launches_per_step, 5),
+                    "algorithmic_bytes_per_launch": int(alg[k] / launches_per_step)}
+
+        line = {"metric": "decoded frames/sec at 4K Main profile, bit-exact YUV; MC kernel HBM GB/s", "value": round(fps, 2), "unit": "frames/s",
+                "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": round(ms_res / a.steps, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8" if a.bit_depth == 8 else "u16", "data": "synthetic", "config": config,
+                "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 * pic_bytes,
+                        "ms_per_step": round(ms_e2e / a.steps, 4)},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof(dominant), "roofline_mc": roof("inter_pred"),
+                "stages": per_stage, "workload_gen_s": round(gen_s, 1)}
+        if not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_inline(seq, ref0, 16 if a.width * a.height > 1920 * 1080 else 32)
+        print(json.dumps(line))
+    for h in prepared:
+        eng.free_prepared(h)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -226,6 +226,14 @@ B200_API void b200_engine_destroy(b200_engine*);
  * engine's stream, leaving the picture resident in DPB slot params.dst_slot. */
 B200_API int  b200_engine_submit_picture(b200_engine*, const b200_picture*);
 
+/* Prepared pictures: validate + upload the records ONCE and keep them resident in HBM; running a prepared
+ * picture only launches the kernels (bench.py `value`: inputs already resident when the timed region starts;
+ * also the replay path for cached pictures).  A prepared picture keeps its own device arena until freed. */
+typedef struct b200_prepared b200_prepared;
+B200_API int  b200_engine_prepare_picture(b200_engine*, const b200_picture*, b200_prepared** out);
+B200_API int  b200_engine_run_prepared(b200_engine*, b200_prepared*);
+B200_API void b200_engine_free_prepared(b200_engine*, b200_prepared*);
+
 /* Fill a slot with a constant (generate_unavailable_reference_picture, decctx.cc:1294). */
 B200_API int  b200_engine_fill_slot(b200_engine*, int slot, const b200_pic_params*, int value_y, int value_c);
 
@@ -249,6 +257,9 @@ B200_API int  b200_engine_slot_device_planes(b200_engine*, int slot, void* plane
  * Only recorded when enabled. */
 B200_API int  b200_engine_enable_timing(b200_engine*, int on);
 B200_API int  b200_engine_last_timing(b200_engine*, float ms[6]);
+/* Sum of the per-stage times over the (up to 256 most recent) pictures submitted since timing was enabled /
+ * last reset; *n_pictures receives how many pictures the sums cover.  Blocks until they have finished. */
+B200_API int  b200_engine_timing_sum(b200_engine*, float ms[6], int* n_pictures, int reset);
 /* Number of kernels this engine has launched so far (bench.py "gpu_launches"). */
 B200_API uint64_t b200_engine_launch_count(const b200_engine*);
 

@@ -115,7 +115,8 @@ EXPORTS = [
     "b200_engine_create", "b200_engine_destroy", "b200_engine_submit_picture", "b200_engine_fill_slot",
     "b200_engine_upload_slot", "b200_engine_read_slot", "b200_engine_read_slot_async", "b200_engine_sync",
     "b200_engine_slot_device_planes", "b200_engine_enable_timing", "b200_engine_last_timing",
-    "b200_engine_launch_count", "b200_engine_stream", "b200_last_error", "b200_abi_version",
+    "b200_engine_launch_count", "b200_engine_stream", "b200_engine_prepare_picture", "b200_engine_run_prepared",
+    "b200_engine_free_prepared", "b200_engine_timing_sum", "b200_last_error", "b200_abi_version",
     "b200_rec_create", "b200_rec_destroy", "b200_rec_begin_picture", "b200_rec_add_slice", "b200_rec_add_weights",
     "b200_rec_add_pu", "b200_rec_add_tu", "b200_rec_set_ctb", "b200_rec_bs_map", "b200_rec_qp_map",
     "b200_rec_nofilt_map", "b200_rec_set_scaling_factors", "b200_rec_end_picture",
@@ -148,6 +149,11 @@ def load(path=None):
     lib.b200_engine_slot_device_planes.argtypes = [vp, C.c_int, PlaneArray, StrideArray]
     lib.b200_engine_enable_timing.argtypes = [vp, C.c_int]
     lib.b200_engine_last_timing.argtypes = [vp, C.POINTER(C.c_float * 6)]
+    lib.b200_engine_prepare_picture.argtypes = [vp, C.POINTER(Picture), C.POINTER(vp)]
+    lib.b200_engine_run_prepared.argtypes = [vp, vp]
+    lib.b200_engine_free_prepared.argtypes = [vp, vp]
+    lib.b200_engine_free_prepared.restype = None
+    lib.b200_engine_timing_sum.argtypes = [vp, C.POINTER(C.c_float * 6), C.POINTER(C.c_int), C.c_int]
     lib.b200_engine_launch_count.argtypes = [vp]
     lib.b200_engine_launch_count.restype = C.c_uint64
     lib.b200_engine_stream.argtypes = [vp]

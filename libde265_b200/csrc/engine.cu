@@ -103,12 +103,27 @@ struct b200_engine {
   unsigned int* sync_buf = nullptr;  // [1 + n_ctb] ticket + done flags
   size_t sync_cap = 0;
   bool timing = false;
-  cudaEvent_t ev[7] = {};
-  float last_ms[6] = {};
-  bool have_timing = false;
+  std::vector<cudaEvent_t> tev;  // timing ring: TIMING_RING pictures x 7 events
+  unsigned tcount = 0;           // pictures recorded since enable / reset
+  cudaEvent_t* ev = nullptr;     // events of the picture being submitted
   uint64_t launches = 0;
   // host scratch reused across pictures
   std::vector<uint32_t> ctb_count, tiles;
+};
+
+#define TIMING_RING 256
+
+struct PicLayout {
+  size_t off[13] = {}, total = 0;
+  int n_tiles = 0;
+  bool run_deblock = false, run_sao = false, has_scaling = false;
+  b200_pic_params params{};
+  uint32_t n_tu = 0;
+};
+
+struct b200_prepared {
+  uint8_t* dev = nullptr;
+  PicLayout L;
 };
 
 static bool g_tables_ready[64] = {};
@@ -149,7 +164,6 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   if (rc) { delete en; return rc; }
   CU(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&en->stage[i].done, cudaEventDisableTiming));
-  for (int i = 0; i < 7; i++) CU(cudaEventCreate(&en->ev[i]));
   CU(cudaFuncSetAttribute(k_recon<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint8_t>)));
   CU(cudaFuncSetAttribute(k_recon<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint16_t>)));
   *out = en;
@@ -169,7 +183,7 @@ extern "C" void b200_engine_destroy(b200_engine* en)
     if (st.done) cudaEventDestroy(st.done);
   }
   if (en->sync_buf) cudaFree(en->sync_buf);
-  for (auto& e : en->ev)
+  for (auto& e : en->tev)
     if (e) cudaEventDestroy(e);
   if (en->stream) cudaStreamDestroy(en->stream);
   delete en;
@@ -181,23 +195,47 @@ extern "C" uint64_t b200_engine_launch_count(const b200_engine* en) { return en 
 extern "C" int b200_engine_enable_timing(b200_engine* en, int on)
 {
   if (!en) return set_err(B200_ERR_INVALID, "null engine");
+  CU(cudaSetDevice(en->device));
+  if (on && en->tev.empty()) {
+    en->tev.assign((size_t)TIMING_RING * 7, nullptr);
+    for (auto& e : en->tev) CU(cudaEventCreate(&e));
+  }
   en->timing = on != 0;
-  en->have_timing = false;
+  en->tcount = 0;
+  return B200_OK;
+}
+
+static int timing_of(b200_engine* en, unsigned idx, float ms[6])
+{
+  cudaEvent_t* ev = &en->tev[(size_t)(idx % TIMING_RING) * 7];
+  CU(cudaEventSynchronize(ev[6]));
+  for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  CU(cudaEventElapsedTime(&ms[5], ev[0], ev[6]));
   return B200_OK;
 }
 
 extern "C" int b200_engine_last_timing(b200_engine* en, float ms[6])
 {
   if (!en || !ms) return set_err(B200_ERR_INVALID, "null argument");
-  if (!en->have_timing) return set_err(B200_ERR_INVALID, "no timed picture yet");
+  if (!en->timing || en->tcount == 0) return set_err(B200_ERR_INVALID, "no timed picture yet");
   CU(cudaSetDevice(en->device));
-  CU(cudaEventSynchronize(en->ev[6]));
-  float total = 0;
-  for (int i = 0; i < 5; i++) {
-    CU(cudaEventElapsedTime(&ms[i], en->ev[i], en->ev[i + 1]));
+  return timing_of(en, en->tcount - 1, ms);
+}
+
+extern "C" int b200_engine_timing_sum(b200_engine* en, float ms[6], int* n_pictures, int reset)
+{
+  if (!en || !ms || !n_pictures) return set_err(B200_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(en->device));
+  for (int i = 0; i < 6; i++) ms[i] = 0;
+  const unsigned n = en->timing ? (en->tcount < TIMING_RING ? en->tcount : TIMING_RING) : 0;
+  for (unsigned k = 0; k < n; k++) {
+    float one[6];
+    int rc = timing_of(en, en->tcount - 1 - k, one);
+    if (rc) return rc;
+    for (int i = 0; i < 6; i++) ms[i] += one[i];
   }
-  CU(cudaEventElapsedTime(&total, en->ev[0], en->ev[6]));
-  ms[5] = total;
+  *n_pictures = (int)n;
+  if (reset) en->tcount = 0;
   return B200_OK;
 }
 
@@ -233,10 +271,12 @@ static DevPic make_devpic(const b200_pic_params& p, const Surface& cur, const Su
 }
 
 template <typename P>
-static int launch_picture(b200_engine* en, const b200_picture* pic, const DevPic& dp, const RefTable& refs, const uint8_t* dbase,
-                          const size_t* off, int n_tiles, bool run_deblock, bool run_sao)
+static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp, const RefTable& refs, const uint8_t* dbase)
 {
   cudaStream_t st = en->stream;
+  const size_t* off = L.off;
+  const int n_tiles = L.n_tiles;
+  const bool run_deblock = L.run_deblock, run_sao = L.run_sao;
   const int n_ctb = dp.wctb * dp.hctb;
   if (en->timing) CU(cudaEventRecord(en->ev[1], st));
   if (n_tiles > 0) {
@@ -245,13 +285,13 @@ static int launch_picture(b200_engine* en, const b200_picture* pic, const DevPic
     en->launches++;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[2], st));
-  if (pic->n_tu > 0 && pic->params.stop_after_stage != B200_STAGE_INTER_PRED) {
+  if (L.n_tu > 0 && L.params.stop_after_stage != B200_STAGE_INTER_PRED) {
     ReconArgs ra;
     ra.tus = (const b200_tu*)(dbase + off[2]);
     ra.ctb_tu_start = (const uint32_t*)(dbase + off[3]);
     ra.ctb_has_intra = dbase + off[4];
     ra.coeffs = (const b200_coeff*)(dbase + off[5]);
-    ra.scaling = pic->scaling_factors ? dbase + off[11] : nullptr;
+    ra.scaling = L.has_scaling ? dbase + off[11] : nullptr;
     ra.ticket = en->sync_buf;
     ra.ctb_done = en->sync_buf + 1;
     CU(cudaMemsetAsync(en->sync_buf, 0, sizeof(unsigned int) * (size_t)(1 + n_ctb), st));
@@ -283,48 +323,26 @@ static int launch_picture(b200_engine* en, const b200_picture* pic, const DevPic
   return B200_OK;
 }
 
-extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* pic)
+// Validates the records, groups TUs by CTB, cuts PUs into MC tiles and packs everything into `hb`
+// (which must hold L->total bytes; call with hb == nullptr first to size it).
+static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
 {
-  if (!en || !pic) return set_err(B200_ERR_INVALID, "null argument");
   const b200_pic_params& p = pic->params;
   int rc = check_params(p);
   if (rc) return rc;
-  CU(cudaSetDevice(en->device));
   if ((pic->n_pu && !pic->pus) || (pic->n_tu && !pic->tus) || (pic->n_coeff && !pic->coeffs) || !pic->slices || !pic->ctbs || !pic->qp_map ||
       !pic->nofilt_map || pic->n_slices == 0)
     return set_err(B200_ERR_INVALID, "missing record arrays");
   if (pic->n_pu >= (1u << 20)) return set_err(B200_ERR_INVALID, "too many PUs");
-
   const int S = 1 << p.log2_ctb_size;
   const int wctb = (p.width + S - 1) / S, hctb = (p.height + S - 1) / S, n_ctb = wctb * hctb;
   const int w4 = (p.width + 3) / 4, h4 = (p.height + 3) / 4, w8 = (p.width + 7) / 8, h8 = (p.height + 7) / 8;
+  L->params = p;
+  L->n_tu = pic->n_tu;
+  L->has_scaling = pic->scaling_factors != nullptr;
+  L->run_deblock = !(p.flags & B200_PIC_SKIP_DEBLOCK) && pic->bs_map && (p.stop_after_stage == B200_STAGE_ALL || p.stop_after_stage == B200_STAGE_DEBLOCK);
+  L->run_sao = (p.flags & B200_PIC_SAO_ENABLED) && !(p.flags & B200_PIC_SKIP_SAO) && p.stop_after_stage == B200_STAGE_ALL;
 
-  const bool run_deblock = !(p.flags & B200_PIC_SKIP_DEBLOCK) && pic->bs_map &&
-                           (p.stop_after_stage == B200_STAGE_ALL || p.stop_after_stage == B200_STAGE_DEBLOCK);
-  const bool run_sao = (p.flags & B200_PIC_SAO_ENABLED) && !(p.flags & B200_PIC_SKIP_SAO) && p.stop_after_stage == B200_STAGE_ALL;
-
-  // ---- surfaces ----
-  Surface& dst = en->slot[p.dst_slot];
-  rc = surface_ensure(dst, p);
-  if (rc) return rc;
-  Surface* cur = &dst;
-  if (run_sao) {
-    rc = surface_ensure(en->scratch, p);
-    if (rc) return rc;
-    cur = &en->scratch;
-  }
-  RefTable refs;
-  memset(&refs, 0, sizeof(refs));
-  for (int i = 0; i < B200_MAX_SLOTS; i++) {
-    const Surface& s = en->slot[i];
-    if (i != p.dst_slot && s.valid && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc && s.bd_y == p.bit_depth_luma &&
-        s.bd_c == p.bit_depth_chroma)
-      for (int c = 0; c < 3; c++) refs.plane[i][c] = s.plane[c];
-  }
-
-  // ---- host preparation: TU grouping by CTB (stable), MC tiles ----
-  // section order: 0 pus, 1 weights, 2 tus(sorted), 3 ctb_tu_start, 4 ctb_has_intra, 5 coeffs, 6 slices, 7 ctbs,
-  //                8 bs_map, 9 qp_map, 10 nofilt_map, 11 scaling, 12 tiles
   std::vector<uint32_t>& tiles = en->tiles;
   tiles.clear();
   for (uint32_t i = 0; i < pic->n_pu; i++) {
@@ -333,13 +351,15 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
         pu.x + pu.w > p.width || pu.y + pu.h > p.height)
       return set_err(B200_ERR_INVALID, "PU %u out of range", i);
     if ((pu.flags & B200_PU_WEIGHTED) && pu.wt_idx >= pic->n_weights) return set_err(B200_ERR_INVALID, "PU %u weight index", i);
+    if (pu.ref_slot[0] >= B200_MAX_SLOTS || pu.ref_slot[1] >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "PU %u reference slot", i);
     if (!(pu.flags & (B200_PU_PRED_L0 | B200_PU_PRED_L1))) continue;
     for (int ty = 0; ty * MC_TILE < pu.h; ty++)
       for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
   }
-  const int n_tiles = (int)tiles.size();
-
-  size_t sz[13], off[13];
+  L->n_tiles = (int)tiles.size();
+  // section order: 0 pus, 1 weights, 2 tus(sorted), 3 ctb_tu_start, 4 ctb_has_intra, 5 coeffs, 6 slices, 7 ctbs,
+  //                8 bs_map, 9 qp_map, 10 nofilt_map, 11 scaling, 12 tiles
+  size_t sz[13];
   sz[0] = sizeof(b200_pu) * pic->n_pu;
   sz[1] = sizeof(b200_weight_entry) * pic->n_weights;
   sz[2] = sizeof(b200_tu) * pic->n_tu;
@@ -348,41 +368,31 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
   sz[5] = sizeof(b200_coeff) * pic->n_coeff;
   sz[6] = sizeof(b200_slice_info) * pic->n_slices;
   sz[7] = sizeof(b200_ctb_info) * (size_t)n_ctb;
-  sz[8] = run_deblock ? (size_t)w4 * h4 : 0;
+  sz[8] = L->run_deblock ? (size_t)w4 * h4 : 0;
   sz[9] = (size_t)w8 * h8;
   sz[10] = (size_t)w8 * h8;
-  sz[11] = pic->scaling_factors ? B200_SCALING_FACTOR_BYTES : 0;
-  sz[12] = sizeof(uint32_t) * (size_t)n_tiles;
+  sz[11] = L->has_scaling ? B200_SCALING_FACTOR_BYTES : 0;
+  sz[12] = sizeof(uint32_t) * (size_t)L->n_tiles;
   size_t total = 0;
-  for (int i = 0; i < 13; i++) { off[i] = total; total += align_up(sz[i], 256); }
-  if (total == 0) total = 256;
+  for (int i = 0; i < 13; i++) { L->off[i] = total; total += align_up(sz[i], 256); }
+  L->total = total ? total : 256;
+  return B200_OK;
+}
 
-  StagingSet& ss = en->stage[en->cur_stage];
-  en->cur_stage ^= 1;
-  if (ss.in_flight) { CU(cudaEventSynchronize(ss.done)); ss.in_flight = false; }
-  if (ss.cap < total) {
-    if (ss.host) cudaFreeHost(ss.host);
-    if (ss.dev) cudaFree(ss.dev);
-    ss.host = nullptr; ss.dev = nullptr;
-    ss.cap = align_up(total + total / 2, 1 << 20);
-    CU(cudaMallocHost(&ss.host, ss.cap));
-    CU(cudaMalloc(&ss.dev, ss.cap));
-  }
-  if (en->sync_cap < (size_t)(1 + n_ctb)) {
-    if (en->sync_buf) cudaFree(en->sync_buf);
-    en->sync_buf = nullptr;
-    CU(cudaMalloc(&en->sync_buf, sizeof(unsigned int) * (size_t)(1 + n_ctb)));
-    en->sync_cap = (size_t)(1 + n_ctb);
-  }
-  uint8_t* hb = ss.host;
-  if (sz[0]) memcpy(hb + off[0], pic->pus, sz[0]);
-  if (sz[1]) memcpy(hb + off[1], pic->weights, sz[1]);
+static int pack_picture(b200_engine* en, const b200_picture* pic, const PicLayout& L, uint8_t* hb)
+{
+  const b200_pic_params& p = pic->params;
+  const size_t* off = L.off;
+  const int S = 1 << p.log2_ctb_size;
+  const int wctb = (p.width + S - 1) / S, hctb = (p.height + S - 1) / S, n_ctb = wctb * hctb;
+  const int w4 = (p.width + 3) / 4, h4 = (p.height + 3) / 4, w8 = (p.width + 7) / 8, h8 = (p.height + 7) / 8;
+  if (pic->n_pu) memcpy(hb + off[0], pic->pus, sizeof(b200_pu) * pic->n_pu);
+  if (pic->n_weights) memcpy(hb + off[1], pic->weights, sizeof(b200_weight_entry) * pic->n_weights);
   {
     // counting sort of TUs by CTB address, keeping decode order inside each CTB
     uint32_t* start = (uint32_t*)(hb + off[3]);
     uint8_t* has_intra = hb + off[4];
-    memset(start, 0, sz[3]);
-    memset(has_intra, 0, sz[4]);
+    memset(has_intra, 0, (size_t)n_ctb);
     std::vector<uint32_t>& cnt = en->ctb_count;
     cnt.assign((size_t)n_ctb, 0);
     for (uint32_t i = 0; i < pic->n_tu; i++) {
@@ -412,30 +422,134 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
       if (tu.flags & B200_TU_INTRA) has_intra[ctb] = 1;
     }
   }
-  if (sz[5]) memcpy(hb + off[5], pic->coeffs, sz[5]);
-  memcpy(hb + off[6], pic->slices, sz[6]);
+  if (pic->n_coeff) memcpy(hb + off[5], pic->coeffs, sizeof(b200_coeff) * pic->n_coeff);
+  memcpy(hb + off[6], pic->slices, sizeof(b200_slice_info) * pic->n_slices);
   for (int i = 0; i < n_ctb; i++)
     if (pic->ctbs[i].slice_idx >= pic->n_slices) return set_err(B200_ERR_INVALID, "CTB %d slice index", i);
-  memcpy(hb + off[7], pic->ctbs, sz[7]);
-  if (sz[8]) memcpy(hb + off[8], pic->bs_map, sz[8]);
-  memcpy(hb + off[9], pic->qp_map, sz[9]);
-  memcpy(hb + off[10], pic->nofilt_map, sz[10]);
-  if (sz[11]) memcpy(hb + off[11], pic->scaling_factors, sz[11]);
-  if (sz[12]) memcpy(hb + off[12], tiles.data(), sz[12]);
+  memcpy(hb + off[7], pic->ctbs, sizeof(b200_ctb_info) * (size_t)n_ctb);
+  if (L.run_deblock) memcpy(hb + off[8], pic->bs_map, (size_t)w4 * h4);
+  memcpy(hb + off[9], pic->qp_map, (size_t)w8 * h8);
+  memcpy(hb + off[10], pic->nofilt_map, (size_t)w8 * h8);
+  if (L.has_scaling) memcpy(hb + off[11], pic->scaling_factors, B200_SCALING_FACTOR_BYTES);
+  if (L.n_tiles) memcpy(hb + off[12], en->tiles.data(), sizeof(uint32_t) * (size_t)L.n_tiles);
+  return B200_OK;
+}
 
-  // ---- device work ----
-  cudaStream_t st = en->stream;
-  if (en->timing) CU(cudaEventRecord(en->ev[0], st));
-  CU(cudaMemcpyAsync(ss.dev, ss.host, total, cudaMemcpyHostToDevice, st));
-  const DevPic dp = make_devpic(p, *cur, dst);
-  if (p.bit_depth_luma > 8) rc = launch_picture<uint16_t>(en, pic, dp, refs, ss.dev, off, n_tiles, run_deblock, run_sao);
-  else rc = launch_picture<uint8_t>(en, pic, dp, refs, ss.dev, off, n_tiles, run_deblock, run_sao);
+static int ensure_staging(StagingSet& ss, size_t total)
+{
+  if (ss.in_flight) { CU(cudaEventSynchronize(ss.done)); ss.in_flight = false; }
+  if (ss.cap < total) {
+    if (ss.host) cudaFreeHost(ss.host);
+    if (ss.dev) cudaFree(ss.dev);
+    ss.host = nullptr; ss.dev = nullptr;
+    ss.cap = align_up(total + total / 2, 1 << 20);
+    CU(cudaMallocHost(&ss.host, ss.cap));
+    CU(cudaMalloc(&ss.dev, ss.cap));
+  }
+  return B200_OK;
+}
+
+// Everything after the records are in device memory at `dbase`.  `upload_from`: pinned source to copy first (or null).
+static int run_layout(b200_engine* en, const PicLayout& L, uint8_t* dbase, const uint8_t* upload_from)
+{
+  const b200_pic_params& p = L.params;
+  const int S = 1 << p.log2_ctb_size;
+  const int n_ctb = ((p.width + S - 1) / S) * ((p.height + S - 1) / S);
+  Surface& dst = en->slot[p.dst_slot];
+  int rc = surface_ensure(dst, p);
   if (rc) return rc;
-  if (en->timing) { CU(cudaEventRecord(en->ev[6], st)); en->have_timing = true; }
-  CU(cudaEventRecord(ss.done, st));
-  ss.in_flight = true;
+  Surface* cur = &dst;
+  if (L.run_sao) {
+    rc = surface_ensure(en->scratch, p);
+    if (rc) return rc;
+    cur = &en->scratch;
+  }
+  RefTable refs;
+  memset(&refs, 0, sizeof(refs));
+  for (int i = 0; i < B200_MAX_SLOTS; i++) {
+    const Surface& s = en->slot[i];
+    if (i != p.dst_slot && s.valid && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc && s.bd_y == p.bit_depth_luma &&
+        s.bd_c == p.bit_depth_chroma)
+      for (int c = 0; c < 3; c++) refs.plane[i][c] = s.plane[c];
+  }
+  if (en->sync_cap < (size_t)(1 + n_ctb)) {
+    if (en->sync_buf) { CU(cudaStreamSynchronize(en->stream)); cudaFree(en->sync_buf); }
+    en->sync_buf = nullptr;
+    CU(cudaMalloc(&en->sync_buf, sizeof(unsigned int) * (size_t)(1 + n_ctb)));
+    en->sync_cap = (size_t)(1 + n_ctb);
+  }
+  cudaStream_t st = en->stream;
+  en->ev = en->timing ? &en->tev[(size_t)(en->tcount % TIMING_RING) * 7] : nullptr;
+  if (en->timing) CU(cudaEventRecord(en->ev[0], st));
+  if (upload_from) CU(cudaMemcpyAsync(dbase, upload_from, L.total, cudaMemcpyHostToDevice, st));
+  const DevPic dp = make_devpic(p, *cur, dst);
+  if (p.bit_depth_luma > 8) rc = launch_picture<uint16_t>(en, L, dp, refs, dbase);
+  else rc = launch_picture<uint8_t>(en, L, dp, refs, dbase);
+  if (rc) return rc;
+  if (en->timing) { CU(cudaEventRecord(en->ev[6], st)); en->tcount++; }
   dst.valid = true;
   return B200_OK;
+}
+
+extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* pic)
+{
+  if (!en || !pic) return set_err(B200_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(en->device));
+  PicLayout L;
+  int rc = plan_picture(en, pic, &L);
+  if (rc) return rc;
+  StagingSet& ss = en->stage[en->cur_stage];
+  en->cur_stage ^= 1;
+  rc = ensure_staging(ss, L.total);
+  if (rc) return rc;
+  rc = pack_picture(en, pic, L, ss.host);
+  if (rc) return rc;
+  rc = run_layout(en, L, ss.dev, ss.host);
+  if (rc) return rc;
+  CU(cudaEventRecord(ss.done, en->stream));
+  ss.in_flight = true;
+  return B200_OK;
+}
+
+extern "C" int b200_engine_prepare_picture(b200_engine* en, const b200_picture* pic, b200_prepared** out)
+{
+  if (!en || !pic || !out) return set_err(B200_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(en->device));
+  b200_prepared* pp = new (std::nothrow) b200_prepared();
+  if (!pp) return set_err(B200_ERR_NOMEM, "out of memory");
+  int rc = plan_picture(en, pic, &pp->L);
+  if (rc) { delete pp; return rc; }
+  StagingSet& ss = en->stage[en->cur_stage];
+  en->cur_stage ^= 1;
+  rc = ensure_staging(ss, pp->L.total);
+  if (!rc) rc = pack_picture(en, pic, pp->L, ss.host);
+  if (rc) { delete pp; return rc; }
+  cudaError_t e = cudaMalloc(&pp->dev, pp->L.total);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pp->dev, ss.host, pp->L.total, cudaMemcpyHostToDevice, en->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(en->stream);
+  if (e != cudaSuccess) {
+    if (pp->dev) cudaFree(pp->dev);
+    delete pp;
+    return set_err(B200_ERR_CUDA, "prepare: %s", cudaGetErrorString(e));
+  }
+  *out = pp;
+  return B200_OK;
+}
+
+extern "C" int b200_engine_run_prepared(b200_engine* en, b200_prepared* pp)
+{
+  if (!en || !pp) return set_err(B200_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(en->device));
+  return run_layout(en, pp->L, pp->dev, nullptr);
+}
+
+extern "C" void b200_engine_free_prepared(b200_engine* en, b200_prepared* pp)
+{
+  if (!en || !pp) return;
+  cudaSetDevice(en->device);
+  cudaStreamSynchronize(en->stream);
+  if (pp->dev) cudaFree(pp->dev);
+  delete pp;
 }
 
 extern "C" int b200_engine_sync(b200_engine* en)

@@ -67,6 +67,24 @@ class Engine:
         capi.check(self.lib.b200_engine_last_timing(self._h, C.byref(ms)), "b200_engine_last_timing")
         return dict(zip(("h2d", "inter_pred", "recon", "deblock", "sao", "total"), list(ms)))
 
+    def timing_sum(self, reset=True):
+        ms = (C.c_float * 6)()
+        n = C.c_int(0)
+        capi.check(self.lib.b200_engine_timing_sum(self._h, C.byref(ms), C.byref(n), int(reset)), "b200_engine_timing_sum")
+        return dict(zip(("h2d", "inter_pred", "recon", "deblock", "sao", "total"), list(ms))), n.value
+
+    def prepare(self, pic):
+        cp = getattr(pic, "c", pic)
+        h = C.c_void_p()
+        capi.check(self.lib.b200_engine_prepare_picture(self._h, C.byref(cp), C.byref(h)), "b200_engine_prepare_picture")
+        return h
+
+    def run_prepared(self, h):
+        capi.check(self.lib.b200_engine_run_prepared(self._h, h), "b200_engine_run_prepared")
+
+    def free_prepared(self, h):
+        self.lib.b200_engine_free_prepared(self._h, h)
+
     def launch_count(self):
         return int(self.lib.b200_engine_launch_count(self._h))
 

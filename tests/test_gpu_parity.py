@@ -1,0 +1,192 @@
+"""GPU parity tests (-m gpu): the CUDA engine, called through the C ABI, against the CPU oracle and the
+committed golden fixtures.  Bit-exact (integer pixel pipeline): every comparison is array equality."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from libde265_b200 import capi, de265, synth
+from libde265_b200.engine import Engine
+import oracle_lib
+from test_cpu_oracle import GOLDEN, GOLDEN_MD5, load_records
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(0)  # raises (never skips) when the CUDA library or device is missing
+    yield e
+    e.close()
+
+
+def md5_planes(planes):
+    return hashlib.md5(b"".join(p.tobytes() for p in planes)).hexdigest()
+
+
+def assert_same(g, o, tag=""):
+    for c, (a, b) in enumerate(zip(g, o)):
+        if not (a == b).all():
+            d = np.argwhere(a != b)
+            raise AssertionError(f"{tag} plane {c}: {len(d)} samples differ, first at (x={d[0][1]}, y={d[0][0]}): gpu {a[tuple(d[0])]} != oracle {b[tuple(d[0])]}")
+
+
+# ---- golden vector: the reference's own known-answer stream ------------------------------------------
+def test_girlshy_golden_records_bit_exact(b200lib, eng):
+    exp = json.load(open(os.path.join(GOLDEN, "girlshy_expected.json")))
+    pics, keep = load_records(b200lib)
+    for i, pic in enumerate(pics):
+        eng.submit(pic)
+        assert md5_planes(eng.read_slot(pic.params.dst_slot, pic.params)) == exp["decode_order_plane_md5"][i], f"picture {i}"
+
+
+@pytest.mark.skipif(oracle_lib.ref_path("libde265_hooked.so") is None, reason="oracle/_ref not shipped")
+def test_girlshy_end_to_end_through_libde265_api(b200lib):
+    """de265.h API -> reference parser (B2 hook sites) -> B200 engine -> decoded pictures; md5 of the dec265-style
+    output must equal the reference's golden md5 (scripts/ci-run.sh:91-92)."""
+    eng = Engine(0)
+    dec = de265.Decoder(oracle_lib.ref_path("libde265_hooked.so"))
+
+    def sink(pic, planes, strides):
+        eng.submit(pic)
+        eng.read_slot_into(pic.params.dst_slot, [planes[0], planes[1], planes[2]], [strides[0], strides[1], strides[2]])
+        return 0
+
+    dec.attach(sink)
+    md = hashlib.md5()
+    n = dec.decode_stream(open(os.path.join(GOLDEN, "girlshy.h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
+    dec.close()
+    assert n == 75 and md.hexdigest() == GOLDEN_MD5
+    assert eng.launch_count() > 75 * 4
+    eng.close()
+
+
+# ---- synthetic pictures vs the oracle -----------------------------------------------------------------
+def run_sequence(eng, orc, W, H, bd, log2_ctb=6, stages=False, **kw):
+    ref = synth.random_planes(W, H, bd, 99)
+    pics = [synth.make_picture(W, H, "I", seed=11, dst_slot=0, bit_depth=bd, log2_ctb=log2_ctb, **kw)]
+    eng.upload_slot(5, pics[0].params, ref)
+    orc.upload_slot(5, pics[0].params, ref)
+    pics.append(synth.make_picture(W, H, "P", seed=12, dst_slot=1, ref_slots=(0, 5), bit_depth=bd, log2_ctb=log2_ctb, **kw))
+    pics.append(synth.make_picture(W, H, "B", seed=13, dst_slot=2, ref_slots=(0, 1, 5), bit_depth=bd, log2_ctb=log2_ctb, **kw))
+    pics.append(synth.make_picture(W, H, "B", seed=14, dst_slot=3, ref_slots=(0, 1, 2), weighted=True, bit_depth=bd, log2_ctb=log2_ctb, **kw))
+    for i, p in enumerate(pics):
+        for st in ((capi.STAGE_INTER_PRED, capi.STAGE_RECON, capi.STAGE_DEBLOCK, capi.STAGE_ALL) if stages else (capi.STAGE_ALL,)):
+            p.c.params.stop_after_stage = st
+            eng.submit(p)
+            orc.reconstruct(p)
+            assert_same(eng.read_slot(p.params.dst_slot, p.params), orc.read_slot(p.params.dst_slot, p.params), f"pic {i} stage {st}")
+        p.c.params.stop_after_stage = 0
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_synthetic_sequence_every_stage(eng, oracle_mod, bd):
+    orc = oracle_mod.Oracle()
+    run_sequence(eng, orc, 416, 240, bd, stages=True)
+    orc.close()
+
+
+@pytest.mark.parametrize("size", [(8, 8), (16, 8), (72, 40), (64, 64), (200, 136), (1288, 8)])
+def test_ragged_and_tiny_pictures(eng, oracle_mod, size):
+    """Pictures that are not a multiple of the CTB size, down to a single minimum CB."""
+    orc = oracle_mod.Oracle()
+    run_sequence(eng, orc, size[0], size[1], 8)
+    orc.close()
+
+
+@pytest.mark.parametrize("log2_ctb", [4, 5])
+def test_small_ctb_sizes(eng, oracle_mod, log2_ctb):
+    orc = oracle_mod.Oracle()
+    run_sequence(eng, orc, 208, 120, 8, log2_ctb=log2_ctb, size_area=(0.0, 0.3 if log2_ctb == 5 else 0.0, 0.4, 0.3))
+    orc.close()
+
+
+def test_multi_slice_scaling_list_no_filters(eng, oracle_mod):
+    orc = oracle_mod.Oracle()
+    run_sequence(eng, orc, 320, 192, 8, n_slices=4, scaling_list=True)
+    run_sequence(eng, orc, 320, 192, 10, deblock=False, sao=False)
+    run_sequence(eng, orc, 320, 192, 8, special_frac=0.15, cbf_prob=0.9)  # many PCM / bypass / transform-skip blocks
+    orc.close()
+
+
+def test_1080p_intra_and_4k_b_frame(eng, oracle_mod):
+    """BASELINE configs 2 and 3 at full size against the oracle (one picture each; the oracle needs a few seconds)."""
+    orc = oracle_mod.Oracle()
+    p = synth.make_picture(1920, 1080, "I", seed=21, dst_slot=0)
+    eng.submit(p)
+    orc.reconstruct(p)
+    assert_same(eng.read_slot(0, p.params), orc.read_slot(0, p.params), "1080p intra")
+    W, H = 3840, 2160
+    refs = [synth.random_planes(W, H, 8, s) for s in (1, 2)]
+    b = synth.make_picture(W, H, "B", seed=22, dst_slot=2, ref_slots=(0, 1))
+    for s, r in enumerate(refs):
+        eng.upload_slot(s, b.params, r)
+        orc.upload_slot(s, b.params, r)
+    eng.submit(b)
+    orc.reconstruct(b)
+    assert_same(eng.read_slot(2, b.params), orc.read_slot(2, b.params), "4K B")
+    orc.close()
+
+
+def test_4k_main10_determinism_and_prepared_path(eng):
+    """Size-independent properties at BASELINE config 4's full size: replaying the same records gives identical
+    pictures (idempotence), and the prepared (HBM-resident) path equals the submit path."""
+    W, H = 3840, 2160
+    refs = [synth.random_planes(W, H, 10, s) for s in (3, 4)]
+    b = synth.make_picture(W, H, "B", seed=23, dst_slot=2, ref_slots=(0, 1), bit_depth=10)
+    for s, r in enumerate(refs):
+        eng.upload_slot(s, b.params, r)
+    eng.submit(b)
+    first = md5_planes(eng.read_slot(2, b.params))
+    eng.submit(b)
+    assert md5_planes(eng.read_slot(2, b.params)) == first
+    h = eng.prepare(b)
+    eng.fill_slot(2, b.params, 0, 0)
+    eng.run_prepared(h)
+    assert md5_planes(eng.read_slot(2, b.params)) == first
+    eng.free_prepared(h)
+
+
+def test_missing_reference_and_fill_slot(eng, oracle_mod):
+    orc = oracle_mod.Oracle()
+    W, H = 128, 64
+    p = synth.make_picture(W, H, "B", seed=31, dst_slot=3, ref_slots=(7, 9))  # slot 9 never written -> mid-grey prediction
+    eng2 = Engine(0)
+    eng2.fill_slot(7, p.params, 77, 200)
+    orc.fill_slot(7, p.params, 77, 200)
+    eng2.submit(p)
+    orc.reconstruct(p)
+    assert_same(eng2.read_slot(3, p.params), orc.read_slot(3, p.params), "missing ref")
+    eng2.close()
+    orc.close()
+
+
+def test_malformed_records_are_rejected(eng):
+    p = synth.make_picture(64, 64, "P", seed=41, dst_slot=1, ref_slots=(0,))
+    p.pus["x"][0] = 62  # not on the 4-sample grid / outside
+    with pytest.raises(capi.B200Error):
+        eng.submit(p)
+    q = synth.make_picture(64, 64, "I", seed=42, dst_slot=1)
+    q.tus["coeff_off"][-1] = 10 ** 7
+    with pytest.raises(capi.B200Error):
+        eng.submit(q)
+    r = synth.make_picture(64, 64, "I", seed=43, dst_slot=1)
+    r.c.params.chroma_format_idc = 3
+    with pytest.raises(capi.B200Error):
+        eng.submit(r)
+
+
+def test_empty_picture(eng, oracle_mod):
+    """No PUs and no TUs: every stage must cope with empty work lists."""
+    orc = oracle_mod.Oracle()
+    p = synth.make_picture(64, 64, "I", seed=44, dst_slot=1)
+    e = synth.SynthPicture(p.params, p.pus[:0], p.weights, p.tus[:0], p.coeffs[:0], p.slices, p.ctbs, p.bs_map, p.qp_map, p.nofilt_map)
+    eng.fill_slot(1, p.params, 50, 60)
+    orc.fill_slot(1, p.params, 50, 60)
+    eng.submit(e)
+    orc.reconstruct(e)
+    assert_same(eng.read_slot(1, p.params), orc.read_slot(1, p.params), "empty")
+    orc.close()

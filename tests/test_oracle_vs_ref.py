@@ -75,9 +75,13 @@ def test_idct_add(ref, orc, log2, bd):
         if bd == 8:
             r = base.astype(np.uint8)
             ref.ref_transform_add_8(0, log2, P(r, u8p), P(co, i16p), C.c_ssize_t(stride))
-            s = base.astype(np.uint8)
-            ref.ref_transform_add_8(1, log2, P(s, u8p), P(co, i16p), C.c_ssize_t(stride))
-            assert (s == r).all()  # the reference's own SIMD-vs-scalar check
+            # the reference's own SIMD-vs-scalar check; the SIMD kernels need 16-byte aligned rows (as in the decoder)
+            raw = np.zeros(nT * 64 + 64, np.uint8)
+            a0 = (-raw.ctypes.data) % 64
+            s = raw[a0:a0 + nT * 64].reshape(nT, 64)
+            s[:, :nT] = base[:, :nT]
+            ref.ref_transform_add_8(1, log2, P(s, u8p), P(co, i16p), C.c_ssize_t(64))
+            assert (s[:, :nT] == r[:, :nT]).all()
         else:
             r = base.astype(np.uint16)
             ref.ref_transform_add_16(0, log2, P(r, u16p), P(co, i16p), C.c_ssize_t(stride), bd)
