@@ -9,6 +9,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -100,22 +101,23 @@ struct b200_engine {
   Surface scratch;
   StagingSet stage[2];
   int cur_stage = 0;
-  unsigned int* sync_buf = nullptr;  // [1 + n_ctb] ticket + done flags
+  uint8_t* sync_buf = nullptr;  // [256 B ticket | pending map Y | Cb | Cr]
   size_t sync_cap = 0;
+  int num_sms = 148;
   bool timing = false;
   std::vector<cudaEvent_t> tev;  // timing ring: TIMING_RING pictures x 7 events
   unsigned tcount = 0;           // pictures recorded since enable / reset
   cudaEvent_t* ev = nullptr;     // events of the picture being submitted
   uint64_t launches = 0;
   // host scratch reused across pictures
-  std::vector<uint32_t> ctb_count, tiles;
+  std::vector<uint32_t> ctb_count, tiles, list_a, list_b, diag_count, task_of, task_first, task_start, task_order;
 };
 
 #define TIMING_RING 256
 
 struct PicLayout {
-  size_t off[13] = {}, total = 0;
-  int n_tiles = 0;
+  size_t off[14] = {}, total = 0;
+  int n_tiles = 0, n_a = 0, n_b = 0, n_task = 0;
   bool run_deblock = false, run_sao = false, has_scaling = false;
   b200_pic_params params{};
   uint32_t n_tu = 0;
@@ -164,8 +166,11 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   if (rc) { delete en; return rc; }
   CU(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&en->stage[i].done, cudaEventDisableTiming));
-  CU(cudaFuncSetAttribute(k_recon<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint8_t>)));
-  CU(cudaFuncSetAttribute(k_recon<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint16_t>)));
+  CU(cudaFuncSetAttribute(k_residual<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint8_t>)));
+  CU(cudaFuncSetAttribute(k_residual<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint16_t>)));
+  CU(cudaFuncSetAttribute(k_intra<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint8_t>)));
+  CU(cudaFuncSetAttribute(k_intra<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint16_t>)));
+  CU(cudaDeviceGetAttribute(&en->num_sms, cudaDevAttrMultiProcessorCount, device));
   *out = en;
   return B200_OK;
 }
@@ -277,7 +282,6 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
   const size_t* off = L.off;
   const int n_tiles = L.n_tiles;
   const bool run_deblock = L.run_deblock, run_sao = L.run_sao;
-  const int n_ctb = dp.wctb * dp.hctb;
   if (en->timing) CU(cudaEventRecord(en->ev[1], st));
   if (n_tiles > 0) {
     k_inter_pred<P><<<(n_tiles + 3) / 4, 128, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
@@ -285,18 +289,57 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
     en->launches++;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[2], st));
-  if (L.n_tu > 0 && L.params.stop_after_stage != B200_STAGE_INTER_PRED) {
+  if ((L.n_a > 0 || L.n_b > 0) && L.params.stop_after_stage != B200_STAGE_INTER_PRED) {
     ReconArgs ra;
     ra.tus = (const b200_tu*)(dbase + off[2]);
-    ra.ctb_tu_start = (const uint32_t*)(dbase + off[3]);
-    ra.ctb_has_intra = dbase + off[4];
     ra.coeffs = (const b200_coeff*)(dbase + off[5]);
     ra.scaling = L.has_scaling ? dbase + off[11] : nullptr;
-    ra.ticket = en->sync_buf;
-    ra.ctb_done = en->sync_buf + 1;
-    CU(cudaMemsetAsync(en->sync_buf, 0, sizeof(unsigned int) * (size_t)(1 + n_ctb), st));
-    k_recon<P><<<n_ctb, RC_THREADS, sizeof(ReconSmem<P>), st>>>(dp, ra);
-    en->launches++;
+    ra.ticket = (unsigned int*)en->sync_buf;
+    const size_t cw4 = (size_t)((dp.cw + 3) / 4), ch4 = (size_t)((dp.ch + 3) / 4);
+    ra.pend[0] = en->sync_buf + 256;
+    ra.pend[1] = ra.pend[0] + (size_t)dp.w4 * dp.h4;
+    ra.pend[2] = ra.pend[1] + cw4 * ch4;
+    ra.pend_w[0] = dp.w4;
+    ra.pend_w[1] = ra.pend_w[2] = (int)cw4;
+    if (L.n_a > 0) {
+      ra.list = (const uint32_t*)(dbase + off[3]);
+      ra.n_list = L.n_a;
+      k_residual<P><<<(L.n_a + RC_WARPS - 1) / RC_WARPS, RC_THREADS, sizeof(ReconSmem<P>), st>>>(dp, ra);
+      en->launches++;
+    }
+    ra.trace = nullptr;
+    if (L.n_b > 0) {
+      unsigned long long* trace_dev = nullptr;
+      const char* trace_path = getenv("B200_TRACE_INTRA");  // debug: per-task timing trace of k_intra appended to this file
+      if (trace_path && L.n_task > 0) {
+        CU(cudaMalloc(&trace_dev, sizeof(unsigned long long) * 4 * (size_t)L.n_task));
+        CU(cudaMemsetAsync(trace_dev, 0, sizeof(unsigned long long) * 4 * (size_t)L.n_task, st));
+        ra.trace = trace_dev;
+      }
+      ra.list = (const uint32_t*)(dbase + off[4]);
+      ra.n_list = L.n_b;
+      CU(cudaMemsetAsync(en->sync_buf, 0, 256 + (size_t)dp.w4 * dp.h4 + 2 * cw4 * ch4, st));
+      k_mark_pending<<<(L.n_b + 255) / 256, 256, 0, st>>>(ra);
+      ra.task_start = (const uint32_t*)(dbase + off[13]);
+      ra.n_task = L.n_task;
+      int grid = (L.n_task + RC_WARPS - 1) / RC_WARPS;
+      const int cap = en->num_sms * 3;
+      if (grid > cap) grid = cap;
+      k_intra<P><<<grid, RC_THREADS, sizeof(ReconSmem<P>), st>>>(dp, ra);
+      en->launches += 2;
+      if (trace_dev) {
+        std::vector<unsigned long long> h(4 * (size_t)L.n_task);
+        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(trace_dev);
+        if (FILE* f = fopen(trace_path, "ab")) {
+          const unsigned long long n = (unsigned long long)L.n_task;
+          fwrite(&n, sizeof(n), 1, f);
+          fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+          fclose(f);
+        }
+      }
+    }
   }
   if (en->timing) CU(cudaEventRecord(en->ev[3], st));
   FilterArgs fa;
@@ -357,14 +400,96 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
       for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
   }
   L->n_tiles = (int)tiles.size();
-  // section order: 0 pus, 1 weights, 2 tus(sorted), 3 ctb_tu_start, 4 ctb_has_intra, 5 coeffs, 6 slices, 7 ctbs,
+  // ---- TU validation + work lists: list_a = non-intra TUs with work, list_b = intra TUs in topological order
+  //      (CTB anti-diagonal x + 2y, then CTB raster, then decode order) ----
+  {
+    std::vector<uint32_t>& la = en->list_a;
+    std::vector<uint32_t>& lb = en->list_b;
+    std::vector<uint32_t>& dc = en->diag_count;
+    la.clear();
+    const int n_diag = wctb + 2 * hctb;
+    dc.assign((size_t)n_diag + 1, 0);
+    uint32_t n_intra = 0;
+    for (uint32_t i = 0; i < pic->n_tu; i++) {
+      const b200_tu& tu = pic->tus[i];
+      const int sh = tu.cidx ? 1 : 0;
+      const int nT = 1 << tu.log2_size;
+      const int pw = tu.cidx ? p.width / 2 : p.width, ph = tu.cidx ? p.height / 2 : p.height;
+      if (tu.log2_size < 2 || tu.log2_size > 5 || tu.cidx > 2 || (tu.cidx && !p.chroma_format_idc) || tu.x + nT > pw || tu.y + nT > ph ||
+          (tu.x & 3) || (tu.y & 3) || (tu.x & (nT - 1)) || (tu.y & (nT - 1)))
+        return set_err(B200_ERR_INVALID, "TU %u out of range", i);
+      if ((size_t)tu.coeff_off + tu.n_coeff > pic->n_coeff || tu.n_coeff > nT * nT) return set_err(B200_ERR_INVALID, "TU %u coefficient range", i);
+      if ((tu.flags & B200_TU_PCM) && tu.n_coeff != nT * nT) return set_err(B200_ERR_INVALID, "PCM TU %u sample count", i);
+      if (tu.flags & B200_TU_INTRA) {
+        if (tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
+        n_intra++;
+      } else if (tu.flags & (B200_TU_CBF | B200_TU_PCM)) {
+        la.push_back(i);
+      }
+    }
+    // ---- intra tasks: the TUs of one plane inside one aligned 16x16-luma / 8x8-chroma region (contiguous per plane in
+    //      decode order); a TU at least as large as the region is a task of its own ----
+    std::vector<uint32_t>& task_of = en->task_of;        // per intra TU (in decode order): task id
+    std::vector<uint32_t>& task_first = en->task_first;  // per task: TU index of its first TU
+    task_of.clear();
+    task_first.clear();
+    {
+      long long cur_key[3] = {-1, -1, -1};
+      uint32_t cur_task[3] = {0, 0, 0};
+      for (uint32_t i = 0; i < pic->n_tu; i++) {
+        const b200_tu& tu = pic->tus[i];
+        if (!(tu.flags & B200_TU_INTRA)) continue;
+        const int c = tu.cidx, G = 16 >> (c ? 1 : 0), nT = 1 << tu.log2_size;
+        long long key = (nT >= G) ? -2 - (long long)i : (((long long)(tu.y / G)) << 20) | (tu.x / G);
+        if (key != cur_key[c]) {
+          cur_key[c] = key;
+          cur_task[c] = (uint32_t)task_first.size();
+          task_first.push_back(i);
+        }
+        task_of.push_back(cur_task[c]);
+      }
+    }
+    const uint32_t n_task = (uint32_t)task_first.size();
+    // topological order of tasks: CTB anti-diagonal x + 2y, ties in decode order of the first TU
+    dc.assign((size_t)n_diag + 1, 0);
+    auto diag_of = [&](uint32_t tu_idx) {
+      const b200_tu& tu = pic->tus[tu_idx];
+      const int sh = tu.cidx ? 1 : 0;
+      return (size_t)((tu.x << sh) >> p.log2_ctb_size) + 2 * (size_t)((tu.y << sh) >> p.log2_ctb_size);
+    };
+    for (uint32_t t = 0; t < n_task; t++) dc[diag_of(task_first[t]) + 1]++;
+    for (int d = 0; d < n_diag; d++) dc[d + 1] += dc[d];
+    std::vector<uint32_t>& order = en->task_order;  // rank of each task in the topological order
+    order.resize(n_task);
+    for (uint32_t t = 0; t < n_task; t++) order[t] = dc[diag_of(task_first[t])]++;
+    // task sizes -> start offsets in topological order
+    std::vector<uint32_t>& ts = en->task_start;
+    ts.assign((size_t)n_task + 1, 0);
+    for (uint32_t k = 0; k < n_intra; k++) ts[order[task_of[k]] + 1]++;
+    for (uint32_t t = 0; t < n_task; t++) ts[t + 1] += ts[t];
+    lb.resize(n_intra);
+    {
+      std::vector<uint32_t>& fill = en->ctb_count;  // reuse as per-task fill cursor
+      fill.assign(ts.begin(), ts.end() - 1);
+      uint32_t k = 0;
+      for (uint32_t i = 0; i < pic->n_tu; i++) {
+        if (!(pic->tus[i].flags & B200_TU_INTRA)) continue;
+        lb[fill[order[task_of[k]]]++] = i;
+        k++;
+      }
+    }
+    L->n_task = (int)n_task;
+    L->n_a = (int)la.size();
+    L->n_b = (int)lb.size();
+  }
+  // section order: 0 pus, 1 weights, 2 tus, 3 list_a (non-intra TU indices), 4 list_b (intra TU indices), 5 coeffs, 6 slices, 7 ctbs,
   //                8 bs_map, 9 qp_map, 10 nofilt_map, 11 scaling, 12 tiles
-  size_t sz[13];
+  size_t sz[14];
   sz[0] = sizeof(b200_pu) * pic->n_pu;
   sz[1] = sizeof(b200_weight_entry) * pic->n_weights;
   sz[2] = sizeof(b200_tu) * pic->n_tu;
-  sz[3] = sizeof(uint32_t) * (size_t)(n_ctb + 1);
-  sz[4] = (size_t)n_ctb;
+  sz[3] = sizeof(uint32_t) * (size_t)L->n_a;
+  sz[4] = sizeof(uint32_t) * (size_t)L->n_b;
   sz[5] = sizeof(b200_coeff) * pic->n_coeff;
   sz[6] = sizeof(b200_slice_info) * pic->n_slices;
   sz[7] = sizeof(b200_ctb_info) * (size_t)n_ctb;
@@ -373,8 +498,9 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
   sz[10] = (size_t)w8 * h8;
   sz[11] = L->has_scaling ? B200_SCALING_FACTOR_BYTES : 0;
   sz[12] = sizeof(uint32_t) * (size_t)L->n_tiles;
+  sz[13] = L->n_task ? sizeof(uint32_t) * (size_t)(L->n_task + 1) : 0;
   size_t total = 0;
-  for (int i = 0; i < 13; i++) { L->off[i] = total; total += align_up(sz[i], 256); }
+  for (int i = 0; i < 14; i++) { L->off[i] = total; total += align_up(sz[i], 256); }
   L->total = total ? total : 256;
   return B200_OK;
 }
@@ -388,40 +514,10 @@ static int pack_picture(b200_engine* en, const b200_picture* pic, const PicLayou
   const int w4 = (p.width + 3) / 4, h4 = (p.height + 3) / 4, w8 = (p.width + 7) / 8, h8 = (p.height + 7) / 8;
   if (pic->n_pu) memcpy(hb + off[0], pic->pus, sizeof(b200_pu) * pic->n_pu);
   if (pic->n_weights) memcpy(hb + off[1], pic->weights, sizeof(b200_weight_entry) * pic->n_weights);
-  {
-    // counting sort of TUs by CTB address, keeping decode order inside each CTB
-    uint32_t* start = (uint32_t*)(hb + off[3]);
-    uint8_t* has_intra = hb + off[4];
-    memset(has_intra, 0, (size_t)n_ctb);
-    std::vector<uint32_t>& cnt = en->ctb_count;
-    cnt.assign((size_t)n_ctb, 0);
-    for (uint32_t i = 0; i < pic->n_tu; i++) {
-      const b200_tu& tu = pic->tus[i];
-      const int sh = tu.cidx ? 1 : 0;
-      const int nT = 1 << tu.log2_size;
-      const int pw = tu.cidx ? p.width / 2 : p.width, ph = tu.cidx ? p.height / 2 : p.height;
-      if (tu.log2_size < 2 || tu.log2_size > 5 || tu.cidx > 2 || (tu.cidx && !p.chroma_format_idc) || tu.x + nT > pw || tu.y + nT > ph ||
-          (tu.x & 3) || (tu.y & 3))
-        return set_err(B200_ERR_INVALID, "TU %u out of range", i);
-      if ((size_t)tu.coeff_off + tu.n_coeff > pic->n_coeff || tu.n_coeff > nT * nT) return set_err(B200_ERR_INVALID, "TU %u coefficient range", i);
-      if ((tu.flags & B200_TU_INTRA) && tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
-      const int cx = (tu.x << sh) >> p.log2_ctb_size, cy = (tu.y << sh) >> p.log2_ctb_size;
-      if ((((tu.x + nT - 1) << sh) >> p.log2_ctb_size) != cx || (((tu.y + nT - 1) << sh) >> p.log2_ctb_size) != cy)
-        return set_err(B200_ERR_INVALID, "TU %u crosses a CTB boundary", i);
-      cnt[(size_t)cx + (size_t)cy * wctb]++;
-    }
-    uint32_t acc = 0;
-    for (int i = 0; i < n_ctb; i++) { start[i] = acc; acc += cnt[i]; cnt[i] = start[i]; }
-    start[n_ctb] = acc;
-    b200_tu* sorted = (b200_tu*)(hb + off[2]);
-    for (uint32_t i = 0; i < pic->n_tu; i++) {
-      const b200_tu& tu = pic->tus[i];
-      const int sh = tu.cidx ? 1 : 0;
-      const size_t ctb = (size_t)((tu.x << sh) >> p.log2_ctb_size) + (size_t)((tu.y << sh) >> p.log2_ctb_size) * wctb;
-      sorted[cnt[ctb]++] = tu;
-      if (tu.flags & B200_TU_INTRA) has_intra[ctb] = 1;
-    }
-  }
+  if (pic->n_tu) memcpy(hb + off[2], pic->tus, sizeof(b200_tu) * pic->n_tu);
+  if (L.n_a) memcpy(hb + off[3], en->list_a.data(), sizeof(uint32_t) * (size_t)L.n_a);
+  if (L.n_b) memcpy(hb + off[4], en->list_b.data(), sizeof(uint32_t) * (size_t)L.n_b);
+  if (L.n_task) memcpy(hb + off[13], en->task_start.data(), sizeof(uint32_t) * (size_t)(L.n_task + 1));
   if (pic->n_coeff) memcpy(hb + off[5], pic->coeffs, sizeof(b200_coeff) * pic->n_coeff);
   memcpy(hb + off[6], pic->slices, sizeof(b200_slice_info) * pic->n_slices);
   for (int i = 0; i < n_ctb; i++)
@@ -472,11 +568,15 @@ static int run_layout(b200_engine* en, const PicLayout& L, uint8_t* dbase, const
         s.bd_c == p.bit_depth_chroma)
       for (int c = 0; c < 3; c++) refs.plane[i][c] = s.plane[c];
   }
-  if (en->sync_cap < (size_t)(1 + n_ctb)) {
-    if (en->sync_buf) { CU(cudaStreamSynchronize(en->stream)); cudaFree(en->sync_buf); }
-    en->sync_buf = nullptr;
-    CU(cudaMalloc(&en->sync_buf, sizeof(unsigned int) * (size_t)(1 + n_ctb)));
-    en->sync_cap = (size_t)(1 + n_ctb);
+  {
+    const size_t cw4 = p.chroma_format_idc ? (size_t)((p.width / 2 + 3) / 4) : 0, ch4 = p.chroma_format_idc ? (size_t)((p.height / 2 + 3) / 4) : 0;
+    const size_t need = 256 + (size_t)((p.width + 3) / 4) * ((p.height + 3) / 4) + 2 * cw4 * ch4;
+    if (en->sync_cap < need) {
+      if (en->sync_buf) { CU(cudaStreamSynchronize(en->stream)); cudaFree(en->sync_buf); }
+      en->sync_buf = nullptr;
+      CU(cudaMalloc(&en->sync_buf, need));
+      en->sync_cap = need;
+    }
   }
   cudaStream_t st = en->stream;
   en->ev = en->timing ? &en->tev[(size_t)(en->tcount % TIMING_RING) * 7] : nullptr;

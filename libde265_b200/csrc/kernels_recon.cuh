@@ -1,16 +1,17 @@
 // kernels_recon.cuh — intra prediction + residual (dequant, inverse DCT/DST, transform-skip, bypass,
-// PCM) for one picture in ONE launch.
+// PCM) for one picture in three launches, one WARP per transform unit.
 //
-// One CTA per CTB.  The CTB's samples (the inter prediction written by k_inter_pred, or nothing yet
-// for intra CUs) plus the neighbouring reconstructed row/column are staged in shared memory, every TU
-// of the CTB is reconstructed there, and the finished CTB is written back with 16-byte row stores.
-//   phase A  all TUs that are not intra (inter residual, PCM): independent -> spread over all warps
-//   phase B  intra TUs: serially dependent inside a colour plane, independent between
-//            planes -> warp c walks plane c's TUs in decode order
-// CTBs that contain intra TUs wait (acquire-spin on a per-CTB flag) until their left, top-left, top
-// and top-right neighbours are finished — the WPP dependency (slice.cc:4789-4795); CTBs are handed
-// out in raster order through an atomic ticket so a waiting CTA only ever waits for CTBs that are
-// already running or done.
+//   k_residual<P>   every TU of a non-intra CU that carries work (inter residual, PCM): no dependencies,
+//                   fully parallel.  Runs after k_inter_pred (it adds onto the prediction).
+//   k_mark_pending  flags the 4x4 units covered by intra TUs as "pending" in a per-plane map.
+//   k_intra<P>      every intra TU: border gather + substitution + smoothing, DC/planar/angular prediction,
+//                   then the TU's residual.  Intra TUs are serially dependent through their neighbours
+//                   (SURVEY §3.2), so the kernel executes the dependency DAG directly: warps claim TUs through
+//                   an atomic ticket in a topological order (CTB anti-diagonal x + 2y, then decode order), poll
+//                   the pending flags of exactly the neighbour units their availability mask says they read,
+//                   reconstruct, write the TU, fence, and clear their own flags.  The lowest unfinished ticket
+//                   never waits on a later one, so the launch cannot deadlock.  Colour planes are independent
+//                   chains.  This gives TU-granular wavefront parallelism instead of one CTB per step.
 //
 // Replaces decode_TU (slice.cc:3460), decode_intra_prediction (intrapred.cc:277-345) incl. border
 // fetch/substitution/smoothing (intrapred.h:185-258,529-674), scale_coefficients (transform.cc:361-642)
@@ -20,32 +21,34 @@
 
 #define RC_WARPS 8
 #define RC_THREADS (RC_WARPS * 32)
-#define RC_LSTRIDE 128  // luma tile row stride (samples): x = -16 .. 111
-#define RC_CSTRIDE 64   // chroma tile row stride: x = -16 .. 47
-#define RC_XOFF 16
-#define RC_LROWS 65
-#define RC_CROWS 33
-#define RC_GSTRIDE 34   // int16 row stride of the first-stage buffer (conflict-free for 32 lanes)
+#define RC_GSTRIDE 34   // int16 row stride of the first-stage buffer
+#define RC_TILE_STRIDE 40  // region tile: rows -1..2G-1 (only column -1 below row G-1), columns -1..2G-1 (G <= 16)
+#define RC_BLK (33 * RC_TILE_STRIDE + 8)
+#define RC_CO_STAGE 256
 
 struct ReconArgs {
-  const b200_tu* tus;            // grouped by CTB, decode order inside
-  const uint32_t* ctb_tu_start;  // [n_ctb + 1]; bit 31 of entry i+1 is NOT used; see ctb_has_intra
-  const uint8_t* ctb_has_intra;  // [n_ctb]
+  const b200_tu* tus;         // decode order, as recorded
+  const uint32_t* list;       // TU indices this launch works on (k_residual: any order; k_intra: grouped by task)
+  int n_list;
+  const uint32_t* task_start; // k_intra: [n_task + 1] offsets into list, tasks in topological order
+  int n_task;
   const b200_coeff* coeffs;
-  const uint8_t* scaling;        // B200_SCALING_FACTOR_BYTES or null
-  unsigned int* ticket;          // zeroed before launch
-  unsigned int* ctb_done;        // [n_ctb], zeroed before launch
+  const uint8_t* scaling;     // B200_SCALING_FACTOR_BYTES or null
+  unsigned int* ticket;       // zeroed before launch (k_intra)
+  unsigned long long* trace;  // optional [n_task][4]: globaltimer at claim, cycles waiting, cycles working, #TUs (debug)
+  uint8_t* pend[3];           // per plane, one byte per 4x4 samples: 1 = covered by an intra TU that is not finished
+  int pend_w[3];
 };
 
 template <typename P>
 struct ReconSmem {
-  P luma[RC_LROWS * RC_LSTRIDE];
-  P chroma[2][RC_CROWS * RC_CSTRIDE];
+  P blk[RC_WARPS][RC_BLK];           // the TU's samples (row stride = nT) or a region tile (see k_intra)
   int16_t coef[RC_WARPS][32 * 32];
   int16_t g[RC_WARPS][32 * RC_GSTRIDE];
-  P border[RC_WARPS][2][4 * 32 + 4];  // [0] gathered/substituted, [1] filtered / angular ref
+  P border[RC_WARPS][2][4 * 32 + 4]; // [0] gathered/substituted, [1] filtered / angular ref
   int8_t dct[32][32];
-  int ctb;
+  b200_tu tu_s[RC_WARPS][16];          // k_intra: the task's TU records (prefetched before the dependency wait)
+  b200_coeff co_s[RC_WARPS][RC_CO_STAGE]; // k_intra: the task's coefficient lists
 };
 
 __device__ __forceinline__ int warp_max(int v)
@@ -61,15 +64,35 @@ __device__ __forceinline__ int warp_sum(int v)
   return v;
 }
 
+// TU block <-> picture plane, 4-byte units (TU rows are 4-byte aligned: x multiple of 4 samples)
+template <typename P>
+__device__ __forceinline__ void block_load(P* blk, const uint8_t* plane, int pitch, int x, int y, int nT, int lane)
+{
+  const int upr = nT * (int)sizeof(P) / 4;
+  for (int o = lane; o < nT * upr; o += 32) {
+    const int r = o / upr, u = o % upr;
+    reinterpret_cast<uint32_t*>(blk + r * nT)[u] = *reinterpret_cast<const uint32_t*>(plane + (size_t)(y + r) * pitch + (size_t)x * sizeof(P) + 4 * u);
+  }
+}
+template <typename P>
+__device__ __forceinline__ void block_store(const P* blk, uint8_t* plane, int pitch, int x, int y, int nT, int lane)
+{
+  const int upr = nT * (int)sizeof(P) / 4;
+  for (int o = lane; o < nT * upr; o += 32) {
+    const int r = o / upr, u = o % upr;
+    *reinterpret_cast<uint32_t*>(plane + (size_t)(y + r) * pitch + (size_t)x * sizeof(P) + 4 * u) = reinterpret_cast<const uint32_t*>(blk + r * nT)[u];
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
-// residual of one TU, executed by one warp; `dst` points at the TU's top-left sample in the smem tile
+// residual of one TU, executed by one warp; `dst` = the TU's samples in shared memory (row stride dstride)
 // -------------------------------------------------------------------------------------------------
 template <typename P>
-__device__ void tu_residual(const b200_tu& tu, const b200_coeff* __restrict__ coeffs, const uint8_t* __restrict__ scaling, P* dst,
+__device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8_t* __restrict__ scaling, P* dst,
                             int dstride, int bd, int16_t* coef, int16_t* g, const int8_t (*dct)[32], int lane)
 {
+  // co = the TU's coefficient list (global memory, or a shared-memory copy staged by the caller)
   const int log2 = tu.log2_size, nT = 1 << log2, n = tu.n_coeff;
-  const b200_coeff* co = coeffs + tu.coeff_off;
   const int flags = tu.flags;
   for (int i = lane; i < nT * nT; i += 32) coef[i] = 0;
   __syncwarp();
@@ -104,8 +127,8 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* __restrict__ co
       max_row = max(max_row, pos >> log2);
       max_col = max(max_col, pos & (nT - 1));
     }
-    max_row = warp_max(max_row);
-    max_col = warp_max(max_col);
+    max_row = __reduce_max_sync(0xffffffffu, max_row);
+    max_col = __reduce_max_sync(0xffffffffu, max_col);
   }
   __syncwarp();
 
@@ -182,16 +205,24 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* __restrict__ co
 }
 
 // -------------------------------------------------------------------------------------------------
-// intra prediction of one TU by one warp.  tile(x,y) addresses the plane's smem tile relative to the
-// TU's top-left sample.
+// intra prediction of one TU by one warp.  Neighbour samples are read relative to `gsrc` (the TU's top-left
+// sample, row stride gstride samples): GLOBAL_SRC = the picture plane in global memory (.cg loads: written by
+// other SMs during this launch), else a shared-memory tile.  The prediction goes to `dst` (row stride dstride).
 // -------------------------------------------------------------------------------------------------
 __constant__ int8_t k_intra_angle[35] = {0,   0,   32,  26,  21,  17, 13, 9,  5,  2,  0,  -2, -5, -9, -13, -17, -21, -26,
                                          -32, -26, -21, -17, -13, -9, -5, -2, 0,  2,  5,  9,  13, 17, 21,  26,  32};
 __constant__ int16_t k_inv_angle[15] = {-4096, -1638, -910, -630, -482, -390, -315, -256, -315, -390, -482, -630, -910, -1638, -4096};
 
-template <typename P>
-__device__ void tu_intra(const b200_tu& tu, P* dst, int dstride, int bd, int bd_luma, uint32_t pic_flags, bool filter_plane, P* b0mem, P* b1mem,
-                         int lane)
+template <bool GLOBAL_SRC, typename P>
+__device__ __forceinline__ int ld_nb(const P* p)
+{
+  if (GLOBAL_SRC) return (int)__ldcg(p);
+  return (int)*p;
+}
+
+template <bool GLOBAL_SRC, typename P>
+__device__ void tu_intra(const b200_tu& tu, const P* gsrc, int gstride, P* dst, int dstride, int bd, int bd_luma, uint32_t pic_flags,
+                         bool filter_plane, P* b0mem, P* b1mem, int lane)
 {
   const int log2 = tu.log2_size, nT = 1 << log2, mode = tu.intra_mode, cidx = tu.cidx;
   const uint64_t avail = tu.avail;
@@ -209,9 +240,9 @@ __device__ void tu_intra(const b200_tu& tu, P* dst, int dstride, int bd, int bd_
       bool av = false;
       int v = 0;
       if (s < total) {
-        if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = dst[-1 + r * dstride]; }
-        else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = dst[-1 - dstride]; }
-        else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = dst[c - dstride]; }
+        if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc - 1 + r * gstride); }
+        else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc - 1 - gstride); }
+        else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc + c - gstride); }
       }
       const unsigned m = __ballot_sync(0xffffffffu, av);
       if (!any && m) { first_val = __shfl_sync(0xffffffffu, v, __ffs(m) - 1); any = true; }
@@ -225,9 +256,9 @@ __device__ void tu_intra(const b200_tu& tu, P* dst, int dstride, int bd, int bd_
         bool av = false;
         int v = 0;
         if (s < total) {
-          if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = dst[-1 + r * dstride]; }
-          else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = dst[-1 - dstride]; }
-          else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = dst[c - dstride]; }
+          if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc - 1 + r * gstride); }
+          else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc - 1 - gstride); }
+          else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc + c - gstride); }
         }
         const unsigned m = __ballot_sync(0xffffffffu, av);
         const unsigned below = m & ((2u << lane) - 1u);  // available lanes <= this one
@@ -321,126 +352,188 @@ __device__ void tu_intra(const b200_tu& tu, P* dst, int dstride, int bd, int bd_
 
 // -------------------------------------------------------------------------------------------------
 template <typename P>
-__global__ void __launch_bounds__(RC_THREADS) k_recon(DevPic pic, ReconArgs args)
+__global__ void __launch_bounds__(RC_THREADS) k_residual(DevPic pic, ReconArgs args)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   ReconSmem<P>& sm = *reinterpret_cast<ReconSmem<P>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) sm.ctb = (int)atomicAdd(args.ticket, 1u);
   for (int i = tid; i < 32 * 32; i += RC_THREADS) sm.dct[i >> 5][i & 31] = c_dct[i >> 5][i & 31];
   __syncthreads();
-  const int ctb = sm.ctb;
-  const int n_ctb = pic.wctb * pic.hctb;
-  if (ctb >= n_ctb) return;
-  const int cx = ctb % pic.wctb, cy = ctb / pic.wctb;
-  const int S = 1 << pic.log2ctb;
-  const int xC = cx << pic.log2ctb, yC = cy << pic.log2ctb;
-  const int bw = min(S, pic.w - xC), bh = min(S, pic.h - yC);  // CTB part inside the picture
-  const uint32_t t0 = args.ctb_tu_start[ctb], t1 = args.ctb_tu_start[ctb + 1];
-  const bool has_intra = args.ctb_has_intra[ctb];
-  const int nplanes = pic.chroma ? 3 : 1;
-
-  if (t1 == t0) {  // nothing to do for this CTB (pure skip CUs): prediction already final
-    if (tid == 0) { __threadfence(); atomicExch(&args.ctb_done[ctb], 1u); }
-    return;
-  }
-
-  // ---- wait for the neighbours an intra CTB may read (left, top-left, top, top-right) ----
-  if (has_intra) {
-    if (tid < 4) {
-      const int nx = (tid == 0) ? cx - 1 : (tid == 1) ? cx - 1 : (tid == 2) ? cx : cx + 1;
-      const int ny = (tid == 0) ? cy : cy - 1;
-      if (nx >= 0 && ny >= 0 && nx < pic.wctb) {
-        const volatile unsigned int* f = args.ctb_done + (nx + ny * pic.wctb);
-        while (*f == 0u) __nanosleep(20);
-      }
-      __threadfence();
+  const int idx = blockIdx.x * RC_WARPS + warp;
+  if (idx >= args.n_list) return;
+  const b200_tu tu = args.tus[args.list[idx]];
+  const int c = tu.cidx, nT = 1 << tu.log2_size;
+  P* blk = sm.blk[warp];
+  if (tu.flags & B200_TU_PCM) {  // slice.cc:4211-4255
+    for (int i = lane; i < tu.n_coeff; i += 32) {
+      const b200_coeff co = args.coeffs[tu.coeff_off + i];
+      blk[co.pos] = (P)(uint16_t)co.level;
     }
-    __syncthreads();
+    __syncwarp();
+  } else {
+    block_load<P>(blk, pic.cur[c], pic.pitch[c], tu.x, tu.y, nT, lane);
+    __syncwarp();
+    tu_residual<P>(tu, args.coeffs + tu.coeff_off, args.scaling, blk, nT, c ? pic.bd_c : pic.bd_y, sm.coef[warp], sm.g[warp], sm.dct, lane);
   }
+  block_store<P>(blk, pic.cur[c], pic.pitch[c], tu.x, tu.y, nT, lane);
+}
 
-  // ---- stage the CTB (+ top row / left column when intra) into shared memory ----
-  for (int c = 0; c < nplanes; c++) {
-    const int sh = c ? 1 : 0;
-    const int w = bw >> sh, h = bh >> sh, x0 = xC >> sh, y0 = yC >> sh;
-    const int pw = c ? pic.cw : pic.w;
-    P* tile = c ? sm.chroma[c - 1] : sm.luma;
-    const int ts = c ? RC_CSTRIDE : RC_LSTRIDE;
-    const uint8_t* src = pic.cur[c];
-    const int pitch = pic.pitch[c];
-    constexpr int VEC = 16 / sizeof(P);
-    const int vpr = (w + VEC - 1) / VEC;  // 16-byte vectors per row (surface rows are padded)
-    for (int i = tid; i < vpr * h; i += RC_THREADS) {
-      const int y = i / vpr, v = i % vpr;
-      // .cg loads: neighbour CTBs are written by other SMs during this launch, L1 must not serve them
-      const uint4 d = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(y0 + y) * pitch + (size_t)(x0 + v * VEC) * sizeof(P)));
-      *reinterpret_cast<uint4*>(&tile[(y + 1) * ts + RC_XOFF + v * VEC]) = d;
-    }
-    if (has_intra) {
-      const int tr = min(S >> sh, 32 >> sh);  // top-right reach = largest TU of the plane
-      if (y0 > 0)
-        for (int x = tid - 1; x < w + tr; x += RC_THREADS)
-          if (x0 + x >= 0 && x0 + x < pw) tile[RC_XOFF + x] = __ldcg(row_ptr<P>(src, pitch, y0 - 1) + x0 + x);
-      if (x0 > 0)
-        for (int y = tid; y < h; y += RC_THREADS) tile[(y + 1) * ts + RC_XOFF - 1] = __ldcg(row_ptr<P>(src, pitch, y0 + y) + x0 - 1);
-    }
+__global__ void k_mark_pending(ReconArgs args)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= args.n_list) return;
+  const b200_tu tu = args.tus[args.list[idx]];
+  const int c = tu.cidx, n4 = 1 << (tu.log2_size - 2);
+  uint8_t* p = args.pend[c] + (tu.y >> 2) * args.pend_w[c] + (tu.x >> 2);
+  for (int j = 0; j < n4; j++)
+    for (int i = 0; i < n4; i++) p[j * args.pend_w[c] + i] = 1;
+}
+
+// Dependency set of a task = the distinct 4x4 units OUTSIDE its region that its TUs' availability masks let them
+// read.  For a region (G x G, G <= 16) these are at most 2G/4 units left of it, the corner and 2G/4 units above it;
+// for a single large TU nT/2 + 1 + nT/2 units.  Each lane owns one such unit (lane 0.. : left column top-down,
+// then the corner, then the top row left-to-right), so one poll round is a single load instruction per warp.
+__device__ __forceinline__ void dep_units_of(const b200_tu& tu, int rx, int ry, int span, uint64_t& left, bool& corner, uint64_t& top)
+{
+  // span = number of units along one side of the dependency frame (2G/4 for a region, nT/2 for a single TU);
+  // (rx, ry) = frame origin in samples.  Adds this TU's needed external units.
+  const int nT = 1 << tu.log2_size, half = nT / 2;
+  const int ux0 = (tu.x - rx) >> 2, uy0 = (tu.y - ry) >> 2;  // TU position inside the frame, in units
+  const uint64_t avail = tu.avail;
+  if (ux0 == 0) {  // left neighbours are outside the frame
+    for (int g = 0; g < half; g++)
+      if (((avail >> g) & 1) && uy0 + g < span) left |= 1ull << (uy0 + g);
+    if ((avail >> B200_AVAIL_CORNER_BIT) & 1) { if (uy0 == 0) corner = true; else left |= 1ull << (uy0 - 1); }
+  } else if (uy0 == 0 && ((avail >> B200_AVAIL_CORNER_BIT) & 1)) {
+    top |= 1ull << (ux0 - 1);
   }
+  if (uy0 == 0)
+    for (int k = 0; k < half; k++)
+      if (((avail >> (B200_AVAIL_TOP_BIT0 + k)) & 1) && ux0 + k < span) top |= 1ull << (ux0 + k);
+}
+
+template <typename P>
+__global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  ReconSmem<P>& sm = *reinterpret_cast<ReconSmem<P>*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 32 * 32; i += RC_THREADS) sm.dct[i >> 5][i & 31] = c_dct[i >> 5][i & 31];
   __syncthreads();
-
-  // ---- phase A: non-intra TUs, one warp each ----
-  for (uint32_t t = t0 + warp; t < t1; t += RC_WARPS) {
-    const b200_tu tu = args.tus[t];
-    if (tu.flags & B200_TU_INTRA) continue;
-    const int c = tu.cidx, sh = c ? 1 : 0;
-    P* tile = c ? sm.chroma[c - 1] : sm.luma;
-    const int ts = c ? RC_CSTRIDE : RC_LSTRIDE;
-    P* dst = tile + (tu.y - (yC >> sh) + 1) * ts + RC_XOFF + (tu.x - (xC >> sh));
-    if (tu.flags & B200_TU_PCM) {
-      const int nT = 1 << tu.log2_size;
-      for (int i = lane; i < tu.n_coeff; i += 32) {
-        const b200_coeff co = args.coeffs[tu.coeff_off + i];
-        dst[(co.pos & (nT - 1)) + (co.pos >> tu.log2_size) * ts] = (P)(uint16_t)co.level;
+  // Persistent warps: each warp keeps claiming the next task of the topological order.
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(args.ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= (unsigned)args.n_task) return;
+    unsigned long long tr_t0 = 0, tr_c0 = 0, tr_c1 = 0;
+    if (args.trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0)); tr_c0 = clock64(); }
+    const uint32_t first = args.task_start[t], count = min(args.task_start[t + 1] - first, 16u);
+    // ---- prefetch everything that does not depend on the neighbours: TU records and coefficient lists ----
+    b200_tu* tus = sm.tu_s[warp];
+    b200_coeff* cos = sm.co_s[warp];
+    if (lane < (int)count) tus[lane] = args.tus[args.list[first + lane]];
+    __syncwarp();
+    {
+      int base = 0;
+      for (uint32_t i = 0; i < count; i++) {
+        const int n = tus[i].n_coeff;
+        if (base + n <= RC_CO_STAGE) {
+          const b200_coeff* src = args.coeffs + tus[i].coeff_off;
+          for (int k = lane; k < n; k += 32) cos[base + k] = src[k];
+        }
+        base += n;
       }
-      __syncwarp();
-    } else if (tu.flags & B200_TU_CBF) {
-      tu_residual<P>(tu, args.coeffs, args.scaling, dst, ts, c ? pic.bd_c : pic.bd_y, sm.coef[warp], sm.g[warp], sm.dct, lane);
     }
-  }
-  __syncthreads();
-
-  // ---- phase B: intra TUs, warp c owns colour plane c ----
-  if (has_intra && warp < nplanes) {
-    const int c = warp, sh = c ? 1 : 0;
-    P* tile = c ? sm.chroma[c - 1] : sm.luma;
-    const int ts = c ? RC_CSTRIDE : RC_LSTRIDE;
+    const b200_tu tu0 = tus[0];
+    const int c = tu0.cidx, sh = c ? 1 : 0;
     const int bd = c ? pic.bd_c : pic.bd_y;
+    const int G = 16 >> sh;  // region size in this plane's samples
+    const bool region = count > 1 || (1 << tu0.log2_size) < G;
+    const int rx = tu0.x & ~(G - 1), ry = tu0.y & ~(G - 1);
     const bool filter_plane = !(pic.flags & B200_PIC_INTRA_SMOOTHING_OFF) && (c == 0 || pic.chroma == 3);
-    for (uint32_t t = t0; t < t1; t++) {
-      const b200_tu tu = args.tus[t];
-      if (!(tu.flags & B200_TU_INTRA) || tu.cidx != c) continue;
-      P* dst = tile + (tu.y - (yC >> sh) + 1) * ts + RC_XOFF + (tu.x - (xC >> sh));
-      tu_intra<P>(tu, dst, ts, bd, pic.bd_y, pic.flags, filter_plane, sm.border[warp][0], sm.border[warp][1], lane);
-      if (tu.flags & B200_TU_CBF) tu_residual<P>(tu, args.coeffs, args.scaling, dst, ts, bd, sm.coef[warp], sm.g[warp], sm.dct, lane);
+    const int gstride = pic.pitch[c] / (int)sizeof(P);
+    const int pwid = c ? pic.cw : pic.w, phei = c ? pic.ch : pic.h;
+    P* blk = sm.blk[warp];
+    __syncwarp();
+    // ---- wait: one flag per distinct external neighbour unit, one lane each ----
+    {
+      const int span = region ? (2 * G) >> 2 : (1 << tu0.log2_size) >> 1;
+      const int fx = region ? rx : tu0.x, fy = region ? ry : tu0.y;
+      uint64_t left = 0, top = 0;
+      bool corner = false;
+      for (uint32_t i = 0; i < count; i++) dep_units_of(tus[i], fx, fy, span, left, corner, top);
+      const int pw = args.pend_w[c];
+      const uint8_t* pend = args.pend[c] + (fy >> 2) * pw + (fx >> 2);
+      const volatile uint8_t* f = nullptr;
+      if (lane < span) { if ((left >> lane) & 1) f = pend + lane * pw - 1; }
+      else if (lane == span) { if (corner) f = pend - pw - 1; }
+      else if (lane - span - 1 < span) { if ((top >> (lane - span - 1)) & 1) f = pend - pw + (lane - span - 1); }
+      const volatile uint8_t* f2 = nullptr;  // single 32x32 TU: 33 units, lane 0 takes the last top unit as well
+      if (span == 16 && lane == 0 && ((top >> 15) & 1)) f2 = pend - pw + 15;
+      unsigned ns = 32;
+      for (;;) {
+        const bool busy = (f && *f) || (f2 && *f2);
+        if (!__any_sync(0xffffffffu, busy)) break;
+        __nanosleep(ns);
+        if (ns < 256) ns *= 2;
+      }
     }
-  }
-  __syncthreads();
+    __threadfence();  // acquire: the neighbours' samples were published before their flags were cleared
+    if (args.trace) tr_c1 = clock64();
 
-  // ---- write the CTB back (16-byte row stores) and publish it ----
-  for (int c = 0; c < nplanes; c++) {
-    const int sh = c ? 1 : 0;
-    const int w = bw >> sh, h = bh >> sh, x0 = xC >> sh, y0 = yC >> sh;
-    const P* tile = c ? sm.chroma[c - 1] : sm.luma;
-    const int ts = c ? RC_CSTRIDE : RC_LSTRIDE;
-    uint8_t* dstp = pic.cur[c];
-    const int pitch = pic.pitch[c];
-    constexpr int VEC = 16 / sizeof(P);
-    const int vpr = (w + VEC - 1) / VEC;
-    for (int i = tid; i < vpr * h; i += RC_THREADS) {
-      const int y = i / vpr, v = i % vpr;
-      *reinterpret_cast<uint4*>(dstp + (size_t)(y0 + y) * pitch + (size_t)(x0 + v * VEC) * sizeof(P)) =
-          *reinterpret_cast<const uint4*>(&tile[(y + 1) * ts + RC_XOFF + v * VEC]);
+    if (!region) {
+      // ---- one TU at least as large as a region: borders straight from the picture ----
+      const int nT = 1 << tu0.log2_size;
+      const P* gsrc = row_ptr<P>(pic.cur[c], pic.pitch[c], tu0.y) + tu0.x;
+      tu_intra<true, P>(tu0, gsrc, gstride, blk, nT, bd, pic.bd_y, pic.flags, filter_plane, sm.border[warp][0], sm.border[warp][1], lane);
+      if (tu0.flags & B200_TU_CBF)
+        tu_residual<P>(tu0, tu0.n_coeff <= RC_CO_STAGE ? cos : args.coeffs + tu0.coeff_off, args.scaling, blk, nT, bd, sm.coef[warp], sm.g[warp], sm.dct, lane);
+      block_store<P>(blk, pic.cur[c], pic.pitch[c], tu0.x, tu0.y, nT, lane);
+    } else {
+      // ---- a region of small TUs: stage region + top row (2G) + left column (2G) in shared memory, run the TUs in order ----
+      const int TS = RC_TILE_STRIDE;
+      P* tile = blk + TS + 1;  // tile(0,0) = region origin; tile(-1,-1) is blk[0]
+      const int gw = min(G, pwid - rx), gh = min(G, phei - ry);
+      for (int o = lane; o < gw * gh; o += 32) {
+        const int x = o % gw, y = o / gw;
+        tile[y * TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx + x);
+      }
+      if (ry > 0)
+        for (int x = lane - 1; x < 2 * G; x += 32)
+          if (rx + x >= 0 && rx + x < pwid) tile[-TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry - 1) + rx + x);
+      if (rx > 0)  // left column incl. the bottom-left reach (available when the region is a top-left child of its parent block)
+        for (int y = lane; y < 2 * G; y += 32)
+          if (ry + y < phei) tile[y * TS - 1] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx - 1);
+      __syncwarp();
+      int base = 0;
+      for (uint32_t i = 0; i < count; i++) {
+        const b200_tu tu = tus[i];
+        P* dst = tile + (tu.y - ry) * TS + (tu.x - rx);
+        tu_intra<false, P>(tu, dst, TS, dst, TS, bd, pic.bd_y, pic.flags, filter_plane, sm.border[warp][0], sm.border[warp][1], lane);
+        if (tu.flags & B200_TU_CBF)
+          tu_residual<P>(tu, (base + tu.n_coeff <= RC_CO_STAGE) ? cos + base : args.coeffs + tu.coeff_off, args.scaling, dst, TS, bd, sm.coef[warp],
+                         sm.g[warp], sm.dct, lane);
+        base += tu.n_coeff;
+      }
+      for (int o = lane; o < gw * gh; o += 32) {
+        const int x = o % gw, y = o / gw;
+        row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y)[rx + x] = tile[y * TS + x];
+      }
+    }
+    __threadfence();  // release: samples before flags
+    __syncwarp();
+    for (uint32_t i = 0; i < count; i++) {
+      const b200_tu tu = tus[i];
+      const int n4 = 1 << (tu.log2_size - 2), pw = args.pend_w[c];
+      uint8_t* pend = args.pend[c] + (tu.y >> 2) * pw + (tu.x >> 2);
+      for (int o = lane; o < n4 * n4; o += 32) *reinterpret_cast<volatile uint8_t*>(pend + (o / n4) * pw + (o % n4)) = 0;
+    }
+    __syncwarp();
+    if (args.trace && lane == 0) {
+      const unsigned long long c2 = clock64();
+      unsigned long long* tr = args.trace + 4ull * t;
+      tr[0] = tr_t0; tr[1] = tr_c1 - tr_c0; tr[2] = c2 - tr_c1; tr[3] = count | ((unsigned long long)c << 8) | ((unsigned long long)tu0.log2_size << 16);
     }
   }
-  __syncthreads();
-  if (tid == 0) { __threadfence(); atomicExch(&args.ctb_done[ctb], 1u); }
 }

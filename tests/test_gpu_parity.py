@@ -180,9 +180,10 @@ def test_malformed_records_are_rejected(eng):
 
 
 def test_empty_picture(eng, oracle_mod):
-    """No PUs and no TUs: every stage must cope with empty work lists."""
+    """No PUs and no TUs: every stage must cope with empty work lists (samples no record covers keep the slot's
+    content; with SAO on they would come from the scratch surface, which only a malformed stream can expose)."""
     orc = oracle_mod.Oracle()
-    p = synth.make_picture(64, 64, "I", seed=44, dst_slot=1)
+    p = synth.make_picture(64, 64, "I", seed=44, dst_slot=1, sao=False)
     e = synth.SynthPicture(p.params, p.pus[:0], p.weights, p.tus[:0], p.coeffs[:0], p.slices, p.ctbs, p.bs_map, p.qp_map, p.nofilt_map)
     eng.fill_slot(1, p.params, 50, 60)
     orc.fill_slot(1, p.params, 50, 60)
