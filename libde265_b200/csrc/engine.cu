@@ -166,10 +166,8 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   if (rc) { delete en; return rc; }
   CU(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&en->stage[i].done, cudaEventDisableTiming));
-  CU(cudaFuncSetAttribute(k_residual<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint8_t>)));
-  CU(cudaFuncSetAttribute(k_residual<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint16_t>)));
-  CU(cudaFuncSetAttribute(k_intra<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint8_t>)));
-  CU(cudaFuncSetAttribute(k_intra<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReconSmem<uint16_t>)));
+  CU(cudaFuncSetAttribute(k_intra<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<uint8_t>)));
+  CU(cudaFuncSetAttribute(k_intra<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<uint16_t>)));
   CU(cudaDeviceGetAttribute(&en->num_sms, cudaDevAttrMultiProcessorCount, device));
   *out = en;
   return B200_OK;
@@ -304,7 +302,7 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
     if (L.n_a > 0) {
       ra.list = (const uint32_t*)(dbase + off[3]);
       ra.n_list = L.n_a;
-      k_residual<P><<<(L.n_a + RC_WARPS - 1) / RC_WARPS, RC_THREADS, sizeof(ReconSmem<P>), st>>>(dp, ra);
+      k_residual<P><<<(L.n_a + RC_WARPS - 1) / RC_WARPS, RC_THREADS, 0, st>>>(dp, ra);
       en->launches++;
     }
     ra.trace = nullptr;
@@ -323,9 +321,9 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
       ra.task_start = (const uint32_t*)(dbase + off[13]);
       ra.n_task = L.n_task;
       int grid = (L.n_task + RC_WARPS - 1) / RC_WARPS;
-      const int cap = en->num_sms * 3;
+      const int cap = en->num_sms * 2;
       if (grid > cap) grid = cap;
-      k_intra<P><<<grid, RC_THREADS, sizeof(ReconSmem<P>), st>>>(dp, ra);
+      k_intra<P><<<grid, RC_THREADS, sizeof(IntraSmem<P>), st>>>(dp, ra);
       en->launches += 2;
       if (trace_dev) {
         std::vector<unsigned long long> h(4 * (size_t)L.n_task);

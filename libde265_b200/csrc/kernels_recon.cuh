@@ -1,17 +1,20 @@
 // kernels_recon.cuh — intra prediction + residual (dequant, inverse DCT/DST, transform-skip, bypass,
-// PCM) for one picture in three launches, one WARP per transform unit.
+// PCM) for one picture in three launches, one WARP per transform unit / intra task.
 //
 //   k_residual<P>   every TU of a non-intra CU that carries work (inter residual, PCM): no dependencies,
 //                   fully parallel.  Runs after k_inter_pred (it adds onto the prediction).
 //   k_mark_pending  flags the 4x4 units covered by intra TUs as "pending" in a per-plane map.
 //   k_intra<P>      every intra TU: border gather + substitution + smoothing, DC/planar/angular prediction,
 //                   then the TU's residual.  Intra TUs are serially dependent through their neighbours
-//                   (SURVEY §3.2), so the kernel executes the dependency DAG directly: warps claim TUs through
-//                   an atomic ticket in a topological order (CTB anti-diagonal x + 2y, then decode order), poll
-//                   the pending flags of exactly the neighbour units their availability mask says they read,
-//                   reconstruct, write the TU, fence, and clear their own flags.  The lowest unfinished ticket
-//                   never waits on a later one, so the launch cannot deadlock.  Colour planes are independent
-//                   chains.  This gives TU-granular wavefront parallelism instead of one CTB per step.
+//                   (SURVEY §3.2), so the kernel executes the dependency DAG directly: warps claim *tasks*
+//                   through an atomic ticket in a topological order (CTB anti-diagonal x + 2y, then decode
+//                   order).  A task = the TUs (<= 8x8) of one plane inside one aligned 16x16-luma / 8x8-chroma
+//                   region, run in decode order on a shared-memory tile, or one larger TU.  Everything that
+//                   does not depend on the neighbours (TU records, coefficient lists, dequant + inverse
+//                   transform into an int32 residual buffer) is done BEFORE the warp polls the pending flags
+//                   of the neighbour units its availability masks let it read; the dependent part is only
+//                   gather -> predict -> add.  After the store: fence, clear own flags.  The lowest unfinished
+//                   ticket never waits on a later one, so the launch cannot deadlock.
 //
 // Replaces decode_TU (slice.cc:3460), decode_intra_prediction (intrapred.cc:277-345) incl. border
 // fetch/substitution/smoothing (intrapred.h:185-258,529-674), scale_coefficients (transform.cc:361-642)
@@ -21,10 +24,11 @@
 
 #define RC_WARPS 8
 #define RC_THREADS (RC_WARPS * 32)
-#define RC_GSTRIDE 34   // int16 row stride of the first-stage buffer
+#define RC_GSTRIDE 34      // int16 row stride of the first-stage buffer
 #define RC_TILE_STRIDE 40  // region tile: rows -1..2G-1 (only column -1 below row G-1), columns -1..2G-1 (G <= 16)
 #define RC_BLK (33 * RC_TILE_STRIDE + 8)
 #define RC_CO_STAGE 256
+#define RC_FULL 0xffffffffu
 
 struct ReconArgs {
   const b200_tu* tus;         // decode order, as recorded
@@ -40,60 +44,40 @@ struct ReconArgs {
   int pend_w[3];
 };
 
-template <typename P>
-struct ReconSmem {
-  P blk[RC_WARPS][RC_BLK];           // the TU's samples (row stride = nT) or a region tile (see k_intra)
+struct ResidualSmem {  // k_residual
   int16_t coef[RC_WARPS][32 * 32];
   int16_t g[RC_WARPS][32 * RC_GSTRIDE];
-  P border[RC_WARPS][2][4 * 32 + 4]; // [0] gathered/substituted, [1] filtered / angular ref
   int8_t dct[32][32];
-  b200_tu tu_s[RC_WARPS][16];          // k_intra: the task's TU records (prefetched before the dependency wait)
-  b200_coeff co_s[RC_WARPS][RC_CO_STAGE]; // k_intra: the task's coefficient lists
 };
 
-__device__ __forceinline__ int warp_max(int v)
-{
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ int warp_sum(int v)
-{
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// TU block <-> picture plane, 4-byte units (TU rows are 4-byte aligned: x multiple of 4 samples)
 template <typename P>
-__device__ __forceinline__ void block_load(P* blk, const uint8_t* plane, int pitch, int x, int y, int nT, int lane)
-{
-  const int upr = nT * (int)sizeof(P) / 4;
-  for (int o = lane; o < nT * upr; o += 32) {
-    const int r = o / upr, u = o % upr;
-    reinterpret_cast<uint32_t*>(blk + r * nT)[u] = *reinterpret_cast<const uint32_t*>(plane + (size_t)(y + r) * pitch + (size_t)x * sizeof(P) + 4 * u);
-  }
-}
-template <typename P>
-__device__ __forceinline__ void block_store(const P* blk, uint8_t* plane, int pitch, int x, int y, int nT, int lane)
-{
-  const int upr = nT * (int)sizeof(P) / 4;
-  for (int o = lane; o < nT * upr; o += 32) {
-    const int r = o / upr, u = o % upr;
-    *reinterpret_cast<uint32_t*>(plane + (size_t)(y + r) * pitch + (size_t)x * sizeof(P) + 4 * u) = reinterpret_cast<const uint32_t*>(blk + r * nT)[u];
-  }
-}
+struct IntraSmem {  // k_intra
+  P blk[RC_WARPS][RC_BLK];            // a region tile, or a large TU's samples (row stride nT)
+  int16_t coef[RC_WARPS][32 * 32];
+  int16_t g[RC_WARPS][32 * RC_GSTRIDE];
+  int32_t res[RC_WARPS][32 * 32];     // the task's residuals, TU after TU (row stride nT inside a TU)
+  P border[RC_WARPS][2][4 * 32 + 4];  // large TUs: [0] gathered/substituted, [1] filtered / angular ref
+  b200_tu tu_s[RC_WARPS][16];
+  b200_coeff co_s[RC_WARPS][RC_CO_STAGE];
+  int8_t dct[32][32];
+};
 
 // -------------------------------------------------------------------------------------------------
-// residual of one TU, executed by one warp; `dst` = the TU's samples in shared memory (row stride dstride)
+// Residual of one TU by one warp.  TO_RES: write the int32 residual r(x,y) to res[x + y*nT]
+// (the caller adds it later); else dst(x,y) = Clip(dst + r) on samples at `dst` (row stride dstride, in
+// GLOBAL memory: each sample is read and written by the same lane exactly once).
+// co = the TU's coefficient list (global memory, or a shared-memory copy staged by the caller).
 // -------------------------------------------------------------------------------------------------
-template <typename P>
-__device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8_t* __restrict__ scaling, P* dst,
-                            int dstride, int bd, int16_t* coef, int16_t* g, const int8_t (*dct)[32], int lane)
+template <typename P, bool TO_RES>
+__device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8_t* __restrict__ scaling, P* dst, int dstride, int32_t* res,
+                            int bd, int16_t* coef, int16_t* g, const int8_t (*dct)[32], int lane)
 {
-  // co = the TU's coefficient list (global memory, or a shared-memory copy staged by the caller)
   const int log2 = tu.log2_size, nT = 1 << log2, n = tu.n_coeff;
   const int flags = tu.flags;
+  auto emit = [&](int x, int y, int r) {
+    if (TO_RES) res[x + (y << log2)] = r;
+    else dst[x + y * dstride] = (P)clip_bd((int)dst[x + y * dstride] + r, bd);
+  };
   for (int i = lane; i < nT * nT; i += 32) coef[i] = 0;
   __syncwarp();
   // ---- dequant + scatter (transform.cc:452-525) ----
@@ -110,15 +94,15 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8
     }
     int bd_shift = bd + log2 - 5;
     if (!scl) bd_shift -= 4;
-    const int qp = tu.qp;
-    const int ls = (qp % 6 == 0) ? 40 : (qp % 6 == 1) ? 45 : (qp % 6 == 2) ? 51 : (qp % 6 == 3) ? 57 : (qp % 6 == 4) ? 64 : 72;
+    const int qp = tu.qp, qm = qp % 6, qd = qp / 6;
+    const int ls = (qm == 0) ? 40 : (qm == 1) ? 45 : (qm == 2) ? 51 : (qm == 3) ? 57 : (qm == 4) ? 64 : 72;
     for (int i = lane; i < n; i += 32) {
       const b200_coeff c = co[i];
       int v;
       if (bypass) {
         v = c.level;
       } else {
-        const long long fact = (long long)((scl ? scl[c.pos] : 1) * ls) << (qp / 6);
+        const long long fact = (long long)((scl ? scl[c.pos] : 1) * ls) << qd;
         long long q = ((long long)c.level * fact + (1ll << (bd_shift - 1))) >> bd_shift;
         v = (int)max(-32768ll, min(32767ll, q));
       }
@@ -127,8 +111,8 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8
       max_row = max(max_row, pos >> log2);
       max_col = max(max_col, pos & (nT - 1));
     }
-    max_row = __reduce_max_sync(0xffffffffu, max_row);
-    max_col = __reduce_max_sync(0xffffffffu, max_col);
+    max_row = __reduce_max_sync(RC_FULL, max_row);
+    max_col = __reduce_max_sync(RC_FULL, max_col);
   }
   __syncwarp();
 
@@ -145,15 +129,14 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8
           int c = coef[x + y * nT];
           if (ts) c = ((int)((unsigned)c << ts_shift) + rnd) >> bd_shift;
           sum += c;
-          dst[x + y * dstride] = (P)clip_bd((int)dst[x + y * dstride] + sum, bd);
+          emit(x, y, sum);
         }
       }
     } else {
       for (int i = lane; i < nT * nT; i += 32) {
         int c = coef[i];
         if (ts) c = ((int)((unsigned)c << ts_shift) + rnd) >> bd_shift;
-        const int x = i & (nT - 1), y = i >> log2;
-        dst[x + y * dstride] = (P)clip_bd((int)dst[x + y * dstride] + c, bd);
+        emit(i & (nT - 1), i >> log2, c);
       }
     }
     __syncwarp();
@@ -162,13 +145,19 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8
 
   const int post_shift = 20 - bd, rnd2 = 1 << (post_shift - 1);
   if (flags & B200_TU_DST) {
-    // fallback-dct.cc:269-407 (mat_8_357 :260-265)
-    const int m[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
+    // fallback-dct.cc:269-407 (mat_8_357 :260-265); m(j,i) selected without a local-memory table
+    auto m = [](int j, int i) -> int {
+      const int t[16] = {29, 55, 74, 84, 74, 74, 0, -74, 84, -29, -74, 55, 55, -84, 74, -29};
+      int r = 0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) r = (k == j * 4 + i) ? t[k] : r;
+      return r;
+    };
     if (lane < 16) {
       const int c = lane & 3, i = lane >> 2;
       int sum = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) sum += m[j][i] * coef[c + j * 4];
+      for (int j = 0; j < 4; j++) sum += m(j, i) * coef[c + j * 4];
       g[i * RC_GSTRIDE + c] = (int16_t)clip3i(-32768, 32767, (sum + 64) >> 7);
     }
     __syncwarp();
@@ -176,9 +165,8 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8
       const int i = lane & 3, y = lane >> 2;
       int sum = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) sum += m[j][i] * g[y * RC_GSTRIDE + j];
-      const int out = clip3i(-32768, 32767, (sum + rnd2) >> post_shift);
-      dst[i + y * dstride] = (P)clip_bd((int)dst[i + y * dstride] + out, bd);
+      for (int j = 0; j < 4; j++) sum += m(j, i) * g[y * RC_GSTRIDE + j];
+      emit(i, y, clip3i(-32768, 32767, (sum + rnd2) >> post_shift));
     }
     __syncwarp();
     return;
@@ -198,33 +186,147 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8
     const int i = o & (nT - 1), y = o >> log2;
     int sum = 0;
     for (int j = 0; j <= max_col; j++) sum += (int)dct[fact * j][i] * (int)g[y * RC_GSTRIDE + j];
-    const int out = (sum + rnd2) >> post_shift;
-    dst[i + y * dstride] = (P)clip_bd((int)dst[i + y * dstride] + out, bd);
+    emit(i, y, (sum + rnd2) >> post_shift);
   }
   __syncwarp();
 }
 
 // -------------------------------------------------------------------------------------------------
-// intra prediction of one TU by one warp.  Neighbour samples are read relative to `gsrc` (the TU's top-left
-// sample, row stride gstride samples): GLOBAL_SRC = the picture plane in global memory (.cg loads: written by
-// other SMs during this launch), else a shared-memory tile.  The prediction goes to `dst` (row stride dstride).
-// -------------------------------------------------------------------------------------------------
 __constant__ int8_t k_intra_angle[35] = {0,   0,   32,  26,  21,  17, 13, 9,  5,  2,  0,  -2, -5, -9, -13, -17, -21, -26,
                                          -32, -26, -21, -17, -13, -9, -5, -2, 0,  2,  5,  9,  13, 17, 21,  26,  32};
 __constant__ int16_t k_inv_angle[15] = {-4096, -1638, -910, -630, -482, -390, -315, -256, -315, -390, -482, -630, -910, -1638, -4096};
 
-template <bool GLOBAL_SRC, typename P>
-__device__ __forceinline__ int ld_nb(const P* p)
-{
-  if (GLOBAL_SRC) return (int)__ldcg(p);
-  return (int)*p;
-}
-
-template <bool GLOBAL_SRC, typename P>
-__device__ void tu_intra(const b200_tu& tu, const P* gsrc, int gstride, P* dst, int dstride, int bd, int bd_luma, uint32_t pic_flags,
-                         bool filter_plane, P* b0mem, P* b1mem, int lane)
+// -------------------------------------------------------------------------------------------------
+// Small TUs (nT = 4 or 8) on a shared-memory tile: the whole border lives in registers (lane s holds scan
+// sample s: s = 0 -> border[-2nT] ... 2nT -> border[0] ... 4nT -> border[2nT]; the 33rd sample of an 8x8 TU is
+// replicated in `ve`), neighbours are exchanged with shuffles only.  dst = the TU's top-left sample in the tile.
+// res = this TU's precomputed residual (row stride nT) or nullptr.  intrapred.h:185-433,529-674.
+// -------------------------------------------------------------------------------------------------
+template <typename P>
+__device__ __forceinline__ void tu_intra_small(const b200_tu& tu, P* dst, int ts, int bd, bool filter_plane, const int32_t* res, int lane)
 {
   const int log2 = tu.log2_size, nT = 1 << log2, mode = tu.intra_mode, cidx = tu.cidx;
+  const uint64_t avail = tu.avail;
+  const int total = 4 * nT + 1;
+  // ---- gather ----
+  int v = 0, ve = 0;
+  bool av = false, av_e = false;
+  {
+    const int i = lane - 2 * nT;
+    if (lane < total) {
+      if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = dst[-1 + r * ts]; }
+      else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = dst[-1 - ts]; }
+      else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = dst[c - ts]; }
+    }
+    if (nT == 8) {  // scan sample 32 = border[16] = top row column 15
+      av_e = (avail >> (B200_AVAIL_TOP_BIT0 + 3)) & 1;
+      if (av_e) ve = dst[15 - ts];
+    }
+  }
+  // ---- substitution (intrapred.h:637-674) ----
+  {
+    const unsigned m = __ballot_sync(RC_FULL, av);
+    if (m == 0 && !av_e) {
+      v = ve = 1 << (bd - 1);
+    } else {
+      const int first_lane = m ? __ffs(m) - 1 : 0;
+      const int fv = __shfl_sync(RC_FULL, v, first_lane);
+      const int first = m ? fv : ve;
+      const unsigned below = m & ((2u << lane) - 1u);
+      const int sv = __shfl_sync(RC_FULL, v, below ? 31 - __clz(below) : 0);
+      v = below ? sv : first;
+      const int last = __shfl_sync(RC_FULL, v, 31);
+      if (!av_e) ve = last;
+    }
+  }
+  // ---- smoothing (intrapred.h:185-258): only nT == 8 can get here with a filter (nT == 4 never filters) ----
+  if (filter_plane && nT == 8 && mode != 1) {
+    const int d = min(abs(mode - 26), abs(mode - 10));
+    if (d > 7) {
+      const int vm = __shfl_up_sync(RC_FULL, v, 1);
+      int vp = __shfl_down_sync(RC_FULL, v, 1);
+      if (lane == 31) vp = ve;
+      if (lane != 0) v = (vp + 2 * v + vm + 2) >> 2;
+    }
+  }
+  // border sample at index i in [-2nT, 2nT]; must be called by all lanes (uniform control flow)
+  auto B = [&](int i) -> int {
+    const int s = i + 2 * nT;
+    const int r = __shfl_sync(RC_FULL, v, s & 31);
+    return (s == 32) ? ve : r;
+  };
+  const int npass = (nT == 4) ? 1 : 2;
+  // ---- prediction ----
+  if (mode == 0) {  // planar, intrapred.h:261-285
+    const int tr = B(1 + nT), bl = B(-1 - nT);
+    for (int p = 0; p < npass; p++) {
+      const int o = lane + 32 * p, x = o & (nT - 1), y = (o >> log2) & (nT - 1);
+      const int l = B(-1 - y), t = B(1 + x);
+      int px = ((nT - 1 - x) * l + (x + 1) * tr + (nT - 1 - y) * t + (y + 1) * bl + nT) >> (log2 + 1);
+      if (o < nT * nT) {
+        if (res) px = clip_bd(px + res[o], bd);
+        dst[x + y * ts] = (P)px;
+      }
+    }
+  } else if (mode == 1) {  // DC, intrapred.h:288-322
+    const int i = lane - 2 * nT;
+    const bool in = (i >= 1 && i <= nT) || (i <= -1 && i >= -nT);
+    const int dc = (__reduce_add_sync(RC_FULL, in ? v : 0) + nT) >> (log2 + 1);
+    const bool edge = (cidx == 0);  // nT < 32 always here
+    const int b1 = B(1), bm1 = B(-1);
+    for (int p = 0; p < npass; p++) {
+      const int o = lane + 32 * p, x = o & (nT - 1), y = (o >> log2) & (nT - 1);
+      const int t = B(x + 1), l = B(-y - 1);
+      int px = dc;
+      if (edge) {
+        if (x == 0 && y == 0) px = (bm1 + 2 * dc + b1 + 2) >> 2;
+        else if (y == 0) px = (t + 3 * dc + 2) >> 2;
+        else if (x == 0) px = (l + 3 * dc + 2) >> 2;
+      }
+      if (o < nT * nT) {
+        if (res) px = clip_bd(px + res[o], bd);
+        dst[x + y * ts] = (P)px;
+      }
+    }
+  } else {  // angular, intrapred.h:330-433
+    const int angle = k_intra_angle[mode];
+    const bool vert = mode >= 18;
+    const int sgn = vert ? 1 : -1;
+    const int inv = (angle < 0) ? (int)k_inv_angle[mode - 11] : 0;
+    const bool bfilt = (cidx == 0 && !(tu.flags & B200_TU_NO_BOUNDARY_FILTER) && (mode == 26 || mode == 10));
+    const int b0 = B(0), b1 = B(1), bm1 = B(-1);
+    // ref[k] = border[sgn*k] for k >= 0, border[-sgn*((k*inv+128)>>8)] for the projected part k < 0
+    auto R = [&](int k) -> int { return B(k >= 0 ? sgn * k : -sgn * ((k * inv + 128) >> 8)); };
+    for (int p = 0; p < npass; p++) {
+      const int o = lane + 32 * p, x = o & (nT - 1), y = (o >> log2) & (nT - 1);
+      const int a = vert ? y : x, b = vert ? x : y;
+      const int idx = ((a + 1) * angle) >> 5, fact = ((a + 1) * angle) & 31;
+      const int r1 = R(b + idx + 1), r2 = R(b + idx + 2);
+      const int l = B(-1 - y), t = B(1 + x);
+      int px = fact ? ((32 - fact) * r1 + fact * r2 + 16) >> 5 : r1;
+      if (bfilt) {
+        if (mode == 26 && x == 0) px = clip_bd(b1 + ((l - b0) >> 1), bd);
+        if (mode == 10 && y == 0) px = clip_bd(bm1 + ((t - b0) >> 1), bd);
+      }
+      if (o < nT * nT) {
+        if (res) px = clip_bd(px + res[o], bd);
+        dst[x + y * ts] = (P)px;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// -------------------------------------------------------------------------------------------------
+// Large TUs (nT = 16 or 32): neighbour samples straight from the picture plane in global memory (`gsrc` = the
+// TU's top-left sample, row stride gstride; .cg loads: written by other SMs during this launch), prediction to
+// `dst` in shared memory (row stride nT), border arrays in shared memory.
+// -------------------------------------------------------------------------------------------------
+template <typename P>
+__device__ void tu_intra_large(const b200_tu& tu, const P* gsrc, int gstride, P* dst, int bd, int bd_luma, uint32_t pic_flags, bool filter_plane,
+                               P* b0mem, P* b1mem, int lane)
+{
+  const int log2 = tu.log2_size, nT = 1 << log2, mode = tu.intra_mode, cidx = tu.cidx, dstride = nT;
   const uint64_t avail = tu.avail;
   P* b0 = b0mem + 2 * 32 + 2;  // centre element; valid [-2nT, 2nT]
   P* b1 = b1mem + 2 * 32 + 2;
@@ -240,9 +342,9 @@ __device__ void tu_intra(const b200_tu& tu, const P* gsrc, int gstride, P* dst, 
       bool av = false;
       int v = 0;
       if (s < total) {
-        if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc - 1 + r * gstride); }
-        else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc - 1 - gstride); }
-        else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc + c - gstride); }
+        if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = (int)__ldcg(gsrc - 1 + r * gstride); }
+        else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = (int)__ldcg(gsrc - 1 - gstride); }
+        else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = (int)__ldcg(gsrc + c - gstride); }
       }
       const unsigned m = __ballot_sync(0xffffffffu, av);
       if (!any && m) { first_val = __shfl_sync(0xffffffffu, v, __ffs(m) - 1); any = true; }
@@ -256,9 +358,9 @@ __device__ void tu_intra(const b200_tu& tu, const P* gsrc, int gstride, P* dst, 
         bool av = false;
         int v = 0;
         if (s < total) {
-          if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc - 1 + r * gstride); }
-          else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc - 1 - gstride); }
-          else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = ld_nb<GLOBAL_SRC, P>(gsrc + c - gstride); }
+          if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = (int)__ldcg(gsrc - 1 + r * gstride); }
+          else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = (int)__ldcg(gsrc - 1 - gstride); }
+          else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = (int)__ldcg(gsrc + c - gstride); }
         }
         const unsigned m = __ballot_sync(0xffffffffu, av);
         const unsigned below = m & ((2u << lane) - 1u);  // available lanes <= this one
@@ -273,9 +375,9 @@ __device__ void tu_intra(const b200_tu& tu, const P* gsrc, int gstride, P* dst, 
   __syncwarp();
   // ---- smoothing (intrapred.h:185-258) ----
   const P* bsrc = b0;
-  if (filter_plane && mode != 1 && nT != 4) {
+  if (filter_plane && mode != 1) {
     const int d = min(abs(mode - 26), abs(mode - 10));
-    const bool filt = (nT == 8) ? (d > 7) : (nT == 16) ? (d > 1) : (d > 0);
+    const bool filt = (nT == 16) ? (d > 1) : (d > 0);
     if (filt) {
       const bool strong = (pic_flags & B200_PIC_STRONG_INTRA_SMOOTHING) && cidx == 0 && nT == 32 &&
                           abs((int)b0[0] + (int)b0[64] - 2 * (int)b0[32]) < (1 << (bd_luma - 5)) &&
@@ -306,7 +408,7 @@ __device__ void tu_intra(const b200_tu& tu, const P* gsrc, int gstride, P* dst, 
   } else if (mode == 1) {
     int part = 0;
     for (int i = lane; i < nT; i += 32) part += (int)bsrc[i + 1] + (int)bsrc[-i - 1];
-    const int dc = (warp_sum(part) + nT) >> (log2 + 1);
+    const int dc = (__reduce_add_sync(RC_FULL, part) + nT) >> (log2 + 1);
     const bool edge = (cidx == 0 && nT < 32);
     for (int o = lane; o < nT * nT; o += 32) {
       const int x = o & (nT - 1), y = o >> log2;
@@ -324,14 +426,15 @@ __device__ void tu_intra(const b200_tu& tu, const P* gsrc, int gstride, P* dst, 
     const int sgn = vert ? 1 : -1;
     P* ref = bfree;  // ref[x] valid on [-nT, 2nT]
     const int last = (nT * angle) >> 5;
+    const int inv = (angle < 0) ? (int)k_inv_angle[mode - 11] : 0;
+    const bool project = (angle < 0) && (last < -1);
     for (int s = lane; s <= 3 * nT; s += 32) {
       const int x = s - nT;
-      int v = 0;
-      bool w = false;
-      if (x >= 0 && x <= nT) { v = bsrc[sgn * x]; w = true; }
-      else if (x > nT) { if (angle >= 0) { v = bsrc[sgn * x]; w = true; } }
-      else if (angle < 0 && last < -1 && x >= last) { v = bsrc[-sgn * ((x * (int)k_inv_angle[mode - 11] + 128) >> 8)]; w = true; }
-      if (w) ref[x] = (P)v;
+      // ref[x] = border[sgn*x] for 0 <= x <= nT (and up to 2nT for non-negative angles); for negative angles the part
+      // x in [last, -1] is projected from the other border through the inverse angle (intrapred.h:352-364,392-404)
+      const bool w = (x >= 0) ? (x <= nT || angle >= 0) : (project && x >= last);
+      const int idx = (x >= 0) ? sgn * x : -sgn * ((x * inv + 128) >> 8);
+      if (w) ref[x] = bsrc[idx];
     }
     __syncwarp();
     const bool bfilt = (cidx == 0 && nT < 32 && !(tu.flags & B200_TU_NO_BOUNDARY_FILTER) && (mode == 26 || mode == 10));
@@ -350,12 +453,22 @@ __device__ void tu_intra(const b200_tu& tu, const P* gsrc, int gstride, P* dst, 
   __syncwarp();
 }
 
+// TU block -> picture plane, 4-byte units (TU rows are 4-byte aligned: x multiple of 4 samples)
+template <typename P>
+__device__ __forceinline__ void block_store(const P* blk, uint8_t* plane, int pitch, int x, int y, int nT, int lane)
+{
+  const int upr = nT * (int)sizeof(P) / 4;
+  for (int o = lane; o < nT * upr; o += 32) {
+    const int r = o / upr, u = o % upr;
+    *reinterpret_cast<uint32_t*>(plane + (size_t)(y + r) * pitch + (size_t)x * sizeof(P) + 4 * u) = reinterpret_cast<const uint32_t*>(blk + r * nT)[u];
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 template <typename P>
 __global__ void __launch_bounds__(RC_THREADS) k_residual(DevPic pic, ReconArgs args)
 {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  ReconSmem<P>& sm = *reinterpret_cast<ReconSmem<P>*>(smem_raw);
+  __shared__ ResidualSmem sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 32 * 32; i += RC_THREADS) sm.dct[i >> 5][i & 31] = c_dct[i >> 5][i & 31];
   __syncthreads();
@@ -363,19 +476,17 @@ __global__ void __launch_bounds__(RC_THREADS) k_residual(DevPic pic, ReconArgs a
   if (idx >= args.n_list) return;
   const b200_tu tu = args.tus[args.list[idx]];
   const int c = tu.cidx, nT = 1 << tu.log2_size;
-  P* blk = sm.blk[warp];
+  P* dst = row_ptr<P>(pic.cur[c], pic.pitch[c], tu.y) + tu.x;
+  const int dstride = pic.pitch[c] / (int)sizeof(P);
   if (tu.flags & B200_TU_PCM) {  // slice.cc:4211-4255
     for (int i = lane; i < tu.n_coeff; i += 32) {
       const b200_coeff co = args.coeffs[tu.coeff_off + i];
-      blk[co.pos] = (P)(uint16_t)co.level;
+      dst[(co.pos & (nT - 1)) + (co.pos >> tu.log2_size) * dstride] = (P)(uint16_t)co.level;
     }
-    __syncwarp();
   } else {
-    block_load<P>(blk, pic.cur[c], pic.pitch[c], tu.x, tu.y, nT, lane);
-    __syncwarp();
-    tu_residual<P>(tu, args.coeffs + tu.coeff_off, args.scaling, blk, nT, c ? pic.bd_c : pic.bd_y, sm.coef[warp], sm.g[warp], sm.dct, lane);
+    tu_residual<P, false>(tu, args.coeffs + tu.coeff_off, args.scaling, dst, dstride, nullptr, c ? pic.bd_c : pic.bd_y, sm.coef[warp], sm.g[warp],
+                          sm.dct, lane);
   }
-  block_store<P>(blk, pic.cur[c], pic.pitch[c], tu.x, tu.y, nT, lane);
 }
 
 __global__ void k_mark_pending(ReconArgs args)
@@ -389,14 +500,11 @@ __global__ void k_mark_pending(ReconArgs args)
     for (int i = 0; i < n4; i++) p[j * args.pend_w[c] + i] = 1;
 }
 
-// Dependency set of a task = the distinct 4x4 units OUTSIDE its region that its TUs' availability masks let them
-// read.  For a region (G x G, G <= 16) these are at most 2G/4 units left of it, the corner and 2G/4 units above it;
-// for a single large TU nT/2 + 1 + nT/2 units.  Each lane owns one such unit (lane 0.. : left column top-down,
-// then the corner, then the top row left-to-right), so one poll round is a single load instruction per warp.
+// Dependency set of a task = the distinct 4x4 units OUTSIDE its frame (region, or the single large TU) that its
+// TUs' availability masks let them read: at most `span` units left of it (top-down), the corner and `span`
+// units above it (left-to-right), span = 2G/4 for a region, nT/2 for a large TU.
 __device__ __forceinline__ void dep_units_of(const b200_tu& tu, int rx, int ry, int span, uint64_t& left, bool& corner, uint64_t& top)
 {
-  // span = number of units along one side of the dependency frame (2G/4 for a region, nT/2 for a single TU);
-  // (rx, ry) = frame origin in samples.  Adds this TU's needed external units.
   const int nT = 1 << tu.log2_size, half = nT / 2;
   const int ux0 = (tu.x - rx) >> 2, uy0 = (tu.y - ry) >> 2;  // TU position inside the frame, in units
   const uint64_t avail = tu.avail;
@@ -416,22 +524,24 @@ template <typename P>
 __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  ReconSmem<P>& sm = *reinterpret_cast<ReconSmem<P>*>(smem_raw);
+  IntraSmem<P>& sm = *reinterpret_cast<IntraSmem<P>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 32 * 32; i += RC_THREADS) sm.dct[i >> 5][i & 31] = c_dct[i >> 5][i & 31];
   __syncthreads();
+  b200_tu* tus = sm.tu_s[warp];
+  b200_coeff* cos = sm.co_s[warp];
+  int32_t* res = sm.res[warp];
+  P* blk = sm.blk[warp];
   // Persistent warps: each warp keeps claiming the next task of the topological order.
   for (;;) {
     unsigned t = 0;
     if (lane == 0) t = atomicAdd(args.ticket, 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
+    t = __shfl_sync(RC_FULL, t, 0);
     if (t >= (unsigned)args.n_task) return;
     unsigned long long tr_t0 = 0, tr_c0 = 0, tr_c1 = 0;
     if (args.trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0)); tr_c0 = clock64(); }
     const uint32_t first = args.task_start[t], count = min(args.task_start[t + 1] - first, 16u);
-    // ---- prefetch everything that does not depend on the neighbours: TU records and coefficient lists ----
-    b200_tu* tus = sm.tu_s[warp];
-    b200_coeff* cos = sm.co_s[warp];
+    // ---- everything that does not depend on the neighbours: TU records, coefficient lists, residuals ----
     if (lane < (int)count) tus[lane] = args.tus[args.list[first + lane]];
     __syncwarp();
     {
@@ -449,32 +559,40 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     const int c = tu0.cidx, sh = c ? 1 : 0;
     const int bd = c ? pic.bd_c : pic.bd_y;
     const int G = 16 >> sh;  // region size in this plane's samples
-    const bool region = count > 1 || (1 << tu0.log2_size) < G;
-    const int rx = tu0.x & ~(G - 1), ry = tu0.y & ~(G - 1);
+    const bool region = (1 << tu0.log2_size) <= 8;
+    const int rx = region ? tu0.x & ~(G - 1) : tu0.x, ry = region ? tu0.y & ~(G - 1) : tu0.y;  // dependency frame origin
     const bool filter_plane = !(pic.flags & B200_PIC_INTRA_SMOOTHING_OFF) && (c == 0 || pic.chroma == 3);
-    const int gstride = pic.pitch[c] / (int)sizeof(P);
     const int pwid = c ? pic.cw : pic.w, phei = c ? pic.ch : pic.h;
-    P* blk = sm.blk[warp];
     __syncwarp();
+    {
+      int cbase = 0, rbase = 0;
+      for (uint32_t i = 0; i < count; i++) {
+        const b200_tu& tu = tus[i];
+        if (tu.flags & B200_TU_CBF)
+          tu_residual<P, true>(tu, (cbase + tu.n_coeff <= RC_CO_STAGE) ? cos + cbase : args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rbase,
+                               bd, sm.coef[warp], sm.g[warp], sm.dct, lane);
+        cbase += tu.n_coeff;
+        rbase += 1 << (2 * tu.log2_size);
+      }
+    }
     // ---- wait: one flag per distinct external neighbour unit, one lane each ----
     {
       const int span = region ? (2 * G) >> 2 : (1 << tu0.log2_size) >> 1;
-      const int fx = region ? rx : tu0.x, fy = region ? ry : tu0.y;
       uint64_t left = 0, top = 0;
       bool corner = false;
-      for (uint32_t i = 0; i < count; i++) dep_units_of(tus[i], fx, fy, span, left, corner, top);
+      for (uint32_t i = 0; i < count; i++) dep_units_of(tus[i], rx, ry, span, left, corner, top);
       const int pw = args.pend_w[c];
-      const uint8_t* pend = args.pend[c] + (fy >> 2) * pw + (fx >> 2);
+      const uint8_t* pend = args.pend[c] + (ry >> 2) * pw + (rx >> 2);
       const volatile uint8_t* f = nullptr;
       if (lane < span) { if ((left >> lane) & 1) f = pend + lane * pw - 1; }
       else if (lane == span) { if (corner) f = pend - pw - 1; }
       else if (lane - span - 1 < span) { if ((top >> (lane - span - 1)) & 1) f = pend - pw + (lane - span - 1); }
-      const volatile uint8_t* f2 = nullptr;  // single 32x32 TU: 33 units, lane 0 takes the last top unit as well
+      const volatile uint8_t* f2 = nullptr;  // 32x32 TU: 33 units, lane 0 takes the last top unit as well
       if (span == 16 && lane == 0 && ((top >> 15) & 1)) f2 = pend - pw + 15;
       unsigned ns = 32;
       for (;;) {
         const bool busy = (f && *f) || (f2 && *f2);
-        if (!__any_sync(0xffffffffu, busy)) break;
+        if (!__any_sync(RC_FULL, busy)) break;
         __nanosleep(ns);
         if (ns < 256) ns *= 2;
       }
@@ -483,12 +601,15 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     if (args.trace) tr_c1 = clock64();
 
     if (!region) {
-      // ---- one TU at least as large as a region: borders straight from the picture ----
+      // ---- one large TU: borders straight from the picture ----
       const int nT = 1 << tu0.log2_size;
+      const int gstride = pic.pitch[c] / (int)sizeof(P);
       const P* gsrc = row_ptr<P>(pic.cur[c], pic.pitch[c], tu0.y) + tu0.x;
-      tu_intra<true, P>(tu0, gsrc, gstride, blk, nT, bd, pic.bd_y, pic.flags, filter_plane, sm.border[warp][0], sm.border[warp][1], lane);
-      if (tu0.flags & B200_TU_CBF)
-        tu_residual<P>(tu0, tu0.n_coeff <= RC_CO_STAGE ? cos : args.coeffs + tu0.coeff_off, args.scaling, blk, nT, bd, sm.coef[warp], sm.g[warp], sm.dct, lane);
+      tu_intra_large<P>(tu0, gsrc, gstride, blk, bd, pic.bd_y, pic.flags, filter_plane, sm.border[warp][0], sm.border[warp][1], lane);
+      if (tu0.flags & B200_TU_CBF) {
+        for (int o = lane; o < nT * nT; o += 32) blk[o] = (P)clip_bd((int)blk[o] + res[o], bd);
+        __syncwarp();
+      }
       block_store<P>(blk, pic.cur[c], pic.pitch[c], tu0.x, tu0.y, nT, lane);
     } else {
       // ---- a region of small TUs: stage region + top row (2G) + left column (2G) in shared memory, run the TUs in order ----
@@ -506,15 +627,11 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
         for (int y = lane; y < 2 * G; y += 32)
           if (ry + y < phei) tile[y * TS - 1] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx - 1);
       __syncwarp();
-      int base = 0;
+      int rbase = 0;
       for (uint32_t i = 0; i < count; i++) {
-        const b200_tu tu = tus[i];
-        P* dst = tile + (tu.y - ry) * TS + (tu.x - rx);
-        tu_intra<false, P>(tu, dst, TS, dst, TS, bd, pic.bd_y, pic.flags, filter_plane, sm.border[warp][0], sm.border[warp][1], lane);
-        if (tu.flags & B200_TU_CBF)
-          tu_residual<P>(tu, (base + tu.n_coeff <= RC_CO_STAGE) ? cos + base : args.coeffs + tu.coeff_off, args.scaling, dst, TS, bd, sm.coef[warp],
-                         sm.g[warp], sm.dct, lane);
-        base += tu.n_coeff;
+        const b200_tu& tu = tus[i];
+        tu_intra_small<P>(tu, tile + (tu.y - ry) * TS + (tu.x - rx), TS, bd, filter_plane, (tu.flags & B200_TU_CBF) ? res + rbase : nullptr, lane);
+        rbase += 1 << (2 * tu.log2_size);
       }
       for (int o = lane; o < gw * gh; o += 32) {
         const int x = o % gw, y = o / gw;
@@ -524,7 +641,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     __threadfence();  // release: samples before flags
     __syncwarp();
     for (uint32_t i = 0; i < count; i++) {
-      const b200_tu tu = tus[i];
+      const b200_tu& tu = tus[i];
       const int n4 = 1 << (tu.log2_size - 2), pw = args.pend_w[c];
       uint8_t* pend = args.pend[c] + (tu.y >> 2) * pw + (tu.x >> 2);
       for (int o = lane; o < n4 * n4; o += 32) *reinterpret_cast<volatile uint8_t*>(pend + (o / n4) * pw + (o % n4)) = 0;
