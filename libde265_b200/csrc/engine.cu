@@ -18,6 +18,7 @@
 #include "dev_common.cuh"
 #include "kernels_filter.cuh"
 #include "kernels_mc.cuh"
+#include "kernels_mc8.cuh"
 #include "kernels_recon.cuh"
 
 // ---- error reporting -----------------------------------------------------------------------------
@@ -146,6 +147,43 @@ static int init_tables(int device)
       m[k][n] = (int8_t)(sign * T[j]);
     }
   CU(cudaMemcpyToSymbol(c_dct, m, sizeof(m)));
+  // ---- packed tap tables of the 8-bit MC kernel (kernels_mc8.cuh) from the HEVC interpolation taps ----
+  {
+    static const int8_t q[4][8] = {{0, 0, 0, 1, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+    static const int8_t ep[8][4] = {{0, 1, 0, 0},     {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
+                                    {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
+    auto pack = [](int b0, int b1, int b2, int b3) { return (uint32_t)(uint8_t)b0 | ((uint32_t)(uint8_t)b1 << 8) | ((uint32_t)(uint8_t)b2 << 16) | ((uint32_t)(uint8_t)b3 << 24); };
+    uint32_t qh[5][4][3], qv[4][5], eh[9][4][2], ev[8][3];
+    for (int f = 0; f < 5; f++) {
+      int8_t t[8];
+      for (int i = 0; i < 8; i++) t[i] = (f == 4) ? (int8_t)(i == 3 ? 64 : 0) : q[f][i];
+      for (int j = 0; j < 4; j++)
+        for (int k = 0; k < 3; k++) {
+          int b[4];
+          for (int i = 0; i < 4; i++) { const int idx = 4 * k + i - j; b[i] = (idx >= 0 && idx < 8) ? t[idx] : 0; }
+          qh[f][j][k] = pack(b[0], b[1], b[2], b[3]);
+        }
+      if (f < 4) {
+        qv[f][0] = pack(t[0], t[1], t[2], t[3]); qv[f][1] = pack(t[4], t[5], t[6], t[7]);
+        qv[f][2] = pack(0, t[0], t[1], t[2]);    qv[f][3] = pack(t[3], t[4], t[5], t[6]); qv[f][4] = pack(t[7], 0, 0, 0);
+      }
+    }
+    for (int f = 0; f < 9; f++) {
+      int8_t t[4];
+      for (int i = 0; i < 4; i++) t[i] = (f == 8) ? (int8_t)(i == 1 ? 64 : 0) : ep[f][i];
+      for (int j = 0; j < 4; j++)
+        for (int k = 0; k < 2; k++) {
+          int b[4];
+          for (int i = 0; i < 4; i++) { const int idx = 4 * k + i - j; b[i] = (idx >= 0 && idx < 4) ? t[idx] : 0; }
+          eh[f][j][k] = pack(b[0], b[1], b[2], b[3]);
+        }
+      if (f < 8) { ev[f][0] = pack(t[0], t[1], t[2], t[3]); ev[f][1] = pack(0, t[0], t[1], t[2]); ev[f][2] = pack(t[3], 0, 0, 0); }
+    }
+    CU(cudaMemcpyToSymbol(c_qh, qh, sizeof(qh)));
+    CU(cudaMemcpyToSymbol(c_qv, qv, sizeof(qv)));
+    CU(cudaMemcpyToSymbol(c_eh, eh, sizeof(eh)));
+    CU(cudaMemcpyToSymbol(c_ev, ev, sizeof(ev)));
+  }
   if (device < 64) g_tables_ready[device] = true;
   return B200_OK;
 }
@@ -282,8 +320,12 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
   const bool run_deblock = L.run_deblock, run_sao = L.run_sao;
   if (en->timing) CU(cudaEventRecord(en->ev[1], st));
   if (n_tiles > 0) {
-    k_inter_pred<P><<<(n_tiles + 3) / 4, 128, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
+    if (sizeof(P) == 1)
+      k_inter_pred8<<<(n_tiles + 3) / 4, 128, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
                                                          (const uint32_t*)(dbase + off[12]), n_tiles);
+    else
+      k_inter_pred<P><<<(n_tiles + 3) / 4, 128, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
+                                                           (const uint32_t*)(dbase + off[12]), n_tiles);
     en->launches++;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[2], st));
