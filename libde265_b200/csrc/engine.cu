@@ -153,7 +153,8 @@ static int init_tables(int device)
     static const int8_t ep[8][4] = {{0, 1, 0, 0},     {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
                                     {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
     auto pack = [](int b0, int b1, int b2, int b3) { return (uint32_t)(uint8_t)b0 | ((uint32_t)(uint8_t)b1 << 8) | ((uint32_t)(uint8_t)b2 << 16) | ((uint32_t)(uint8_t)b3 << 24); };
-    uint32_t qh[5][4][3], qv[4][5], eh[9][4][2], ev[8][3];
+    static Mc8Tables tb;
+    auto& qh = tb.qh; auto& qv = tb.qv; auto& eh = tb.eh; auto& ev = tb.ev;
     for (int f = 0; f < 5; f++) {
       int8_t t[8];
       for (int i = 0; i < 8; i++) t[i] = (f == 4) ? (int8_t)(i == 3 ? 64 : 0) : q[f][i];
@@ -179,10 +180,7 @@ static int init_tables(int device)
         }
       if (f < 8) { ev[f][0] = pack(t[0], t[1], t[2], t[3]); ev[f][1] = pack(0, t[0], t[1], t[2]); ev[f][2] = pack(t[3], 0, 0, 0); }
     }
-    CU(cudaMemcpyToSymbol(c_qh, qh, sizeof(qh)));
-    CU(cudaMemcpyToSymbol(c_qv, qv, sizeof(qv)));
-    CU(cudaMemcpyToSymbol(c_eh, eh, sizeof(eh)));
-    CU(cudaMemcpyToSymbol(c_ev, ev, sizeof(ev)));
+    CU(cudaMemcpyToSymbol(c_mc8, &tb, sizeof(tb)));
   }
   if (device < 64) g_tables_ready[device] = true;
   return B200_OK;
@@ -321,7 +319,7 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
   if (en->timing) CU(cudaEventRecord(en->ev[1], st));
   if (n_tiles > 0) {
     if (sizeof(P) == 1)
-      k_inter_pred8<<<(n_tiles + 3) / 4, 128, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
+      k_inter_pred8<<<std::min((n_tiles + MC8_UNITS_PER_CTA - 1) / MC8_UNITS_PER_CTA, en->num_sms * 5), MC8_WARPS * 32, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
                                                          (const uint32_t*)(dbase + off[12]), n_tiles);
     else
       k_inter_pred<P><<<(n_tiles + 3) / 4, 128, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
@@ -397,8 +395,8 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
   }
   if (en->timing) CU(cudaEventRecord(en->ev[4], st));
   if (run_sao) {
-    dim3 grid((dp.w + 255) / 256, dp.h, dp.chroma ? 3 : 1);
-    k_sao<P><<<grid, 256, 0, st>>>(dp, fa);
+    dim3 grid((dp.w / 8 + 127) / 128, dp.h, dp.chroma ? 3 : 1);
+    k_sao<P><<<grid, 128, 0, st>>>(dp, fa);
     en->launches++;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[5], st));
@@ -428,6 +426,7 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
 
   std::vector<uint32_t>& tiles = en->tiles;
   tiles.clear();
+  const bool wide = p.bit_depth_luma > 8;  // same rule as the launch_picture<P> dispatch
   for (uint32_t i = 0; i < pic->n_pu; i++) {
     const b200_pu& pu = pic->pus[i];
     if (pu.w == 0 || pu.h == 0 || pu.w > 64 || pu.h > 64 || (pu.w & 3) || (pu.h & 3) || (pu.x & 3) || (pu.y & 3) ||
@@ -436,8 +435,13 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
     if ((pu.flags & B200_PU_WEIGHTED) && pu.wt_idx >= pic->n_weights) return set_err(B200_ERR_INVALID, "PU %u weight index", i);
     if (pu.ref_slot[0] >= B200_MAX_SLOTS || pu.ref_slot[1] >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "PU %u reference slot", i);
     if (!(pu.flags & (B200_PU_PRED_L0 | B200_PU_PRED_L1))) continue;
-    for (int ty = 0; ty * MC_TILE < pu.h; ty++)
-      for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
+    if (wide) {  // 16-bit path: <= 16x16 tiles, one warp each (kernels_mc.cuh)
+      for (int ty = 0; ty * MC_TILE < pu.h; ty++)
+        for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
+    } else {     // 8-bit path: <= 8x16 units, one quarter-warp each (kernels_mc8.cuh)
+      for (int uy = 0; uy * MC8_UH < pu.h; uy++)
+        for (int ux = 0; ux * MC8_UW < pu.w; ux++) tiles.push_back(MC8_UNIT(i, ux, uy));
+    }
   }
   L->n_tiles = (int)tiles.size();
   // ---- TU validation + work lists: list_a = non-intra TUs with work, list_b = intra TUs in topological order

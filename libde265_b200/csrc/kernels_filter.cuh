@@ -9,6 +9,8 @@
 //   exactly like sao.cc:327-382), copying samples that SAO leaves untouched.  Replaces apply_sao_internal
 //   (sao.cc:28-263).
 #pragma once
+#include <type_traits>
+
 #include "dev_common.cuh"
 
 struct FilterArgs {
@@ -141,62 +143,132 @@ __global__ void __launch_bounds__(128) k_deblock(DevPic pic, FilterArgs a)
 }
 
 // -------------------------------------------------------------------------------------------------
+// One SAO sample (sao.cc:103-262).  xC/yC = CTB origin in this plane, i/j = position inside the CTB.
 template <typename P>
-__global__ void __launch_bounds__(256) k_sao(DevPic pic, FilterArgs a)
+__device__ __forceinline__ int sao_sample(const DevPic& pic, const FilterArgs& a, const b200_ctb_info& ci, int c, int sh, int x, int y, int v,
+                                          int width, int height, int type, int ctbshift)
+{
+  const int bd = c ? pic.bd_c : pic.bd_y, maxv = (1 << bd) - 1;
+  if (nofilt_at(pic, a, x << sh, y << sh)) return v;
+  if (type == 2) {
+    const int cls = (ci.sao_eo_class >> (2 * c)) & 3;
+    const int hx0 = (cls == 1) ? 0 : (cls == 3) ? 1 : -1, hx1 = -hx0;
+    const int vy0 = (cls == 0) ? 0 : -1, vy1 = -vy0;
+    const int S = 1 << ctbshift;
+    const int xC = (x >> ctbshift) << ctbshift, yC = (y >> ctbshift) << ctbshift;
+    const int ctbW = min(S, width - xC), ctbH = min(S, height - yC);
+    const int i = x - xC, j = y - yC;
+    if (i == 0 || j == 0 || i == ctbW - 1 || j == ctbH - 1) {
+      // sao.cc:49: slice address of the CTB looked up with COMPONENT coordinates (reference quirk, kept)
+      const int ctb_addr = (int)slice_at(pic, a, min(xC, pic.w - 1), min(yC, pic.h - 1)).slice_addr_rs;
+      const b200_slice_info& sc = slice_at(pic, a, x << sh, y << sh);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int xS = x + (k ? hx1 : hx0), yS = y + (k ? vy1 : vy0);
+        if (xS < 0 || yS < 0 || xS >= width || yS >= height) return v;
+        const b200_ctb_info& cn = a.ctbs[((xS << sh) >> pic.log2ctb) + ((yS << sh) >> pic.log2ctb) * pic.wctb];
+        const b200_slice_info& sn = a.slices[cn.slice_idx];
+        if ((int)sn.slice_addr_rs < ctb_addr && !(sc.flags & B200_SLICE_LF_ACROSS_SLICES)) return v;
+        if ((int)sn.slice_addr_rs > ctb_addr && !(sn.flags & B200_SLICE_LF_ACROSS_SLICES)) return v;
+        if (!(pic.flags & B200_PIC_LF_ACROSS_TILES) && cn.tile_id != ci.tile_id) return v;
+      }
+    }
+    const int na = row_ptr<P>(pic.cur[c], pic.pitch[c], y + vy0)[x + hx0];
+    const int nb = row_ptr<P>(pic.cur[c], pic.pitch[c], y + vy1)[x + hx1];
+    const int e = ((v > na) - (v < na)) + ((v > nb) - (v < nb));
+    const int off = (e == 0) ? 0 : ci.sao_offset[c][e < 0 ? e + 2 : e + 1];  // [-2,-1,1,2] -> offsets 0,1,2,3 (sao.cc:95-100)
+    return clip3i(0, maxv, v + off);
+  }
+  const int band = clip3i(0, maxv, v) >> (bd - 5);
+  const int k = (band - ci.sao_band_pos[c]) & 31;
+  return (k < 4) ? clip3i(0, maxv, v + ci.sao_offset[c][k]) : v;
+}
+
+// One thread per 8 horizontally adjacent samples (8 never straddles a CTB: CTB widths are multiples of 8 in
+// every plane).  SAO-off groups move as one 8/16-byte vector.  Edge-offset groups read their neighbour rows as one
+// vector + one scalar each and classify all 8 samples in registers; only samples on a CTB border (where the
+// slice/tile/picture availability rules of sao.cc:125-190 apply) and groups touching a no-filter block (pcm/bypass)
+// take the per-sample path.
+template <typename P>
+__global__ void __launch_bounds__(128) k_sao(DevPic pic, FilterArgs a)
 {
   const int c = blockIdx.z;  // colour plane
   const int sh = c ? 1 : 0;
   const int width = c ? pic.cw : pic.w, height = c ? pic.ch : pic.h;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 8, y = blockIdx.y;
   if (x >= width || y >= height) return;
-  const P* in = row_ptr<P>(pic.cur[c], pic.pitch[c], y);
-  P* out = row_ptr<P>(pic.out[c], pic.pitch[c], y);
-  const int v = in[x];
-  int res = v;
+  const int pitch = pic.pitch[c];
+  const P* in = row_ptr<P>(pic.cur[c], pitch, y) + x;
+  P* out = row_ptr<P>(pic.out[c], pitch, y) + x;
   const int ctbshift = pic.log2ctb - sh;
-  const int xCtb = x >> ctbshift, yCtb = y >> ctbshift;
-  const b200_ctb_info& ci = a.ctbs[xCtb + yCtb * pic.wctb];
+  const b200_ctb_info ci = a.ctbs[(x >> ctbshift) + (y >> ctbshift) * pic.wctb];
   const b200_slice_info& sl = a.slices[ci.slice_idx];
   const bool on = c ? (sl.flags & B200_SLICE_SAO_CHROMA) : (sl.flags & B200_SLICE_SAO_LUMA);
-  const int type = (ci.sao_type >> (2 * c)) & 3;
-  if (on && type != 0 && !nofilt_at(pic, a, x << sh, y << sh)) {
-    const int bd = c ? pic.bd_c : pic.bd_y, maxv = (1 << bd) - 1;
-    if (type == 2) {
+  const int type = on ? (ci.sao_type >> (2 * c)) & 3 : 0;
+  const int n = min(8, width - x);  // picture widths are multiples of 4 in every plane (8 luma)
+  typedef typename std::conditional<sizeof(P) == 1, uint2, uint4>::type V8;  // 8 samples
+  union Vec { V8 q; P s[8]; };
+  Vec v, r;
+  v.q = *reinterpret_cast<const V8*>(in);  // the row pitch leaves >= 16 bytes after the last sample
+  if (type == 0) {
+    if (n == 8) *reinterpret_cast<V8*>(out) = v.q;
+    else
+      for (int k = 0; k < n; k++) out[k] = v.s[k];
+    return;
+  }
+  const int bd = c ? pic.bd_c : pic.bd_y, maxv = (1 << bd) - 1;
+  // no-filter flags of the 8x8 luma blocks under this group (1 block for luma, 2 for chroma)
+  const uint8_t* nfp = a.nofilt_map + ((x << sh) >> 3) + ((y << sh) >> 3) * pic.w8;
+  const bool nf = (nfp[0] & 1) || (sh && ((x << sh) >> 3) + 1 < pic.w8 && (nfp[1] & 1));
+  const int S = 1 << ctbshift;
+  const int xC = (x >> ctbshift) << ctbshift, yC = (y >> ctbshift) << ctbshift;
+  const int ctbW = min(S, width - xC), ctbH = min(S, height - yC);
+  unsigned slow = nf ? 0xFFu : 0u;  // samples that must take the per-sample path
+  const int o0 = ci.sao_offset[c][0], o1 = ci.sao_offset[c][1], o2 = ci.sao_offset[c][2], o3 = ci.sao_offset[c][3];
+  if (type == 2) {
+    const int j = y - yC;
+    if (j == 0 || j == ctbH - 1) slow = 0xFFu;
+    if (x == xC) slow |= 1u;
+    if (x + 8 >= xC + ctbW) slow |= 1u << (xC + ctbW - 1 - x);
+    if (slow != 0xFFu) {
       const int cls = (ci.sao_eo_class >> (2 * c)) & 3;
-      const int hx0 = (cls == 1) ? 0 : (cls == 3) ? 1 : -1, hx1 = -hx0;
-      const int vy0 = (cls == 0) ? 0 : -1, vy1 = -vy0;
-      const int S = 1 << ctbshift;
-      const int xC = xCtb << ctbshift, yC = yCtb << ctbshift;
-      const int ctbW = min(S, width - xC), ctbH = min(S, height - yC);
-      const int i = x - xC, j = y - yC;
-      bool skip = false;
-      if (i == 0 || j == 0 || i == ctbW - 1 || j == ctbH - 1) {
-        // sao.cc:49: slice address of the CTB looked up with COMPONENT coordinates (reference quirk, kept)
-        const int ctb_addr = (int)slice_at(pic, a, min(xC, pic.w - 1), min(yC, pic.h - 1)).slice_addr_rs;
-        const b200_slice_info& sc = slice_at(pic, a, x << sh, y << sh);
+      const int hx0 = (cls == 1) ? 0 : (cls == 3) ? 1 : -1;
+      const int vy0 = (cls == 0) ? 0 : -1;
+      // neighbour a = (x+hx0, y+vy0), neighbour b = (x-hx0, y-vy0); rows y+-1 are inside the CTB here
+      const P* ra = row_ptr<P>(pic.cur[c], pitch, y + vy0) + x;
+      const P* rb = row_ptr<P>(pic.cur[c], pitch, y - vy0) + x;
+      Vec va, vb;
+      va.q = *reinterpret_cast<const V8*>(ra);
+      vb.q = *reinterpret_cast<const V8*>(rb);
+      const int ea = hx0 ? ra[hx0 < 0 ? -1 : 8] : 0, eb = hx0 ? rb[hx0 < 0 ? 8 : -1] : 0;
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-          const int xS = x + (k ? hx1 : hx0), yS = y + (k ? vy1 : vy0);
-          if (xS < 0 || yS < 0 || xS >= width || yS >= height) { skip = true; break; }
-          const b200_ctb_info& cn = a.ctbs[((xS << sh) >> pic.log2ctb) + ((yS << sh) >> pic.log2ctb) * pic.wctb];
-          const b200_slice_info& sn = a.slices[cn.slice_idx];
-          if ((int)sn.slice_addr_rs < ctb_addr && !(sc.flags & B200_SLICE_LF_ACROSS_SLICES)) { skip = true; break; }
-          if ((int)sn.slice_addr_rs > ctb_addr && !(sn.flags & B200_SLICE_LF_ACROSS_SLICES)) { skip = true; break; }
-          if (!(pic.flags & B200_PIC_LF_ACROSS_TILES) && cn.tile_id != ci.tile_id) { skip = true; break; }
-        }
+      for (int k = 0; k < 8; k++) {
+        int na, nb;
+        if (hx0 == 0) { na = va.s[k]; nb = vb.s[k]; }
+        else if (hx0 < 0) { na = k ? va.s[k - 1] : ea; nb = (k < 7) ? vb.s[k + 1] : eb; }
+        else { na = (k < 7) ? va.s[k + 1] : ea; nb = k ? vb.s[k - 1] : eb; }
+        const int s = v.s[k];
+        const int e = ((s > na) - (s < na)) + ((s > nb) - (s < nb));
+        const int off = (e == -2) ? o0 : (e == -1) ? o1 : (e == 1) ? o2 : (e == 2) ? o3 : 0;  // sao.cc:95-100
+        r.s[k] = (P)clip3i(0, maxv, s + off);
       }
-      if (!skip) {
-        const int na = row_ptr<P>(pic.cur[c], pic.pitch[c], y + vy0)[x + hx0];
-        const int nb = row_ptr<P>(pic.cur[c], pic.pitch[c], y + vy1)[x + hx1];
-        const int e = ((v > na) - (v < na)) + ((v > nb) - (v < nb));
-        const int off = (e == 0) ? 0 : ci.sao_offset[c][e < 0 ? e + 2 : e + 1];  // [-2,-1,1,2] -> offsets 0,1,2,3 (sao.cc:95-100)
-        res = clip3i(0, maxv, v + off);
-      }
-    } else {
-      const int band = clip3i(0, maxv, v) >> (bd - 5);
-      const int k = (band - ci.sao_band_pos[c]) & 31;
-      if (k < 4) res = clip3i(0, maxv, v + ci.sao_offset[c][k]);
+    }
+  } else {
+    const int pos = ci.sao_band_pos[c];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int s = v.s[k];
+      const int b = ((s >> (bd - 5)) - pos) & 31;
+      const int off = (b == 0) ? o0 : (b == 1) ? o1 : (b == 2) ? o2 : (b == 3) ? o3 : 0;
+      r.s[k] = (P)clip3i(0, maxv, s + off);
     }
   }
-  out[x] = (P)res;
+  if (slow) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (((slow >> k) & 1) && k < n) r.s[k] = (P)sao_sample<P>(pic, a, ci, c, sh, x + k, y, v.s[k], width, height, type, ctbshift);
+  }
+  if (n == 8) *reinterpret_cast<V8*>(out) = r.q;
+  else
+    for (int k = 0; k < n; k++) out[k] = r.s[k];
 }

@@ -1,35 +1,49 @@
 // kernels_mc8.cuh — 8-bit inter prediction with packed integer dot products (the roofline-graded kernel).
 //
-// Same contract as k_inter_pred<uint8_t> (kernels_mc.cuh): one warp per <=16x16 luma tile (+ its 8x8 Cb/Cr),
-// luma 8-tap / chroma 4-tap separable interpolation (motion.cc:48-282, fallback-motion.cc:262-636) fused with the
-// four weighting modes (fallback-motion.cc:33-256).  What changes is the arithmetic:
+// Replaces mc_luma / mc_chroma (motion.cc:48-282), every put_hevc_qpel/epel table entry
+// (fallback-motion.cc:262-636) and the four put_*_pred functions (fallback-motion.cc:33-256) for one picture's
+// worth of PUs in ONE launch.
+//
+// Work split: the host cuts every PU into UNITS of at most 8x16 luma samples (+ the co-located 4x8 Cb/Cr samples).
+// A quarter-warp (8 lanes) owns a unit, so a warp works on four independent units at once and lanes stay busy
+// for every PU size down to 8x8.  CTAs are persistent (grid-stride over units) and keep the packed tap tables in
+// shared memory (each quarter-warp may need a different phase).
 //
 //   pass 1 (horizontal, on bytes): a lane produces 4 adjacent outputs of one row from 12 source bytes held in three
-//     32-bit registers (aligned 16-byte load + funnel shifts); output j is  dp4a(b0,T[j][0]) + dp4a(b1,T[j][1]) +
-//     dp4a(b2,T[j][2])  with the 8 taps pre-shifted by j bytes into T (11 dp4a per 4 outputs instead of 32 MACs).
-//     Results (|v| < 2^15, no shift at 8 bit) go to a per-warp shared-memory strip stored COLUMN-major, so that two
+//     32-bit registers (four aligned 32-bit loads + funnel shifts); output j is dp4a(b0,T[j][0]) + dp4a(b1,T[j][1]) +
+//     dp4a(b2,T[j][2]) with the 8 taps pre-shifted by j bytes into T (11 dp4a per 4 outputs instead of 32 MACs).
+//     Results (|v| < 2^15, no shift at 8 bit) go to the unit's shared-memory strip stored COLUMN-major, so that two
 //     vertically adjacent samples share a 32-bit word.
-//   pass 2 (vertical, on int16 pairs): a lane produces 8 rows of one column from 8 words of the strip with dp2a
-//     (4 dp2a for even rows, 5 for odd rows: the taps are pre-packed for both parities), then >> 6, int16 wrap
-//     (SURVEY App. A.1), weighting, clip, byte stores.
-//   Integer phases use the identity tap, so there is one code path; a zero vertical phase skips pass 2 and its 7 halo rows.
-//   Tiles whose reference window crosses the left/right picture edge build their 12 bytes from clamped loads
+//   pass 2 (vertical, on int16 pairs): a lane owns one column and produces 8 rows at a time from 8 strip words with
+//     dp2a (4 per even row, 5 per odd row: taps pre-packed for both parities), then >> 6 with int16 wrap
+//      as one bit-field extract, the weighting (all four modes through one branch-free
+//     multiply-add-shift-offset form), saturation and byte stores.
+//   Integer phases use the identity tap, so there is one code path; a zero vertical phase skips pass 2 and its halo rows.
+//   Units whose reference window crosses the left/right picture edge build their source bytes from clamped loads
 //   (motion.cc:147-153); rows are always clamped.
 //
-// Tap tables live in constant memory and are built on the host from the HEVC filter taps (engine.cu init_tables).
+// Tap tables are built on the host from the HEVC filter taps (engine.cu init_tables) into constant memory.
 #pragma once
 #include "dev_common.cuh"
-#include "kernels_mc.cuh"
 
-#define MC8_CS 26   // luma strip: int16 column stride (>= 23 rows, even, spreads columns over banks)
-#define MC8_CCS 12  // chroma strip column stride (>= 11 rows)
-#define MC8_STRIP (16 * MC8_CS + 2 * 8 * MC8_CCS)
+#define MC8_UW 8      // unit width  (luma samples)
+#define MC8_UH 16     // unit height
+#define MC8_CS 24     // luma strip: int16 column stride (>= 23 rows, even)
+#define MC8_CCS 12    // chroma strip column stride (>= 11 rows)
+#define MC8_USTRIP (8 * MC8_CS + 2 * 4 * MC8_CCS + 8)  // one unit, one list (+8: bank skew between units)
+#define MC8_WARPS 4
+#define MC8_UNITS_PER_CTA (MC8_WARPS * 4)
 
-// [frac 0..3, 4 = integer position with gain 64][output j][word]
-__constant__ uint32_t c_qh[5][4][3];
-__constant__ uint32_t c_qv[4][5];      // [frac][A,B (even rows), C,D,E (odd rows)]
-__constant__ uint32_t c_eh[9][4][2];   // [frac 0..7, 8 = integer with gain 64][output j][word]
-__constant__ uint32_t c_ev[8][3];      // [frac][A (even), C,D (odd)]
+// unit word: bits 0-19 PU index, 20-22 x offset / 8, 23-24 y offset / 16
+#define MC8_UNIT(pu, ux, uy) ((uint32_t)(pu) | ((uint32_t)(ux) << 20) | ((uint32_t)(uy) << 23))
+
+struct Mc8Tables {
+  uint32_t qh[5][4][3];  // [frac 0..3, 4 = integer position with gain 64][output j][word]
+  uint32_t qv[4][5];     // [frac][A,B (even rows), C,D,E (odd rows)]
+  uint32_t eh[9][4][2];  // [frac 0..7, 8 = integer with gain 64][output j][word]
+  uint32_t ev[8][3];     // [frac][A (even), C,D (odd)]
+};
+__constant__ Mc8Tables c_mc8;
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
 {
@@ -49,21 +63,31 @@ __device__ __forceinline__ int dp2a_hi_ss(uint32_t a, uint32_t b, int c)
   asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+// (v >> shift) wrapped to int16: one signed bit-field extract of 16 bits at `shift`
+__device__ __forceinline__ int shr_wrap16(int v, int shift)
+{
+  int d;
+  asm("bfe.s32 %0, %1, %2, 16;" : "=r"(d) : "r"(v), "r"(shift));
+  return d;
+}
+__device__ __forceinline__ int sat_u8(int v)
+{
+  int d;
+  asm("cvt.sat.u8.s32 %0, %1;" : "=r"(d) : "r"(v));
+  return d;
+}
 
-// Source bytes starting at column xb of row `row` (row pointer is 256-byte aligned; pitch >= width + 16).
-template <int NW>  // NW = number of 32-bit words of source bytes wanted (3 for luma: 12 bytes, 2 for chroma: 8 bytes)
-__device__ __forceinline__ void load_bytes(const uint8_t* row, int xb, int pw, bool clampx, uint32_t (&b)[3])
+// Source bytes starting at column xb of `row` (row pointer 256-byte aligned; pitch >= width + 16).
+template <int NW>  // 3 words (12 bytes) for luma, 2 words (8 bytes) for chroma
+__device__ __forceinline__ void mc8_load(const uint8_t* row, int xb, int pw, bool clampx, uint32_t (&b)[3])
 {
   if (!clampx) {
-    const int xa = xb & ~3, sh = (xb & 3) * 8;
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(row + xa);
+    const int sh = (xb & 3) * 8;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(row + (xb & ~3));
     const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
     b[0] = __funnelshift_r(w0, w1, sh);
     b[1] = __funnelshift_r(w1, w2, sh);
-    if (NW == 3) {
-      const uint32_t w3 = p[3];
-      b[2] = __funnelshift_r(w2, w3, sh);
-    }
+    if (NW == 3) b[2] = __funnelshift_r(w2, p[3], sh);
   } else {
 #pragma unroll
     for (int k = 0; k < NW; k++) {
@@ -75,208 +99,256 @@ __device__ __forceinline__ void load_bytes(const uint8_t* row, int xb, int pw, b
   }
 }
 
-// pass 1 for one plane of one list: strip[col * CS + r] = sum_k taps[k] * ref[y][x + col + k - before]
-template <int CS, bool LUMA>
-__device__ __forceinline__ void mc8_hpass(int16_t* strip, const uint8_t* ref, int pitch, int pw, int ph, int x_int, int y_int, int tw, int nrows,
-                                          int before_rows, const uint32_t* taps /* [4][LUMA ? 3 : 2] */, int r0, int rstep, int g, bool active)
+// Branch-free weighting: out = sat_u8(((a*w0 + b*w1 + rnd) >> shift) + off) covers fallback-motion.cc:33-256:
+//   uni          (a + 32) >> 6                                   w0=1 w1=0 rnd=32            shift=6        off=0
+//   bi average   (a + b + 64) >> 7                               w0=1 w1=1 rnd=64            shift=7        off=0
+//   uni explicit ((a*w + 2^(wd-1)) >> wd) + o                    w0=w w1=0 rnd=2^(wd-1)      shift=wd       off=o
+//   bi explicit  (a*w0 + b*w1 + ((o0+o1+1) << wd)) >> (wd+1)     w0,w1     rnd=(o0+o1+1)<<wd shift=wd+1     off=0
+struct Mc8Weight {
+  int w0, w1, rnd, shift, off;
+};
+__device__ __forceinline__ Mc8Weight mc8_weight(bool bi, bool wgt, int lu, const b200_weight_entry* __restrict__ wp_, int c)
 {
-  constexpr int BEFORE = LUMA ? 3 : 1;
-  constexpr int NW = LUMA ? 3 : 2;
-  const int ng = (tw + 3) >> 2;
-  const int xb = x_int + 4 * g - BEFORE;
-  // the whole window of the tile is inside the picture horizontally?
-  const bool clampx = (x_int - BEFORE < 0) || (x_int + tw + (LUMA ? 4 : 2) > pw - 1);
-  uint32_t t[4][NW];
-#pragma unroll
-  for (int j = 0; j < 4; j++)
-#pragma unroll
-    for (int k = 0; k < NW; k++) t[j][k] = taps[j * NW + k];
-  if (!active || g >= ng) return;
-  for (int r = r0; r < nrows; r += rstep) {
-    const int ya = clip3i(0, ph - 1, y_int + r - before_rows);
-    uint32_t b[3];
-    load_bytes<NW>(ref + (size_t)ya * pitch, xb, pw, clampx, b);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      int s = dp4a_us(b[0], t[j][0], 0);
-      s = dp4a_us(b[1], t[j][1], s);
-      if (LUMA && j > 0) s = dp4a_us(b[2], t[j][2], s);
-      if (4 * g + j < tw) strip[(4 * g + j) * CS + r] = (int16_t)s;
-    }
-  }
-}
-
-// pass 2 for NOUT consecutive rows of one column; w[] = the strip words of that column starting at the first output row
-// (row pair per word).  LUMA: NOUT = 8, 8 words; chroma: NOUT = 4, 4 words.  Returns int16-wrapped values.
-template <bool LUMA>
-__device__ __forceinline__ void mc8_vpass(const uint32_t* w, const uint32_t* tv, int shift, int* out)
-{
-  if (LUMA) {
-    const uint32_t A = tv[0], B = tv[1], C = tv[2], D = tv[3], E = tv[4];
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-      int e = dp2a_lo_ss(w[m], A, 0);
-      e = dp2a_hi_ss(w[m + 1], A, e);
-      e = dp2a_lo_ss(w[m + 2], B, e);
-      e = dp2a_hi_ss(w[m + 3], B, e);
-      int o = dp2a_lo_ss(w[m], C, 0);
-      o = dp2a_hi_ss(w[m + 1], C, o);
-      o = dp2a_lo_ss(w[m + 2], D, o);
-      o = dp2a_hi_ss(w[m + 3], D, o);
-      o = dp2a_lo_ss(w[m + 4], E, o);
-      out[2 * m] = (int)(int16_t)(e >> shift);
-      out[2 * m + 1] = (int)(int16_t)(o >> shift);
-    }
+  Mc8Weight r;
+  if (!wgt) {
+    r.w0 = 1; r.w1 = bi ? 1 : 0; r.rnd = bi ? 64 : 32; r.shift = bi ? 7 : 6; r.off = 0;
   } else {
-    const uint32_t A = tv[0], C = tv[1], D = tv[2];
-#pragma unroll
-    for (int m = 0; m < 2; m++) {
-      int e = dp2a_lo_ss(w[m], A, 0);
-      e = dp2a_hi_ss(w[m + 1], A, e);
-      int o = dp2a_lo_ss(w[m], C, 0);
-      o = dp2a_hi_ss(w[m + 1], C, o);
-      o = dp2a_lo_ss(w[m + 2], D, o);
-      out[2 * m] = (int)(int16_t)(e >> shift);
-      out[2 * m + 1] = (int)(int16_t)(o >> shift);
-    }
+    const int wd = c ? wp_->log2wd_chroma : wp_->log2wd_luma;
+    if (bi) { r.w0 = wp_->w[0][c]; r.w1 = wp_->w[1][c]; r.rnd = (int)((unsigned)(wp_->o[0][c] + wp_->o[1][c] + 1) << wd); r.shift = wd + 1; r.off = 0; }
+    else { r.w0 = wp_->w[lu][c]; r.w1 = 0; r.rnd = 1 << (wd - 1); r.shift = wd; r.off = wp_->o[lu][c]; }
   }
+  return r;
 }
 
-__global__ void __launch_bounds__(128) k_inter_pred8(DevPic pic, RefTable refs, const b200_pu* __restrict__ pus,
-                                                     const b200_weight_entry* __restrict__ wts, const uint32_t* __restrict__ tiles, int n_tiles)
+__global__ void __launch_bounds__(MC8_WARPS * 32, 5)
+k_inter_pred8(DevPic pic, RefTable refs, const b200_pu* __restrict__ pus, const b200_weight_entry* __restrict__ wts,
+              const uint32_t* __restrict__ units, int n_units)
 {
-  __shared__ __align__(16) int16_t s_strip[4][2][MC8_STRIP + 8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * 4 + warp;
-  if (tile >= n_tiles) return;
-  const uint32_t t = tiles[tile];
-  const b200_pu pu = pus[t & 0xFFFFF];
-  const int tx = (t >> 20) & 3, ty = (t >> 22) & 3;
-  const int x0 = pu.x + tx * MC_TILE, y0 = pu.y + ty * MC_TILE;
-  const int tw = min(MC_TILE, pu.w - tx * MC_TILE), th = min(MC_TILE, pu.h - ty * MC_TILE);
-  const bool use0 = pu.flags & B200_PU_PRED_L0, use1 = pu.flags & B200_PU_PRED_L1;
-  const bool has_chroma = pic.chroma != 0;
-  const int cwd = tw >> 1, chh = th >> 1;
-
-  int yf[2] = {0, 0}, yfc[2] = {0, 0}, sh_l[2] = {0, 0}, sh_c[2] = {0, 0};
-  bool missing[2] = {false, false};
-#pragma unroll
-  for (int l = 0; l < 2; l++) {
-    if (!(l ? use1 : use0)) continue;
-    const int slot = pu.ref_slot[l];
-    const uint8_t* ry = (slot >= 0) ? refs.plane[slot][0] : nullptr;
-    if (!ry) { missing[l] = true; continue; }
-    const int mvx = pu.mv[l][0], mvy = pu.mv[l][1];
-    int16_t* strip = s_strip[warp][l];
-    {
-      const int xf = mvx & 3;
-      yf[l] = mvy & 3;
-      const int hidx = (xf == 0 && yf[l] == 0) ? 4 : xf;  // full-sample: gain 64 (<< 6), no second pass
-      sh_l[l] = (xf && yf[l]) ? 6 : 0;
-      const int nrows = th + (yf[l] ? 7 : 0);
-      mc8_hpass<MC8_CS, true>(strip, ry, pic.pitch[0], pic.w, pic.h, x0 + (mvx >> 2), y0 + (mvy >> 2), tw, nrows, yf[l] ? 3 : 0, &c_qh[hidx][0][0],
-                              lane >> 2, 8, lane & 3, true);
-    }
-    if (has_chroma) {
-      const int xfc = mvx & 7;
-      yfc[l] = mvy & 7;
-      const int hidx = (xfc == 0 && yfc[l] == 0) ? 8 : xfc;
-      sh_c[l] = (xfc && yfc[l]) ? 6 : 0;
-      const int nrows = chh + (yfc[l] ? 3 : 0);
-      const int pl = (lane >> 1) & 1;
-      mc8_hpass<MC8_CCS, false>(strip + 16 * MC8_CS + pl * 8 * MC8_CCS, refs.plane[slot][1 + pl], pic.pitch[1], pic.cw, pic.ch, (x0 >> 1) + (mvx >> 3),
-                                (y0 >> 1) + (mvy >> 3), cwd, nrows, yfc[l] ? 1 : 0, &c_eh[hidx][0][0], lane >> 2, 8, lane & 1, true);
-    }
-  }
-  __syncwarp();
-
-  // weighting parameters per plane (motion.cc:493-688)
-  const bool bi = use0 && use1;
-  const int lu = use0 ? 0 : 1;
-  const bool wgt = pu.flags & B200_PU_WEIGHTED;
-  b200_weight_entry we;
-  if (wgt) we = wts[pu.wt_idx];
-
-  // ---- luma: lane -> (column, 8-row half) ----
+  __shared__ Mc8Tables s_tab;
+  __shared__ __align__(16) int16_t s_strip[MC8_WARPS][4][2][MC8_USTRIP];
   {
-    const int c = lane & 15, h = lane >> 4;
-    if (c < tw && 8 * h < th) {
-      int v[2][8];
-#pragma unroll
-      for (int l = 0; l < 2; l++) {
-        if (!(l ? use1 : use0)) continue;
-        if (missing[l]) {
-#pragma unroll
-          for (int k = 0; k < 8; k++) v[l][k] = 1 << 13;
-          continue;
-        }
-        const uint32_t* col = reinterpret_cast<const uint32_t*>(s_strip[warp][l] + c * MC8_CS + 8 * h);
-        uint32_t w[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) w[k] = col[k];
-        if (yf[l]) {
-          mc8_vpass<true>(w, c_qv[yf[l]], sh_l[l], v[l]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            v[l][2 * k] = (int)(int16_t)(w[k] & 0xffff);
-            v[l][2 * k + 1] = (int)(int16_t)(w[k] >> 16);
-          }
-        }
-      }
-      WeightParams wp;
-      wp.mode = (bi ? 1 : 0) + (wgt ? 2 : 0);
-      if (wgt) {
-        wp.log2wd = we.log2wd_luma;
-        if (bi) { wp.w0 = we.w[0][0]; wp.o0 = we.o[0][0]; wp.w1 = we.w[1][0]; wp.o1 = we.o[1][0]; }
-        else { wp.w0 = we.w[lu][0]; wp.o0 = we.o[lu][0]; wp.w1 = 0; wp.o1 = 0; }
-      }
-      uint8_t* dst = pic.cur[0] + (size_t)(y0 + 8 * h) * pic.pitch[0] + x0 + c;
-      const int nr = min(8, th - 8 * h);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        if (k < nr) dst[(size_t)k * pic.pitch[0]] = (uint8_t)weight_sample(bi ? v[0][k] : v[lu][k], bi ? v[1][k] : 0, wp, 8);
-    }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_mc8);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(Mc8Tables) / 4); i += MC8_WARPS * 32) dst[i] = src[i];
   }
-  // ---- chroma: lane -> (plane, column, 4-row half) ----
-  if (has_chroma) {
-    const int pl = lane >> 4, c = lane & 7, h = (lane >> 3) & 1;
-    if (c < cwd && 4 * h < chh) {
-      int v[2][4];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane >> 3, l8 = lane & 7;
+  const bool has_chroma = pic.chroma != 0;
+
+  for (int base = blockIdx.x * MC8_UNITS_PER_CTA; base < n_units; base += gridDim.x * MC8_UNITS_PER_CTA) {
+    const int u = base + warp * 4 + q;
+    const bool valid = u < n_units;
+    b200_pu pu;
+    int x0 = 0, y0 = 0, tw = 0, th = 0;
+    if (valid) {
+      const uint32_t uw = units[u];
+      pu = pus[uw & 0xFFFFF];
+      const int ux = (uw >> 20) & 7, uy = (uw >> 23) & 3;
+      x0 = pu.x + ux * MC8_UW; y0 = pu.y + uy * MC8_UH;
+      tw = min(MC8_UW, pu.w - ux * MC8_UW); th = min(MC8_UH, pu.h - uy * MC8_UH);
+    } else {
+      pu.flags = 0;
+    }
+    const bool use0 = pu.flags & B200_PU_PRED_L0, use1 = pu.flags & B200_PU_PRED_L1;
+    const int cwd = tw >> 1, chh = th >> 1;
+    int yf[2] = {0, 0}, yfc[2] = {0, 0};
+    bool missing[2] = {false, false};
+
+    // ================= pass 1: horizontal, both lists =================
 #pragma unroll
-      for (int l = 0; l < 2; l++) {
-        if (!(l ? use1 : use0)) continue;
-        if (missing[l]) {
+    for (int l = 0; l < 2; l++) {
+      const bool used = l ? use1 : use0;
+      const int slot = used ? pu.ref_slot[l] : -1;
+      const uint8_t* ry = (slot >= 0) ? refs.plane[slot][0] : nullptr;
+      missing[l] = used && !ry;
+      if (!ry) continue;
+      const int mvx = pu.mv[l][0], mvy = pu.mv[l][1];
+      int16_t* strip = s_strip[warp][q][l];
+      {  // ---- luma ----
+        const int xf = mvx & 3;
+        yf[l] = mvy & 3;
+        const uint32_t* tp = &s_tab.qh[(xf == 0 && yf[l] == 0) ? 4 : xf][0][0];  // full-sample position: gain 64 (<< 6), no second pass
+        uint32_t t[4][3];
 #pragma unroll
-          for (int k = 0; k < 4; k++) v[l][k] = 1 << 13;
-          continue;
-        }
-        const uint32_t* col = reinterpret_cast<const uint32_t*>(s_strip[warp][l] + 16 * MC8_CS + pl * 8 * MC8_CCS + c * MC8_CCS + 4 * h);
-        uint32_t w[4];
+        for (int j = 0; j < 4; j++)
 #pragma unroll
-        for (int k = 0; k < 4; k++) w[k] = col[k];
-        if (yfc[l]) {
-          mc8_vpass<false>(w, c_ev[yfc[l]], sh_c[l], v[l]);
-        } else {
+          for (int k = 0; k < 3; k++) t[j][k] = tp[j * 3 + k];
+        const int x_int = x0 + (mvx >> 2), y_int = y0 + (mvy >> 2) - (yf[l] ? 3 : 0);
+        const int nrows = th + (yf[l] ? 7 : 0);
+        const bool clampx = (x_int - 3 < 0) || (x_int + tw + 4 > pic.w - 1);
+        // lanes of the quarter-warp: two 4-sample groups x 4 rows per iteration (8-wide unit) or 8 rows (4-wide unit)
+        const bool two = tw > 4;
+        const int g = two ? (l8 & 1) : 0;
+        const int rstep = two ? 4 : 8;
+        const int xb = x_int + 4 * g - 3;
+        for (int r = two ? (l8 >> 1) : l8; r < nrows; r += rstep) {
+          const int ya = clip3i(0, pic.h - 1, y_int + r);
+          uint32_t b[3];
+          mc8_load<3>(ry + (size_t)ya * pic.pitch[0], xb, pic.w, clampx, b);
+          int16_t* o = strip + (4 * g) * MC8_CS + r;
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            v[l][2 * k] = (int)(int16_t)(w[k] & 0xffff);
-            v[l][2 * k + 1] = (int)(int16_t)(w[k] >> 16);
+          for (int j = 0; j < 4; j++) {
+            int s = dp4a_us(b[0], t[j][0], 0);
+            s = dp4a_us(b[1], t[j][1], s);
+            if (j > 0) s = dp4a_us(b[2], t[j][2], s);
+            o[j * MC8_CS] = (int16_t)s;
           }
         }
       }
-      WeightParams wp;
-      wp.mode = (bi ? 1 : 0) + (wgt ? 2 : 0);
-      if (wgt) {
-        wp.log2wd = we.log2wd_chroma;
-        if (bi) { wp.w0 = we.w[0][1 + pl]; wp.o0 = we.o[0][1 + pl]; wp.w1 = we.w[1][1 + pl]; wp.o1 = we.o[1][1 + pl]; }
-        else { wp.w0 = we.w[lu][1 + pl]; wp.o0 = we.o[lu][1 + pl]; wp.w1 = 0; wp.o1 = 0; }
-      }
-      uint8_t* dst = pic.cur[1 + pl] + (size_t)((y0 >> 1) + 4 * h) * pic.pitch[1 + pl] + (x0 >> 1) + c;
-      const int nr = min(4, chh - 4 * h);
+      if (has_chroma) {  // ---- chroma: lane -> (plane, row) ; 4:2:0: chroma mv in eighth samples = luma mv (motion.cc:196-206)
+        const int xfc = mvx & 7;
+        yfc[l] = mvy & 7;
+        const uint32_t* tp = &s_tab.eh[(xfc == 0 && yfc[l] == 0) ? 8 : xfc][0][0];
+        uint32_t t[4][2];
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (k < nr) dst[(size_t)k * pic.pitch[1 + pl]] = (uint8_t)weight_sample(bi ? v[0][k] : v[lu][k], bi ? v[1][k] : 0, wp, 8);
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int k = 0; k < 2; k++) t[j][k] = tp[j * 2 + k];
+        const int x_int = (x0 >> 1) + (mvx >> 3), y_int = (y0 >> 1) + (mvy >> 3) - (yfc[l] ? 1 : 0);
+        const int nrows = chh + (yfc[l] ? 3 : 0);
+        const bool clampx = (x_int - 1 < 0) || (x_int + cwd + 2 > pic.cw - 1);
+        const int pl = l8 & 1;
+        const uint8_t* rc = refs.plane[slot][1 + pl];
+        int16_t* cstrip = strip + 8 * MC8_CS + pl * 4 * MC8_CCS;
+        for (int r = l8 >> 1; r < nrows; r += 4) {
+          const int ya = clip3i(0, pic.ch - 1, y_int + r);
+          uint32_t b[3];
+          mc8_load<2>(rc + (size_t)ya * pic.pitch[1], x_int - 1, pic.cw, clampx, b);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            int s = dp4a_us(b[0], t[j][0], 0);
+            if (j > 0) s = dp4a_us(b[1], t[j][1], s);
+            cstrip[j * MC8_CCS + r] = (int16_t)s;
+          }
+        }
+      }
     }
+    __syncwarp();
+
+    // ================= pass 2: vertical + weighting + store =================
+    const bool bi = use0 && use1;
+    const int lu = use0 ? 0 : 1;
+    const bool wgt = pu.flags & B200_PU_WEIGHTED;
+    const b200_weight_entry* we = wts + (wgt ? pu.wt_idx : 0);
+    {  // ---- luma: lane -> column l8, two blocks of 8 rows ----
+      const Mc8Weight wp = mc8_weight(bi, wgt, lu, we, 0);
+      const int la = bi ? 0 : lu;  // list providing operand a
+      uint32_t tv[2][5];
+#pragma unroll
+      for (int l = 0; l < 2; l++)
+#pragma unroll
+        for (int k = 0; k < 5; k++) tv[l][k] = s_tab.qv[yf[l]][k];
+      const int shl[2] = {((pu.mv[0][0] & 3) && yf[0]) ? 6 : 0, ((pu.mv[1][0] & 3) && yf[1]) ? 6 : 0};
+      const bool act = valid && (use0 || use1) && l8 < tw;
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++) {
+        if (!(act && 8 * hb < th)) continue;
+        int v[2][8];
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+          const bool need = (l == la) || (bi && l == 1);
+          if (!need || missing[l]) {  // never-written slot: mid-grey intermediate (decctx.cc:1538-1583 conceals with grey)
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[l][k] = need ? (1 << 13) : 0;
+            continue;
+          }
+          const uint32_t* col = reinterpret_cast<const uint32_t*>(s_strip[warp][q][l] + l8 * MC8_CS + 8 * hb);
+          uint32_t w[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) w[k] = col[k];
+          if (yf[l]) {
+            const uint32_t A = tv[l][0], B = tv[l][1], C = tv[l][2], D = tv[l][3], E = tv[l][4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+              int e = dp2a_lo_ss(w[m], A, 0);
+              e = dp2a_hi_ss(w[m + 1], A, e);
+              e = dp2a_lo_ss(w[m + 2], B, e);
+              e = dp2a_hi_ss(w[m + 3], B, e);
+              int o = dp2a_lo_ss(w[m], C, 0);
+              o = dp2a_hi_ss(w[m + 1], C, o);
+              o = dp2a_lo_ss(w[m + 2], D, o);
+              o = dp2a_hi_ss(w[m + 3], D, o);
+              o = dp2a_lo_ss(w[m + 4], E, o);
+              v[l][2 * m] = shr_wrap16(e, shl[l]);
+              v[l][2 * m + 1] = shr_wrap16(o, shl[l]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              v[l][2 * k] = (int)(int16_t)(w[k] & 0xffff);
+              v[l][2 * k + 1] = (int)w[k] >> 16;
+            }
+          }
+        }
+        uint8_t* dst = pic.cur[0] + (size_t)(y0 + 8 * hb) * pic.pitch[0] + x0 + l8;
+        const int nr = th - 8 * hb;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int a = (la == 0) ? v[0][k] : v[1][k];
+          const int out = sat_u8(((a * wp.w0 + v[1][k] * wp.w1 + wp.rnd) >> wp.shift) + wp.off);
+          if (k < nr) dst[0] = (uint8_t)out;
+          dst += pic.pitch[0];
+        }
+      }
+    }
+    if (has_chroma) {  // ---- chroma: lane -> (plane l8 >> 2, column l8 & 3), two blocks of 4 rows ----
+      const int pl = l8 >> 2, c = l8 & 3;
+      const Mc8Weight wp = mc8_weight(bi, wgt, lu, we, 1 + pl);
+      const int la = bi ? 0 : lu;
+      uint32_t tv[2][3];
+#pragma unroll
+      for (int l = 0; l < 2; l++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) tv[l][k] = s_tab.ev[yfc[l]][k];
+      const int shl[2] = {((pu.mv[0][0] & 7) && yfc[0]) ? 6 : 0, ((pu.mv[1][0] & 7) && yfc[1]) ? 6 : 0};
+      const bool act = valid && (use0 || use1) && c < cwd;
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++) {
+        if (!(act && 4 * hb < chh)) continue;
+        int v[2][4];
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+          const bool need = (l == la) || (bi && l == 1);
+          if (!need || missing[l]) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[l][k] = need ? (1 << 13) : 0;
+            continue;
+          }
+          const uint32_t* col = reinterpret_cast<const uint32_t*>(s_strip[warp][q][l] + 8 * MC8_CS + pl * 4 * MC8_CCS + c * MC8_CCS + 4 * hb);
+          uint32_t w[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) w[k] = col[k];
+          if (yfc[l]) {
+            const uint32_t A = tv[l][0], C = tv[l][1], D = tv[l][2];
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+              int e = dp2a_lo_ss(w[m], A, 0);
+              e = dp2a_hi_ss(w[m + 1], A, e);
+              int o = dp2a_lo_ss(w[m], C, 0);
+              o = dp2a_hi_ss(w[m + 1], C, o);
+              o = dp2a_lo_ss(w[m + 2], D, o);
+              v[l][2 * m] = shr_wrap16(e, shl[l]);
+              v[l][2 * m + 1] = shr_wrap16(o, shl[l]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              v[l][2 * k] = (int)(int16_t)(w[k] & 0xffff);
+              v[l][2 * k + 1] = (int)w[k] >> 16;
+            }
+          }
+        }
+        uint8_t* dst = pic.cur[1 + pl] + (size_t)((y0 >> 1) + 4 * hb) * pic.pitch[1 + pl] + (x0 >> 1) + c;
+        const int nr = chh - 4 * hb;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int a = (la == 0) ? v[0][k] : v[1][k];
+          const int out = sat_u8(((a * wp.w0 + v[1][k] * wp.w1 + wp.rnd) >> wp.shift) + wp.off);
+          if (k < nr) dst[0] = (uint8_t)out;
+          dst += pic.pitch[1 + pl];
+        }
+      }
+    }
+    __syncwarp();  // the strips are reused by the next group of units
   }
 }
