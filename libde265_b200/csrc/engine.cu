@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -61,7 +62,9 @@ static void surface_free(Surface& s)
 
 static int bytes_per_sample(int bd) { return bd > 8 ? 2 : 1; }
 
-static int surface_ensure(Surface& s, const b200_pic_params& p)
+// New surfaces are zero-filled ON THE ENGINE'S STREAM (it is non-blocking: a memset on the legacy stream could land after
+// kernels launched later on the engine's stream).
+static int surface_ensure(Surface& s, const b200_pic_params& p, cudaStream_t st)
 {
   const int cw = p.chroma_format_idc ? p.width / 2 : 0, ch = p.chroma_format_idc ? p.height / 2 : 0;
   if (s.plane[0] && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc &&
@@ -78,10 +81,10 @@ static int surface_ensure(Surface& s, const b200_pic_params& p)
   s.pitch[0] = (int)align_up((size_t)p.width * bytes_per_sample(p.bit_depth_luma) + 16, 256);
   s.pitch[1] = s.pitch[2] = cw ? (int)align_up((size_t)cw * bytes_per_sample(p.bit_depth_chroma) + 16, 256) : 0;
   CU(cudaMalloc(&s.plane[0], (size_t)s.pitch[0] * p.height));
-  CU(cudaMemset(s.plane[0], 0, (size_t)s.pitch[0] * p.height));
+  CU(cudaMemsetAsync(s.plane[0], 0, (size_t)s.pitch[0] * p.height, st));
   for (int c = 1; c < 3 && cw; c++) {
     CU(cudaMalloc(&s.plane[c], (size_t)s.pitch[c] * ch));
-    CU(cudaMemset(s.plane[c], 0, (size_t)s.pitch[c] * ch));
+    CU(cudaMemsetAsync(s.plane[c], 0, (size_t)s.pitch[c] * ch, st));
   }
   return B200_OK;
 }
@@ -111,14 +114,14 @@ struct b200_engine {
   cudaEvent_t* ev = nullptr;     // events of the picture being submitted
   uint64_t launches = 0;
   // host scratch reused across pictures
-  std::vector<uint32_t> ctb_count, tiles, list_a, list_b, diag_count, task_of, task_first, task_start, task_order;
+  std::vector<uint32_t> ctb_count, tiles, list_a, list_a8, list_a4, list_b, diag_count, task_of, task_first, task_start, task_order;
 };
 
 #define TIMING_RING 256
 
 struct PicLayout {
   size_t off[14] = {}, total = 0;
-  int n_tiles = 0, n_a = 0, n_b = 0, n_task = 0;
+  int n_tiles = 0, n_a = 0, n_aw = 0, n_a8 = 0, n_b = 0, n_task = 0;
   bool run_deblock = false, run_sao = false, has_scaling = false;
   b200_pic_params params{};
   uint32_t n_tu = 0;
@@ -147,6 +150,25 @@ static int init_tables(int device)
       m[k][n] = (int8_t)(sign * T[j]);
     }
   CU(cudaMemcpyToSymbol(c_dct, m, sizeof(m)));
+  {  // packed transform matrices of the sub-warp residual paths (kernels_residual.cuh): 4 rows of one column per word
+    static ResTables rt;
+    auto col4 = [&](int nT, int jq, int i) {
+      uint32_t w = 0;
+      for (int b = 0; b < 4; b++) w |= (uint32_t)(uint8_t)m[(32 / nT) * (4 * jq + b)][i] << (8 * b);
+      return w;
+    };
+    for (int i = 0; i < 4; i++) rt.m4[i] = col4(4, 0, i);
+    for (int jq = 0; jq < 2; jq++) for (int i = 0; i < 8; i++) rt.m8[jq][i] = col4(8, jq, i);
+    for (int jq = 0; jq < 4; jq++) for (int i = 0; i < 16; i++) rt.m16[jq][i] = col4(16, jq, i);
+    for (int jq = 0; jq < 8; jq++) for (int i = 0; i < 32; i++) rt.m32[jq][i] = col4(32, jq, i);
+    // DST-VII: M[j][i] = round(128 * 2/3 * sin((2j+1)(i+1)pi/9)) (fallback-dct.cc:260-265 holds the same 16 numbers)
+    for (int i = 0; i < 4; i++) {
+      uint32_t w = 0;
+      for (int j = 0; j < 4; j++) w |= (uint32_t)(uint8_t)(int8_t)lround(128.0 * 2.0 / 3.0 * sin((2 * j + 1) * (i + 1) * M_PI / 9.0)) << (8 * j);
+      rt.dst4[i] = w;
+    }
+    CU(cudaMemcpyToSymbol(c_res, &rt, sizeof(rt)));
+  }
   // ---- packed tap tables of the 8-bit MC kernel (kernels_mc8.cuh) from the HEVC interpolation taps ----
   {
     static const int8_t q[4][8] = {{0, 0, 0, 1, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
@@ -309,6 +331,13 @@ static DevPic make_devpic(const b200_pic_params& p, const Surface& cur, const Su
   return d;
 }
 
+// sync_buf layout: [256 B ticket | pending map Y | Cb | Cr | (256-aligned) SAO neighbour-availability masks]
+static size_t sync_sao_offset(const b200_pic_params& p)
+{
+  const size_t cw4 = p.chroma_format_idc ? (size_t)((p.width / 2 + 3) / 4) : 0, ch4 = p.chroma_format_idc ? (size_t)((p.height / 2 + 3) / 4) : 0;
+  return (256 + (size_t)((p.width + 3) / 4) * ((p.height + 3) / 4) + 2 * cw4 * ch4 + 255) & ~(size_t)255;
+}
+
 template <typename P>
 static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp, const RefTable& refs, const uint8_t* dbase)
 {
@@ -342,7 +371,10 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
     if (L.n_a > 0) {
       ra.list = (const uint32_t*)(dbase + off[3]);
       ra.n_list = L.n_a;
-      k_residual<P><<<(L.n_a + RC_WARPS - 1) / RC_WARPS, RC_THREADS, 0, st>>>(dp, ra);
+      ra.n_listw = L.n_aw;
+      ra.n_list8 = L.n_a8;
+      const int items = L.n_aw + (L.n_a8 + 3) / 4 + (L.n_a - L.n_aw - L.n_a8 + 31) / 32;
+      k_residual<P><<<std::min((items + RC_WARPS - 1) / RC_WARPS, en->num_sms * 4), RC_THREADS, 0, st>>>(dp, ra);
       en->launches++;
     }
     ra.trace = nullptr;
@@ -395,9 +427,12 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
   }
   if (en->timing) CU(cudaEventRecord(en->ev[4], st));
   if (run_sao) {
+    uint16_t* avail = (uint16_t*)(en->sync_buf + sync_sao_offset(L.params));
+    fa.sao_avail = avail;
+    k_sao_prep<<<(2 * dp.wctb * dp.hctb + 127) / 128, 128, 0, st>>>(dp, fa, avail);
     dim3 grid((dp.w / 8 + 127) / 128, dp.h, dp.chroma ? 3 : 1);
     k_sao<P><<<grid, 128, 0, st>>>(dp, fa);
-    en->launches++;
+    en->launches += 2;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[5], st));
   CU(cudaGetLastError());
@@ -450,7 +485,10 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
     std::vector<uint32_t>& la = en->list_a;
     std::vector<uint32_t>& lb = en->list_b;
     std::vector<uint32_t>& dc = en->diag_count;
+    std::vector<uint32_t>&la8 = en->list_a8, &la4 = en->list_a4;
     la.clear();
+    la8.clear();
+    la4.clear();
     const int n_diag = wctb + 2 * hctb;
     dc.assign((size_t)n_diag + 1, 0);
     uint32_t n_intra = 0;
@@ -468,9 +506,16 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
         if (tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
         n_intra++;
       } else if (tu.flags & (B200_TU_CBF | B200_TU_PCM)) {
-        la.push_back(i);
+        // k_residual work classes: warp per TU (16x16, 32x32, PCM) | quarter-warp per 8x8 TU | lane per 4x4 TU
+        if ((tu.flags & B200_TU_PCM) || tu.log2_size > 3) la.push_back(i);
+        else if (tu.log2_size == 3) la8.push_back(i);
+        else la4.push_back(i);
       }
     }
+    L->n_aw = (int)la.size();
+    L->n_a8 = (int)la8.size();
+    la.insert(la.end(), la8.begin(), la8.end());
+    la.insert(la.end(), la4.begin(), la4.end());
     // ---- intra tasks: the TUs of one plane inside one aligned 16x16-luma / 8x8-chroma region (contiguous per plane in
     //      decode order); a TU at least as large as the region is a task of its own ----
     std::vector<uint32_t>& task_of = en->task_of;        // per intra TU (in decode order): task id
@@ -596,11 +641,11 @@ static int run_layout(b200_engine* en, const PicLayout& L, uint8_t* dbase, const
   const int S = 1 << p.log2_ctb_size;
   const int n_ctb = ((p.width + S - 1) / S) * ((p.height + S - 1) / S);
   Surface& dst = en->slot[p.dst_slot];
-  int rc = surface_ensure(dst, p);
+  int rc = surface_ensure(dst, p, en->stream);
   if (rc) return rc;
   Surface* cur = &dst;
   if (L.run_sao) {
-    rc = surface_ensure(en->scratch, p);
+    rc = surface_ensure(en->scratch, p, en->stream);
     if (rc) return rc;
     cur = &en->scratch;
   }
@@ -614,7 +659,8 @@ static int run_layout(b200_engine* en, const PicLayout& L, uint8_t* dbase, const
   }
   {
     const size_t cw4 = p.chroma_format_idc ? (size_t)((p.width / 2 + 3) / 4) : 0, ch4 = p.chroma_format_idc ? (size_t)((p.height / 2 + 3) / 4) : 0;
-    const size_t need = 256 + (size_t)((p.width + 3) / 4) * ((p.height + 3) / 4) + 2 * cw4 * ch4;
+    const size_t n_ctb = (size_t)((p.width + (1 << p.log2_ctb_size) - 1) >> p.log2_ctb_size) * ((p.height + (1 << p.log2_ctb_size) - 1) >> p.log2_ctb_size);
+    const size_t need = sync_sao_offset(p) + 2 * n_ctb * sizeof(uint16_t);
     if (en->sync_cap < need) {
       if (en->sync_buf) { CU(cudaStreamSynchronize(en->stream)); cudaFree(en->sync_buf); }
       en->sync_buf = nullptr;
@@ -718,7 +764,7 @@ extern "C" int b200_engine_fill_slot(b200_engine* en, int slot, const b200_pic_p
   if (rc) return rc;
   CU(cudaSetDevice(en->device));
   Surface& s = en->slot[slot];
-  rc = surface_ensure(s, *p);
+  rc = surface_ensure(s, *p, en->stream);
   if (rc) return rc;
   for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
     const int w = c ? s.cw : s.w, h = c ? s.ch : s.h;
@@ -739,7 +785,7 @@ extern "C" int b200_engine_upload_slot(b200_engine* en, int slot, const b200_pic
   if (rc) return rc;
   CU(cudaSetDevice(en->device));
   Surface& s = en->slot[slot];
-  rc = surface_ensure(s, *p);
+  rc = surface_ensure(s, *p, en->stream);
   if (rc) return rc;
   for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
     const int w = c ? s.cw : s.w, h = c ? s.ch : s.h, bps = bytes_per_sample(c ? s.bd_c : s.bd_y);

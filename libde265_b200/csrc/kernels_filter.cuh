@@ -19,6 +19,7 @@ struct FilterArgs {
   const uint8_t* nofilt_map;
   const b200_slice_info* slices;
   const b200_ctb_info* ctbs;
+  const uint16_t* sao_avail;  // k_sao_prep output: [luma CTBs | chroma CTBs]
 };
 
 __constant__ uint8_t k_tab_beta[52] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  6,  7,
@@ -184,11 +185,42 @@ __device__ __forceinline__ int sao_sample(const DevPic& pic, const FilterArgs& a
   return (k < 4) ? clip3i(0, maxv, v + ci.sao_offset[c][k]) : v;
 }
 
+// Per CTB and plane kind (0 luma, 1 chroma): which of the 8 neighbouring CTBs SAO edge classification may read
+// (sao.cc:125-190: picture bounds, slice order + slice_loop_filter_across_slices, tiles).  Bit (dy+1)*3 + (dx+1).
+// The "current" slice address is looked up with the CTB origin in COMPONENT coordinates (sao.cc:49, kept).
+__global__ void k_sao_prep(DevPic pic, FilterArgs a, uint16_t* __restrict__ avail)
+{
+  const int n_ctb = pic.wctb * pic.hctb;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n_ctb) return;
+  const int kind = t / n_ctb, ctb = t - kind * n_ctb;
+  const int cx = ctb % pic.wctb, cy = ctb / pic.wctb;
+  const b200_ctb_info& ci = a.ctbs[ctb];
+  const b200_slice_info& sc = a.slices[ci.slice_idx];
+  const int xC = (cx << pic.log2ctb) >> kind, yC = (cy << pic.log2ctb) >> kind;  // component coordinates
+  const int ctb_addr = (int)slice_at(pic, a, min(xC, pic.w - 1), min(yC, pic.h - 1)).slice_addr_rs;
+  // the centre bit follows the same rule: with the component-coordinate lookup the "current" slice address may differ from
+  // the CTB's own, and the reference applies the test to both neighbours of every sample on the CTB border
+  unsigned m = 0;
+  for (int dy = -1; dy <= 1; dy++)
+    for (int dx = -1; dx <= 1; dx++) {
+      const int nx = cx + dx, ny = cy + dy;
+      if (nx < 0 || ny < 0 || nx >= pic.wctb || ny >= pic.hctb) continue;
+      const b200_ctb_info& cn = a.ctbs[nx + ny * pic.wctb];
+      const b200_slice_info& sn = a.slices[cn.slice_idx];
+      if ((int)sn.slice_addr_rs < ctb_addr && !(sc.flags & B200_SLICE_LF_ACROSS_SLICES)) continue;
+      if ((int)sn.slice_addr_rs > ctb_addr && !(sn.flags & B200_SLICE_LF_ACROSS_SLICES)) continue;
+      if (!(pic.flags & B200_PIC_LF_ACROSS_TILES) && cn.tile_id != ci.tile_id) continue;
+      m |= 1u << ((dy + 1) * 3 + dx + 1);
+    }
+  avail[t] = (uint16_t)m;
+}
+
 // One thread per 8 horizontally adjacent samples (8 never straddles a CTB: CTB widths are multiples of 8 in
-// every plane).  SAO-off groups move as one 8/16-byte vector.  Edge-offset groups read their neighbour rows as one
-// vector + one scalar each and classify all 8 samples in registers; only samples on a CTB border (where the
-// slice/tile/picture availability rules of sao.cc:125-190 apply) and groups touching a no-filter block (pcm/bypass)
-// take the per-sample path.
+// every plane).  SAO-off groups move as one 8/16-byte vector.  Edge-offset groups read their two neighbour rows as
+// one vector + one scalar each and classify all 8 samples in registers, using the CTB's neighbour-availability
+// mask from k_sao_prep for samples whose neighbours lie in another CTB; only groups touching a no-filter block
+// (pcm / transquant bypass) take the per-sample path.
 template <typename P>
 __global__ void __launch_bounds__(128) k_sao(DevPic pic, FilterArgs a)
 {
@@ -201,74 +233,97 @@ __global__ void __launch_bounds__(128) k_sao(DevPic pic, FilterArgs a)
   const P* in = row_ptr<P>(pic.cur[c], pitch, y) + x;
   P* out = row_ptr<P>(pic.out[c], pitch, y) + x;
   const int ctbshift = pic.log2ctb - sh;
-  const b200_ctb_info ci = a.ctbs[(x >> ctbshift) + (y >> ctbshift) * pic.wctb];
-  const b200_slice_info& sl = a.slices[ci.slice_idx];
+  const int ctb = (x >> ctbshift) + (y >> ctbshift) * pic.wctb;
+  // the 24-byte CTB record as three 64-bit words (fields extracted with shifts: no dynamically indexed local copy)
+  const unsigned long long* cw = reinterpret_cast<const unsigned long long*>(a.ctbs + ctb);
+  const unsigned long long w0 = cw[0], w1 = cw[1], w2 = cw[2];
+  const b200_slice_info& sl = a.slices[w0 & 0xFFFF];
   const bool on = c ? (sl.flags & B200_SLICE_SAO_CHROMA) : (sl.flags & B200_SLICE_SAO_LUMA);
-  const int type = on ? (ci.sao_type >> (2 * c)) & 3 : 0;
+  const int type = on ? (int)(w0 >> (32 + 2 * c)) & 3 : 0;
   const int n = min(8, width - x);  // picture widths are multiples of 4 in every plane (8 luma)
   typedef typename std::conditional<sizeof(P) == 1, uint2, uint4>::type V8;  // 8 samples
   union Vec { V8 q; P s[8]; };
   Vec v, r;
   v.q = *reinterpret_cast<const V8*>(in);  // the row pitch leaves >= 16 bytes after the last sample
+  auto store = [&](const Vec& t) {  // n is 8, or 4 at the right edge of a plane whose width is 4 mod 8
+    if (n == 8) *reinterpret_cast<V8*>(out) = t.q;
+    else if (sizeof(P) == 1) *reinterpret_cast<uint32_t*>(out) = *reinterpret_cast<const uint32_t*>(&t.q);
+    else *reinterpret_cast<uint2*>(out) = *reinterpret_cast<const uint2*>(&t.q);
+  };
   if (type == 0) {
-    if (n == 8) *reinterpret_cast<V8*>(out) = v.q;
-    else
-      for (int k = 0; k < n; k++) out[k] = v.s[k];
+    store(v);
     return;
   }
   const int bd = c ? pic.bd_c : pic.bd_y, maxv = (1 << bd) - 1;
   // no-filter flags of the 8x8 luma blocks under this group (1 block for luma, 2 for chroma)
   const uint8_t* nfp = a.nofilt_map + ((x << sh) >> 3) + ((y << sh) >> 3) * pic.w8;
   const bool nf = (nfp[0] & 1) || (sh && ((x << sh) >> 3) + 1 < pic.w8 && (nfp[1] & 1));
-  const int S = 1 << ctbshift;
-  const int xC = (x >> ctbshift) << ctbshift, yC = (y >> ctbshift) << ctbshift;
-  const int ctbW = min(S, width - xC), ctbH = min(S, height - yC);
-  unsigned slow = nf ? 0xFFu : 0u;  // samples that must take the per-sample path
-  const int o0 = ci.sao_offset[c][0], o1 = ci.sao_offset[c][1], o2 = ci.sao_offset[c][2], o3 = ci.sao_offset[c][3];
-  if (type == 2) {
-    const int j = y - yC;
-    if (j == 0 || j == ctbH - 1) slow = 0xFFu;
-    if (x == xC) slow |= 1u;
-    if (x + 8 >= xC + ctbW) slow |= 1u << (xC + ctbW - 1 - x);
-    if (slow != 0xFFu) {
-      const int cls = (ci.sao_eo_class >> (2 * c)) & 3;
-      const int hx0 = (cls == 1) ? 0 : (cls == 3) ? 1 : -1;
-      const int vy0 = (cls == 0) ? 0 : -1;
-      // neighbour a = (x+hx0, y+vy0), neighbour b = (x-hx0, y-vy0); rows y+-1 are inside the CTB here
-      const P* ra = row_ptr<P>(pic.cur[c], pitch, y + vy0) + x;
-      const P* rb = row_ptr<P>(pic.cur[c], pitch, y - vy0) + x;
-      Vec va, vb;
-      va.q = *reinterpret_cast<const V8*>(ra);
-      vb.q = *reinterpret_cast<const V8*>(rb);
-      const int ea = hx0 ? ra[hx0 < 0 ? -1 : 8] : 0, eb = hx0 ? rb[hx0 < 0 ? 8 : -1] : 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        int na, nb;
-        if (hx0 == 0) { na = va.s[k]; nb = vb.s[k]; }
-        else if (hx0 < 0) { na = k ? va.s[k - 1] : ea; nb = (k < 7) ? vb.s[k + 1] : eb; }
-        else { na = (k < 7) ? va.s[k + 1] : ea; nb = k ? vb.s[k - 1] : eb; }
-        const int s = v.s[k];
-        const int e = ((s > na) - (s < na)) + ((s > nb) - (s < nb));
-        const int off = (e == -2) ? o0 : (e == -1) ? o1 : (e == 1) ? o2 : (e == 2) ? o3 : 0;  // sao.cc:95-100
-        r.s[k] = (P)clip3i(0, maxv, s + off);
-      }
-    }
-  } else {
-    const int pos = ci.sao_band_pos[c];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int s = v.s[k];
-      const int b = ((s >> (bd - 5)) - pos) & 31;
-      const int off = (b == 0) ? o0 : (b == 1) ? o1 : (b == 2) ? o2 : (b == 3) ? o3 : 0;
-      r.s[k] = (P)clip3i(0, maxv, s + off);
-    }
-  }
-  if (slow) {
+  const unsigned o4 = (c == 0) ? (unsigned)(w1 >> 8) : (c == 1) ? ((unsigned)(w1 >> 40) | ((unsigned)w2 << 24)) : (unsigned)(w2 >> 8);
+  if (nf) {
 #pragma unroll
     for (int k = 0; k < 8; k++)
-      if (((slow >> k) & 1) && k < n) r.s[k] = (P)sao_sample<P>(pic, a, ci, c, sh, x + k, y, v.s[k], width, height, type, ctbshift);
+      if (k < n) out[k] = (P)sao_sample<P>(pic, a, a.ctbs[ctb], c, sh, x + k, y, v.s[k], width, height, type, ctbshift);
+    return;
   }
-  if (n == 8) *reinterpret_cast<V8*>(out) = r.q;
-  else
-    for (int k = 0; k < n; k++) out[k] = r.s[k];
+  // Offsets as bytes [o0, o1, 0, o2, o3]: an edge sample indexes it with e + 2 (sao.cc:95-100), a band sample with its
+  // band number mapped 0,1,2,3 -> 0,1,3,4; index 2 = no offset.  One byte permute with sign replication does the lookup,
+  // so edge and band CTBs (and all four edge classes) share one instruction stream: no divergence inside a warp.
+  const unsigned tlo = (o4 & 0xFFFFu) | ((o4 & 0xFF0000u) << 8), thi = o4 >> 24;
+  const bool edge = type == 2;
+  unsigned bad = 0;  // edge: samples whose neighbours are not available
+  int na_[8], nb_[8];
+  if (edge) {
+    const int S = 1 << ctbshift;
+    const int xC = (x >> ctbshift) << ctbshift, yC = (y >> ctbshift) << ctbshift;
+    const int ctbW = min(S, width - xC), ctbH = min(S, height - yC);
+    const int i = x - xC, j = y - yC;
+    const int cls = (int)(w0 >> (40 + 2 * c)) & 3;
+    const int hx0 = (cls == 1) ? 0 : (cls == 3) ? 1 : -1;
+    const int vy0 = (cls == 0) ? 0 : -1;
+    // neighbour a = (x+hx0, y+vy0), neighbour b = (x-hx0, y-vy0)
+    const unsigned m = a.sao_avail[(c ? pic.wctb * pic.hctb : 0) + ctb];
+    const int dya = (j + vy0 < 0) ? -1 : 0, dyb = (j - vy0 >= ctbH) ? 1 : 0;  // vy0 <= 0
+    // availability of a / b in the CTB column of the sample itself, and in the column one step in a's / b's x direction
+    const unsigned a_mid = (m >> ((dya + 1) * 3 + 1)) & 1, b_mid = (m >> ((dyb + 1) * 3 + 1)) & 1;
+    const unsigned a_side = (m >> ((dya + 1) * 3 + 1 + hx0)) & 1, b_side = (m >> ((dyb + 1) * 3 + 1 - hx0)) & 1;
+    const unsigned first = (i == 0) ? 1u : 0u, last = (i + 8 >= ctbW) ? 1u << (ctbW - 1 - i) : 0u;  // CTB border columns in this group
+    unsigned ma = a_mid ? 0xFFu : 0u, mb = b_mid ? 0xFFu : 0u;
+    const unsigned sa = (hx0 < 0) ? first : (hx0 > 0) ? last : 0u, sb = (hx0 > 0) ? first : (hx0 < 0) ? last : 0u;  // sample whose a / b is in the side CTB
+    ma = (ma & ~sa) | (a_side ? sa : 0u);
+    mb = (mb & ~sb) | (b_side ? sb : 0u);
+    const unsigned border = (j == 0 || j == ctbH - 1) ? 0xFFu : (first | last);  // sao.cc:125: tests only on the CTB border
+    bad = border & ~(ma & mb);
+    const int ya = max(y + vy0, 0), yb = min(y - vy0, height - 1);  // clamped rows are only read when unavailable
+    const P* ra = row_ptr<P>(pic.cur[c], pitch, ya) + x;
+    const P* rb = row_ptr<P>(pic.cur[c], pitch, yb) + x;
+    Vec va, vb;
+    va.q = *reinterpret_cast<const V8*>(ra);
+    vb.q = *reinterpret_cast<const V8*>(rb);
+    // samples x-1 and x+8 of both rows (never read before the first sample of a row)
+    const int la = x ? ra[-1] : 0, lb = x ? rb[-1] : 0, ha = ra[8], hb = rb[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int am = k ? va.s[k - 1] : la, ap = (k < 7) ? va.s[k + 1] : ha;
+      const int bm = k ? vb.s[k - 1] : lb, bp = (k < 7) ? vb.s[k + 1] : hb;
+      na_[k] = (hx0 < 0) ? am : (hx0 > 0) ? ap : (int)va.s[k];
+      nb_[k] = (hx0 < 0) ? bp : (hx0 > 0) ? bm : (int)vb.s[k];
+    }
+  }
+  const int pos = (c == 0) ? (int)(w0 >> 48) & 0xFF : (c == 1) ? (int)(w0 >> 56) : (int)(w1 & 0xFF);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int s = v.s[k];
+    int idx;
+    if (edge) {
+      const int e = clip3i(-1, 1, s - na_[k]) + clip3i(-1, 1, s - nb_[k]);
+      idx = ((bad >> k) & 1) ? 2 : e + 2;
+    } else {
+      const int b = ((s >> (bd - 5)) - pos) & 31;
+      idx = (b > 3) ? 2 : b + (b >> 1);
+    }
+    int off;  // byte idx of {thi:tlo}, sign-extended (selector nibble bit 3 = replicate the byte's sign)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(off) : "r"(tlo), "r"(thi), "r"((unsigned)idx * 0x1111u + 0x8880u));
+    r.s[k] = (P)clip3i(0, maxv, s + off);
+  }
+  store(r);
 }

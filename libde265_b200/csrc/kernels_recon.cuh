@@ -21,6 +21,7 @@
 // and the transform_* / add_residual / dequant entries of the DSP table (fallback-dct.cc).
 #pragma once
 #include "dev_common.cuh"
+#include "kernels_residual.cuh"
 
 #define RC_WARPS 8
 #define RC_THREADS (RC_WARPS * 32)
@@ -34,6 +35,7 @@ struct ReconArgs {
   const b200_tu* tus;         // decode order, as recorded
   const uint32_t* list;       // TU indices this launch works on (k_residual: any order; k_intra: grouped by task)
   int n_list;
+  int n_listw, n_list8;       // k_residual: list = [n_listw warp-per-TU entries | n_list8 8x8 TUs | the rest: 4x4 TUs]
   const uint32_t* task_start; // k_intra: [n_task + 1] offsets into list, tasks in topological order
   int n_task;
   const b200_coeff* coeffs;
@@ -48,6 +50,7 @@ struct ResidualSmem {  // k_residual
   int16_t coef[RC_WARPS][32 * 32];
   int16_t g[RC_WARPS][32 * RC_GSTRIDE];
   int8_t dct[32][32];
+  ResTables tb;
 };
 
 template <typename P>
@@ -465,27 +468,54 @@ __device__ __forceinline__ void block_store(const P* blk, uint8_t* plane, int pi
 }
 
 // -------------------------------------------------------------------------------------------------
+// Persistent CTAs; work items per warp, heaviest class first: one large / PCM TU, then four 8x8 TUs, then 32 4x4 TUs.
 template <typename P>
 __global__ void __launch_bounds__(RC_THREADS) k_residual(DevPic pic, ReconArgs args)
 {
   __shared__ ResidualSmem sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 32 * 32; i += RC_THREADS) sm.dct[i >> 5][i & 31] = c_dct[i >> 5][i & 31];
+  for (int i = tid; i < (int)(sizeof(ResTables) / 4); i += RC_THREADS) reinterpret_cast<uint32_t*>(&sm.tb)[i] = reinterpret_cast<const uint32_t*>(&c_res)[i];
   __syncthreads();
-  const int idx = blockIdx.x * RC_WARPS + warp;
-  if (idx >= args.n_list) return;
-  const b200_tu tu = args.tus[args.list[idx]];
-  const int c = tu.cidx, nT = 1 << tu.log2_size;
-  P* dst = row_ptr<P>(pic.cur[c], pic.pitch[c], tu.y) + tu.x;
-  const int dstride = pic.pitch[c] / (int)sizeof(P);
-  if (tu.flags & B200_TU_PCM) {  // slice.cc:4211-4255
-    for (int i = lane; i < tu.n_coeff; i += 32) {
-      const b200_coeff co = args.coeffs[tu.coeff_off + i];
-      dst[(co.pos & (nT - 1)) + (co.pos >> tu.log2_size) * dstride] = (P)(uint16_t)co.level;
+  const int n4 = args.n_list - args.n_listw - args.n_list8;
+  const int Ww = args.n_listw, W8 = (args.n_list8 + 3) >> 2, W4 = (n4 + 31) >> 5;
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(sm.coef[warp]);  // 256 words are enough for the sub-warp paths
+  for (int wi = blockIdx.x * RC_WARPS + warp; wi < Ww + W8 + W4; wi += gridDim.x * RC_WARPS) {
+    if (wi < Ww) {
+      const b200_tu tu = args.tus[args.list[wi]];
+      const int c = tu.cidx, nT = 1 << tu.log2_size;
+      P* dst = row_ptr<P>(pic.cur[c], pic.pitch[c], tu.y) + tu.x;
+      const int dstride = pic.pitch[c] / (int)sizeof(P);
+      if (tu.flags & B200_TU_PCM) {  // slice.cc:4211-4255
+        for (int i = lane; i < tu.n_coeff; i += 32) {
+          const b200_coeff co = args.coeffs[tu.coeff_off + i];
+          dst[(co.pos & (nT - 1)) + (co.pos >> tu.log2_size) * dstride] = (P)(uint16_t)co.level;
+        }
+      } else {
+        tu_residual<P, false>(tu, args.coeffs + tu.coeff_off, args.scaling, dst, dstride, nullptr, c ? pic.bd_c : pic.bd_y, sm.coef[warp], sm.g[warp],
+                              sm.dct, lane);
+      }
+    } else if (wi < Ww + W8) {
+      const int idx = Ww + (wi - Ww) * 4 + (lane >> 3);
+      const bool active = idx < Ww + args.n_list8;
+      b200_tu tu;
+      if (active) tu = args.tus[args.list[idx]];
+      else { tu.x = tu.y = 0; tu.cidx = 0; tu.coeff_off = 0; }
+      const int c = tu.cidx;
+      P* dst = row_ptr<P>(pic.cur[c], pic.pitch[c], tu.y) + tu.x;
+      res8_quarter<P, false>(active, tu, args.coeffs + tu.coeff_off, args.scaling, dst, pic.pitch[c] / (int)sizeof(P), nullptr, c ? pic.bd_c : pic.bd_y,
+                             scratch + (lane >> 3) * 64, lane & 7, sm.tb);
+    } else {
+      const int idx = Ww + args.n_list8 + (wi - Ww - W8) * 32 + lane;
+      if (idx < args.n_list) {
+        const b200_tu tu = args.tus[args.list[idx]];
+        const int c = tu.cidx;
+        P* dst = row_ptr<P>(pic.cur[c], pic.pitch[c], tu.y) + tu.x;
+        res4_lane<P, false>(tu, args.coeffs + tu.coeff_off, args.scaling, dst, pic.pitch[c] / (int)sizeof(P), nullptr, c ? pic.bd_c : pic.bd_y, scratch, lane,
+                            sm.tb);
+      }
     }
-  } else {
-    tu_residual<P, false>(tu, args.coeffs + tu.coeff_off, args.scaling, dst, dstride, nullptr, c ? pic.bd_c : pic.bd_y, sm.coef[warp], sm.g[warp],
-                          sm.dct, lane);
+    __syncwarp();
   }
 }
 
