@@ -61,8 +61,8 @@ struct IntraSmem {  // k_intra
   int32_t res[RC_WARPS][32 * 32];     // the task's residuals, TU after TU (row stride nT inside a TU)
   P border[RC_WARPS][2][4 * 32 + 4];  // large TUs: [0] gathered/substituted, [1] filtered / angular ref
   b200_tu tu_s[RC_WARPS][16];
-  b200_coeff co_s[RC_WARPS][RC_CO_STAGE];
   int8_t dct[32][32];
+  ResTables tb;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -557,9 +557,9 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
   IntraSmem<P>& sm = *reinterpret_cast<IntraSmem<P>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 32 * 32; i += RC_THREADS) sm.dct[i >> 5][i & 31] = c_dct[i >> 5][i & 31];
+  for (int i = tid; i < (int)(sizeof(ResTables) / 4); i += RC_THREADS) reinterpret_cast<uint32_t*>(&sm.tb)[i] = reinterpret_cast<const uint32_t*>(&c_res)[i];
   __syncthreads();
   b200_tu* tus = sm.tu_s[warp];
-  b200_coeff* cos = sm.co_s[warp];
   int32_t* res = sm.res[warp];
   P* blk = sm.blk[warp];
   // Persistent warps: each warp keeps claiming the next task of the topological order.
@@ -574,17 +574,6 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     // ---- everything that does not depend on the neighbours: TU records, coefficient lists, residuals ----
     if (lane < (int)count) tus[lane] = args.tus[args.list[first + lane]];
     __syncwarp();
-    {
-      int base = 0;
-      for (uint32_t i = 0; i < count; i++) {
-        const int n = tus[i].n_coeff;
-        if (base + n <= RC_CO_STAGE) {
-          const b200_coeff* src = args.coeffs + tus[i].coeff_off;
-          for (int k = lane; k < n; k += 32) cos[base + k] = src[k];
-        }
-        base += n;
-      }
-    }
     const b200_tu tu0 = tus[0];
     const int c = tu0.cidx, sh = c ? 1 : 0;
     const int bd = c ? pic.bd_c : pic.bd_y;
@@ -593,16 +582,40 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     const int rx = region ? tu0.x & ~(G - 1) : tu0.x, ry = region ? tu0.y & ~(G - 1) : tu0.y;  // dependency frame origin
     const bool filter_plane = !(pic.flags & B200_PIC_INTRA_SMOOTHING_OFF) && (c == 0 || pic.chroma == 3);
     const int pwid = c ? pic.cw : pic.w, phei = c ? pic.ch : pic.h;
-    __syncwarp();
     {
-      int cbase = 0, rbase = 0;
-      for (uint32_t i = 0; i < count; i++) {
-        const b200_tu& tu = tus[i];
-        if (tu.flags & B200_TU_CBF)
-          tu_residual<P, true>(tu, (cbase + tu.n_coeff <= RC_CO_STAGE) ? cos + cbase : args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rbase,
-                               bd, sm.coef[warp], sm.g[warp], sm.dct, lane);
-        cbase += tu.n_coeff;
-        rbase += 1 << (2 * tu.log2_size);
+      // residuals of all the task's TUs, in parallel where the sizes allow: lane i owns TU i's record; 4x4 TUs run one
+      // per lane, 8x8 TUs one per quarter-warp, larger ones one after the other on the whole warp.  res holds the TUs'
+      // residual blocks back to back (exclusive prefix sum of nT^2 over the lanes).
+      const bool mine = lane < (int)count;
+      const b200_tu& mytu = tus[mine ? lane : 0];
+      const int l2 = mytu.log2_size, sz = mine ? 1 << (2 * l2) : 0;
+      int incl = sz;
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        const int up = __shfl_up_sync(RC_FULL, incl, d);
+        if (lane >= d) incl += up;
+      }
+      const int my_rbase = incl - sz;
+      const bool cbf = mine && (mytu.flags & B200_TU_CBF);
+      const unsigned m8 = __ballot_sync(RC_FULL, cbf && l2 == 3), mw = __ballot_sync(RC_FULL, cbf && l2 > 3);
+      uint32_t* scratch = reinterpret_cast<uint32_t*>(sm.coef[warp]);
+      if (cbf && l2 == 2) res4_lane<P, true>(mytu, args.coeffs + mytu.coeff_off, args.scaling, nullptr, 0, res + my_rbase, bd, scratch, lane, sm.tb);
+      __syncwarp();
+      for (unsigned rem = m8; rem;) {
+        const int q = lane >> 3;
+        const unsigned idx = __fns(rem, 0, q + 1);  // q-th pending 8x8 TU (0xffffffff: none)
+        const bool active = idx < 32u;
+        const b200_tu& tu = tus[active ? idx : 0];
+        const int rb = __shfl_sync(RC_FULL, my_rbase, active ? idx : 0);
+        res8_quarter<P, true>(active, tu, args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rb, bd, scratch + q * 64, lane & 7, sm.tb);
+#pragma unroll
+        for (int k = 0; k < 4; k++) rem &= rem - 1;  // (0 & -1 stays 0)
+      }
+      for (unsigned rem = mw; rem; rem &= rem - 1) {
+        const int idx = __ffs(rem) - 1;
+        const b200_tu& tu = tus[idx];
+        const int rb = __shfl_sync(RC_FULL, my_rbase, idx);
+        tu_residual<P, true>(tu, args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rb, bd, sm.coef[warp], sm.g[warp], sm.dct, lane);
       }
     }
     // ---- wait: one flag per distinct external neighbour unit, one lane each ----
