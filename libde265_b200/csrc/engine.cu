@@ -98,15 +98,35 @@ struct StagingSet {
   bool in_flight = false;
 };
 
-struct b200_engine {
-  int device = 0;
+// One pipeline context = one CUDA stream with everything a picture in flight needs privately.  Pictures are issued
+// round-robin onto the contexts; cross-context ordering comes from per-slot events (SlotSync): a picture waits for the
+// writers of its reference slots and for every earlier reader / writer of its destination slot.  So pictures that do
+// not depend on each other (the B pictures of one hierarchy level, the next intra period's I picture) overlap, and a
+// latency-bound kernel (the intra DAG) of one picture leaves the SMs to the others.
+#define B200_MAX_CTX 8
+struct PipeCtx {
   cudaStream_t stream = nullptr;
-  Surface slot[B200_MAX_SLOTS];
-  Surface scratch;
+  Surface scratch;              // pre-SAO picture
   StagingSet stage[2];
   int cur_stage = 0;
-  uint8_t* sync_buf = nullptr;  // [256 B ticket | pending map Y | Cb | Cr]
+  uint8_t* sync_buf = nullptr;  // [256 B ticket | pending map Y | Cb | Cr | SAO masks]
   size_t sync_cap = 0;
+  cudaEvent_t tail = nullptr;   // b200_engine_join
+};
+
+struct SlotSync {
+  cudaEvent_t written = nullptr;
+  int writer = -1;                       // context of the last writer, -1: none in flight
+  cudaEvent_t read[B200_MAX_CTX] = {};   // last read of this slot issued on each context
+  bool read_pending[B200_MAX_CTX] = {};
+};
+
+struct b200_engine {
+  int device = 0;
+  PipeCtx ctx[B200_MAX_CTX];
+  int n_ctx = 1, next_ctx = 0;
+  Surface slot[B200_MAX_SLOTS];
+  SlotSync ssync[B200_MAX_SLOTS];
   int num_sms = 148;
   bool timing = false;
   std::vector<cudaEvent_t> tev;  // timing ring: TIMING_RING pictures x 7 events
@@ -121,6 +141,7 @@ struct b200_engine {
 
 struct PicLayout {
   size_t off[14] = {}, total = 0;
+  uint32_t ref_mask = 0;  // slots the picture's PUs read
   int n_tiles = 0, n_a = 0, n_aw = 0, n_a8 = 0, n_b = 0, n_task = 0;
   bool run_deblock = false, run_sao = false, has_scaling = false;
   b200_pic_params params{};
@@ -222,8 +243,18 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   en->device = device;
   int rc = init_tables(device);
   if (rc) { delete en; return rc; }
-  CU(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&en->stage[i].done, cudaEventDisableTiming));
+  en->n_ctx = 4;
+  if (const char* e = getenv("B200_STREAMS")) en->n_ctx = std::max(1, std::min(B200_MAX_CTX, atoi(e)));
+  for (int k = 0; k < B200_MAX_CTX; k++) {
+    PipeCtx& cx = en->ctx[k];
+    CU(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&cx.tail, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&cx.stage[i].done, cudaEventDisableTiming));
+  }
+  for (auto& ss : en->ssync) {
+    CU(cudaEventCreateWithFlags(&ss.written, cudaEventDisableTiming));
+    for (int k = 0; k < B200_MAX_CTX; k++) CU(cudaEventCreateWithFlags(&ss.read[k], cudaEventDisableTiming));
+  }
   CU(cudaFuncSetAttribute(k_intra<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<uint8_t>)));
   CU(cudaFuncSetAttribute(k_intra<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<uint16_t>)));
   CU(cudaDeviceGetAttribute(&en->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -235,22 +266,64 @@ extern "C" void b200_engine_destroy(b200_engine* en)
 {
   if (!en) return;
   cudaSetDevice(en->device);
-  if (en->stream) cudaStreamSynchronize(en->stream);
+  cudaDeviceSynchronize();
   for (auto& s : en->slot) surface_free(s);
-  surface_free(en->scratch);
-  for (auto& st : en->stage) {
-    if (st.host) cudaFreeHost(st.host);
-    if (st.dev) cudaFree(st.dev);
-    if (st.done) cudaEventDestroy(st.done);
+  for (auto& cx : en->ctx) {
+    surface_free(cx.scratch);
+    for (auto& st : cx.stage) {
+      if (st.host) cudaFreeHost(st.host);
+      if (st.dev) cudaFree(st.dev);
+      if (st.done) cudaEventDestroy(st.done);
+    }
+    if (cx.sync_buf) cudaFree(cx.sync_buf);
+    if (cx.tail) cudaEventDestroy(cx.tail);
+    if (cx.stream) cudaStreamDestroy(cx.stream);
   }
-  if (en->sync_buf) cudaFree(en->sync_buf);
+  for (auto& ss : en->ssync) {
+    if (ss.written) cudaEventDestroy(ss.written);
+    for (auto& e : ss.read)
+      if (e) cudaEventDestroy(e);
+  }
   for (auto& e : en->tev)
     if (e) cudaEventDestroy(e);
-  if (en->stream) cudaStreamDestroy(en->stream);
   delete en;
 }
 
-extern "C" void* b200_engine_stream(b200_engine* en) { return en ? (void*)en->stream : nullptr; }
+extern "C" void* b200_engine_stream(b200_engine* en) { return en ? (void*)en->ctx[0].stream : nullptr; }
+
+static int sync_all(b200_engine* en)
+{
+  for (int k = 0; k < B200_MAX_CTX; k++) CU(cudaStreamSynchronize(en->ctx[k].stream));
+  for (auto& ss : en->ssync) {
+    ss.writer = -1;
+    for (auto& r : ss.read_pending) r = false;
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_engine_set_streams(b200_engine* en, int n)
+{
+  if (!en || n < 1 || n > B200_MAX_CTX) return set_err(B200_ERR_INVALID, "stream count must be 1..%d", B200_MAX_CTX);
+  CU(cudaSetDevice(en->device));
+  int rc = sync_all(en);
+  if (rc) return rc;
+  en->n_ctx = n;
+  en->next_ctx = 0;
+  return B200_OK;
+}
+
+// Makes stream 0 (b200_engine_stream) wait for everything issued so far on the other streams: an event recorded on
+// stream 0 afterwards marks the completion of all submitted pictures.
+extern "C" int b200_engine_join(b200_engine* en)
+{
+  if (!en) return set_err(B200_ERR_INVALID, "null engine");
+  CU(cudaSetDevice(en->device));
+  for (int k = 1; k < B200_MAX_CTX; k++) {
+    CU(cudaEventRecord(en->ctx[k].tail, en->ctx[k].stream));
+    CU(cudaStreamWaitEvent(en->ctx[0].stream, en->ctx[k].tail, 0));
+  }
+  return B200_OK;
+}
 extern "C" uint64_t b200_engine_launch_count(const b200_engine* en) { return en ? en->launches : 0; }
 
 extern "C" int b200_engine_enable_timing(b200_engine* en, int on)
@@ -339,9 +412,9 @@ static size_t sync_sao_offset(const b200_pic_params& p)
 }
 
 template <typename P>
-static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp, const RefTable& refs, const uint8_t* dbase)
+static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, const DevPic& dp, const RefTable& refs, const uint8_t* dbase)
 {
-  cudaStream_t st = en->stream;
+  cudaStream_t st = cx.stream;
   const size_t* off = L.off;
   const int n_tiles = L.n_tiles;
   const bool run_deblock = L.run_deblock, run_sao = L.run_sao;
@@ -361,9 +434,9 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
     ra.tus = (const b200_tu*)(dbase + off[2]);
     ra.coeffs = (const b200_coeff*)(dbase + off[5]);
     ra.scaling = L.has_scaling ? dbase + off[11] : nullptr;
-    ra.ticket = (unsigned int*)en->sync_buf;
+    ra.ticket = (unsigned int*)cx.sync_buf;
     const size_t cw4 = (size_t)((dp.cw + 3) / 4), ch4 = (size_t)((dp.ch + 3) / 4);
-    ra.pend[0] = en->sync_buf + 256;
+    ra.pend[0] = cx.sync_buf + 256;
     ra.pend[1] = ra.pend[0] + (size_t)dp.w4 * dp.h4;
     ra.pend[2] = ra.pend[1] + cw4 * ch4;
     ra.pend_w[0] = dp.w4;
@@ -388,7 +461,7 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
       }
       ra.list = (const uint32_t*)(dbase + off[4]);
       ra.n_list = L.n_b;
-      CU(cudaMemsetAsync(en->sync_buf, 0, 256 + (size_t)dp.w4 * dp.h4 + 2 * cw4 * ch4, st));
+      CU(cudaMemsetAsync(cx.sync_buf, 0, 256 + (size_t)dp.w4 * dp.h4 + 2 * cw4 * ch4, st));
       k_mark_pending<<<(L.n_b + 255) / 256, 256, 0, st>>>(ra);
       ra.task_start = (const uint32_t*)(dbase + off[13]);
       ra.n_task = L.n_task;
@@ -427,7 +500,7 @@ static int launch_picture(b200_engine* en, const PicLayout& L, const DevPic& dp,
   }
   if (en->timing) CU(cudaEventRecord(en->ev[4], st));
   if (run_sao) {
-    uint16_t* avail = (uint16_t*)(en->sync_buf + sync_sao_offset(L.params));
+    uint16_t* avail = (uint16_t*)(cx.sync_buf + sync_sao_offset(L.params));
     fa.sao_avail = avail;
     k_sao_prep<<<(2 * dp.wctb * dp.hctb + 127) / 128, 128, 0, st>>>(dp, fa, avail);
     dim3 grid((dp.w / 8 + 127) / 128, dp.h, dp.chroma ? 3 : 1);
@@ -470,6 +543,8 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
     if ((pu.flags & B200_PU_WEIGHTED) && pu.wt_idx >= pic->n_weights) return set_err(B200_ERR_INVALID, "PU %u weight index", i);
     if (pu.ref_slot[0] >= B200_MAX_SLOTS || pu.ref_slot[1] >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "PU %u reference slot", i);
     if (!(pu.flags & (B200_PU_PRED_L0 | B200_PU_PRED_L1))) continue;
+    if ((pu.flags & B200_PU_PRED_L0) && pu.ref_slot[0] >= 0) L->ref_mask |= 1u << pu.ref_slot[0];
+    if ((pu.flags & B200_PU_PRED_L1) && pu.ref_slot[1] >= 0) L->ref_mask |= 1u << pu.ref_slot[1];
     if (wide) {  // 16-bit path: <= 16x16 tiles, one warp each (kernels_mc.cuh)
       for (int ty = 0; ty * MC_TILE < pu.h; ty++)
         for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
@@ -634,20 +709,54 @@ static int ensure_staging(StagingSet& ss, size_t total)
   return B200_OK;
 }
 
-// Everything after the records are in device memory at `dbase`.  `upload_from`: pinned source to copy first (or null).
-static int run_layout(b200_engine* en, const PicLayout& L, uint8_t* dbase, const uint8_t* upload_from)
+// Cross-stream ordering for a picture issued on context `k` (SlotSync): wait for the writers of its reference slots and
+// for every earlier reader / writer of its destination slot that ran on another stream.
+static int order_before(b200_engine* en, int k, const PicLayout& L)
 {
+  cudaStream_t st = en->ctx[k].stream;
+  const int d = L.params.dst_slot;
+  for (int r = 0; r < B200_MAX_SLOTS; r++) {
+    if (!((L.ref_mask >> r) & 1) && r != d) continue;
+    SlotSync& ss = en->ssync[r];
+    if (ss.writer >= 0 && ss.writer != k) CU(cudaStreamWaitEvent(st, ss.written, 0));
+  }
+  SlotSync& sd = en->ssync[d];
+  for (int c = 0; c < B200_MAX_CTX; c++)
+    if (c != k && sd.read_pending[c]) CU(cudaStreamWaitEvent(st, sd.read[c], 0));
+  return B200_OK;
+}
+
+static int order_after(b200_engine* en, int k, const PicLayout& L)
+{
+  cudaStream_t st = en->ctx[k].stream;
+  const int d = L.params.dst_slot;
+  if (en->n_ctx > 1) {
+    for (int r = 0; r < B200_MAX_SLOTS; r++) {
+      if (!((L.ref_mask >> r) & 1) || r == d) continue;
+      CU(cudaEventRecord(en->ssync[r].read[k], st));
+      en->ssync[r].read_pending[k] = true;
+    }
+  }
+  SlotSync& sd = en->ssync[d];
+  CU(cudaEventRecord(sd.written, st));
+  sd.writer = k;
+  for (auto& rp : sd.read_pending) rp = false;  // this picture waited for them; later pictures wait for this one
+  return B200_OK;
+}
+
+// Everything after the records are in device memory at `dbase`.  `upload_from`: pinned source to copy first (or null).
+static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase, const uint8_t* upload_from)
+{
+  PipeCtx& cx = en->ctx[k];
   const b200_pic_params& p = L.params;
-  const int S = 1 << p.log2_ctb_size;
-  const int n_ctb = ((p.width + S - 1) / S) * ((p.height + S - 1) / S);
   Surface& dst = en->slot[p.dst_slot];
-  int rc = surface_ensure(dst, p, en->stream);
+  int rc = surface_ensure(dst, p, cx.stream);
   if (rc) return rc;
   Surface* cur = &dst;
   if (L.run_sao) {
-    rc = surface_ensure(en->scratch, p, en->stream);
+    rc = surface_ensure(cx.scratch, p, cx.stream);
     if (rc) return rc;
-    cur = &en->scratch;
+    cur = &cx.scratch;
   }
   RefTable refs;
   memset(&refs, 0, sizeof(refs));
@@ -658,27 +767,39 @@ static int run_layout(b200_engine* en, const PicLayout& L, uint8_t* dbase, const
       for (int c = 0; c < 3; c++) refs.plane[i][c] = s.plane[c];
   }
   {
-    const size_t cw4 = p.chroma_format_idc ? (size_t)((p.width / 2 + 3) / 4) : 0, ch4 = p.chroma_format_idc ? (size_t)((p.height / 2 + 3) / 4) : 0;
     const size_t n_ctb = (size_t)((p.width + (1 << p.log2_ctb_size) - 1) >> p.log2_ctb_size) * ((p.height + (1 << p.log2_ctb_size) - 1) >> p.log2_ctb_size);
     const size_t need = sync_sao_offset(p) + 2 * n_ctb * sizeof(uint16_t);
-    if (en->sync_cap < need) {
-      if (en->sync_buf) { CU(cudaStreamSynchronize(en->stream)); cudaFree(en->sync_buf); }
-      en->sync_buf = nullptr;
-      CU(cudaMalloc(&en->sync_buf, need));
-      en->sync_cap = need;
+    if (cx.sync_cap < need) {
+      if (cx.sync_buf) { CU(cudaStreamSynchronize(cx.stream)); cudaFree(cx.sync_buf); }
+      cx.sync_buf = nullptr;
+      CU(cudaMalloc(&cx.sync_buf, need));
+      cx.sync_cap = need;
     }
   }
-  cudaStream_t st = en->stream;
+  cudaStream_t st = cx.stream;
   en->ev = en->timing ? &en->tev[(size_t)(en->tcount % TIMING_RING) * 7] : nullptr;
   if (en->timing) CU(cudaEventRecord(en->ev[0], st));
-  if (upload_from) CU(cudaMemcpyAsync(dbase, upload_from, L.total, cudaMemcpyHostToDevice, st));
+  if (upload_from) CU(cudaMemcpyAsync(dbase, upload_from, L.total, cudaMemcpyHostToDevice, st));  // records first: overlaps the waits below
+  rc = order_before(en, k, L);
+  if (rc) return rc;
   const DevPic dp = make_devpic(p, *cur, dst);
-  if (p.bit_depth_luma > 8) rc = launch_picture<uint16_t>(en, L, dp, refs, dbase);
-  else rc = launch_picture<uint8_t>(en, L, dp, refs, dbase);
+  if (p.bit_depth_luma > 8) rc = launch_picture<uint16_t>(en, cx, L, dp, refs, dbase);
+  else rc = launch_picture<uint8_t>(en, cx, L, dp, refs, dbase);
   if (rc) return rc;
   if (en->timing) { CU(cudaEventRecord(en->ev[6], st)); en->tcount++; }
+  rc = order_after(en, k, L);
+  if (rc) return rc;
   dst.valid = true;
   return B200_OK;
+}
+
+// Per-stage timing needs the stages of consecutive pictures not to overlap: one stream while it is on.
+static int pick_ctx(b200_engine* en)
+{
+  if (en->timing || en->n_ctx <= 1) return 0;
+  const int k = en->next_ctx;
+  en->next_ctx = (en->next_ctx + 1) % en->n_ctx;
+  return k;
 }
 
 extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* pic)
@@ -688,15 +809,17 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
   PicLayout L;
   int rc = plan_picture(en, pic, &L);
   if (rc) return rc;
-  StagingSet& ss = en->stage[en->cur_stage];
-  en->cur_stage ^= 1;
+  const int k = pick_ctx(en);
+  PipeCtx& cx = en->ctx[k];
+  StagingSet& ss = cx.stage[cx.cur_stage];
+  cx.cur_stage ^= 1;
   rc = ensure_staging(ss, L.total);
   if (rc) return rc;
   rc = pack_picture(en, pic, L, ss.host);
   if (rc) return rc;
-  rc = run_layout(en, L, ss.dev, ss.host);
+  rc = run_layout(en, k, L, ss.dev, ss.host);
   if (rc) return rc;
-  CU(cudaEventRecord(ss.done, en->stream));
+  CU(cudaEventRecord(ss.done, cx.stream));
   ss.in_flight = true;
   return B200_OK;
 }
@@ -709,14 +832,15 @@ extern "C" int b200_engine_prepare_picture(b200_engine* en, const b200_picture* 
   if (!pp) return set_err(B200_ERR_NOMEM, "out of memory");
   int rc = plan_picture(en, pic, &pp->L);
   if (rc) { delete pp; return rc; }
-  StagingSet& ss = en->stage[en->cur_stage];
-  en->cur_stage ^= 1;
+  PipeCtx& cx = en->ctx[0];
+  StagingSet& ss = cx.stage[cx.cur_stage];
+  cx.cur_stage ^= 1;
   rc = ensure_staging(ss, pp->L.total);
   if (!rc) rc = pack_picture(en, pic, pp->L, ss.host);
   if (rc) { delete pp; return rc; }
   cudaError_t e = cudaMalloc(&pp->dev, pp->L.total);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(pp->dev, ss.host, pp->L.total, cudaMemcpyHostToDevice, en->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(en->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pp->dev, ss.host, pp->L.total, cudaMemcpyHostToDevice, cx.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cx.stream);
   if (e != cudaSuccess) {
     if (pp->dev) cudaFree(pp->dev);
     delete pp;
@@ -730,14 +854,14 @@ extern "C" int b200_engine_run_prepared(b200_engine* en, b200_prepared* pp)
 {
   if (!en || !pp) return set_err(B200_ERR_INVALID, "null argument");
   CU(cudaSetDevice(en->device));
-  return run_layout(en, pp->L, pp->dev, nullptr);
+  return run_layout(en, pick_ctx(en), pp->L, pp->dev, nullptr);
 }
 
 extern "C" void b200_engine_free_prepared(b200_engine* en, b200_prepared* pp)
 {
   if (!en || !pp) return;
   cudaSetDevice(en->device);
-  cudaStreamSynchronize(en->stream);
+  sync_all(en);
   if (pp->dev) cudaFree(pp->dev);
   delete pp;
 }
@@ -746,8 +870,7 @@ extern "C" int b200_engine_sync(b200_engine* en)
 {
   if (!en) return set_err(B200_ERR_INVALID, "null engine");
   CU(cudaSetDevice(en->device));
-  CU(cudaStreamSynchronize(en->stream));
-  return B200_OK;
+  return sync_all(en);
 }
 
 template <typename P>
@@ -763,17 +886,22 @@ extern "C" int b200_engine_fill_slot(b200_engine* en, int slot, const b200_pic_p
   int rc = check_params(*p);
   if (rc) return rc;
   CU(cudaSetDevice(en->device));
+  rc = sync_all(en);  // utility call: quiesce, then write on stream 0
+  if (rc) return rc;
+  cudaStream_t st = en->ctx[0].stream;
   Surface& s = en->slot[slot];
-  rc = surface_ensure(s, *p, en->stream);
+  rc = surface_ensure(s, *p, st);
   if (rc) return rc;
   for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
     const int w = c ? s.cw : s.w, h = c ? s.ch : s.h;
     dim3 grid((w + 255) / 256, h);
-    if (p->bit_depth_luma > 8) k_fill<uint16_t><<<grid, 256, 0, en->stream>>>(s.plane[c], s.pitch[c], w, h, c ? vc : vy);
-    else k_fill<uint8_t><<<grid, 256, 0, en->stream>>>(s.plane[c], s.pitch[c], w, h, c ? vc : vy);
+    if (p->bit_depth_luma > 8) k_fill<uint16_t><<<grid, 256, 0, st>>>(s.plane[c], s.pitch[c], w, h, c ? vc : vy);
+    else k_fill<uint8_t><<<grid, 256, 0, st>>>(s.plane[c], s.pitch[c], w, h, c ? vc : vy);
     en->launches++;
   }
   CU(cudaGetLastError());
+  CU(cudaEventRecord(en->ssync[slot].written, st));
+  en->ssync[slot].writer = 0;
   s.valid = true;
   return B200_OK;
 }
@@ -784,15 +912,18 @@ extern "C" int b200_engine_upload_slot(b200_engine* en, int slot, const b200_pic
   int rc = check_params(*p);
   if (rc) return rc;
   CU(cudaSetDevice(en->device));
+  rc = sync_all(en);  // utility call: quiesce, then write on stream 0
+  if (rc) return rc;
+  cudaStream_t st = en->ctx[0].stream;
   Surface& s = en->slot[slot];
-  rc = surface_ensure(s, *p, en->stream);
+  rc = surface_ensure(s, *p, st);
   if (rc) return rc;
   for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
     const int w = c ? s.cw : s.w, h = c ? s.ch : s.h, bps = bytes_per_sample(c ? s.bd_c : s.bd_y);
     if (!planes[c]) return set_err(B200_ERR_INVALID, "plane %d missing", c);
-    CU(cudaMemcpy2DAsync(s.plane[c], s.pitch[c], planes[c], strides[c], (size_t)w * bps, h, cudaMemcpyHostToDevice, en->stream));
+    CU(cudaMemcpy2DAsync(s.plane[c], s.pitch[c], planes[c], strides[c], (size_t)w * bps, h, cudaMemcpyHostToDevice, st));
   }
-  CU(cudaStreamSynchronize(en->stream));  // the source may be pageable / reused by the caller
+  CU(cudaStreamSynchronize(st));  // the source may be pageable / reused by the caller
   s.valid = true;
   return B200_OK;
 }
@@ -803,11 +934,17 @@ extern "C" int b200_engine_read_slot_async(b200_engine* en, int slot, void* cons
   const Surface& s = en->slot[slot];
   if (!s.valid) return set_err(B200_ERR_INVALID, "slot %d holds no picture", slot);
   CU(cudaSetDevice(en->device));
+  // on the stream of the slot's last writer: ordered after it without an event, and a read other streams must respect
+  SlotSync& ss = en->ssync[slot];
+  const int k = ss.writer >= 0 ? ss.writer : 0;
+  cudaStream_t st = en->ctx[k].stream;
   for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
     if (!planes[c]) continue;
     const int w = c ? s.cw : s.w, h = c ? s.ch : s.h, bps = bytes_per_sample(c ? s.bd_c : s.bd_y);
-    CU(cudaMemcpy2DAsync(planes[c], strides[c], s.plane[c], s.pitch[c], (size_t)w * bps, h, cudaMemcpyDeviceToHost, en->stream));
+    CU(cudaMemcpy2DAsync(planes[c], strides[c], s.plane[c], s.pitch[c], (size_t)w * bps, h, cudaMemcpyDeviceToHost, st));
   }
+  CU(cudaEventRecord(ss.read[k], st));
+  ss.read_pending[k] = true;
   return B200_OK;
 }
 
@@ -815,7 +952,8 @@ extern "C" int b200_engine_read_slot(b200_engine* en, int slot, void* const plan
 {
   int rc = b200_engine_read_slot_async(en, slot, planes, strides);
   if (rc) return rc;
-  CU(cudaStreamSynchronize(en->stream));
+  const int k = en->ssync[slot].writer >= 0 ? en->ssync[slot].writer : 0;
+  CU(cudaStreamSynchronize(en->ctx[k].stream));
   return B200_OK;
 }
 

@@ -47,149 +47,145 @@ struct ReconArgs {
 };
 
 struct ResidualSmem {  // k_residual
-  int16_t coef[RC_WARPS][32 * 32];
+  int16_t coef[RC_WARPS][32 * RC_GSTRIDE];  // column-major coefficients (tu_residual) / scratch of the sub-warp paths
   int16_t g[RC_WARPS][32 * RC_GSTRIDE];
-  int8_t dct[32][32];
   ResTables tb;
 };
 
 template <typename P>
 struct IntraSmem {  // k_intra
   P blk[RC_WARPS][RC_BLK];            // a region tile, or a large TU's samples (row stride nT)
-  int16_t coef[RC_WARPS][32 * 32];
+  int16_t coef[RC_WARPS][32 * RC_GSTRIDE];
   int16_t g[RC_WARPS][32 * RC_GSTRIDE];
   int32_t res[RC_WARPS][32 * 32];     // the task's residuals, TU after TU (row stride nT inside a TU)
   P border[RC_WARPS][2][4 * 32 + 4];  // large TUs: [0] gathered/substituted, [1] filtered / angular ref
   b200_tu tu_s[RC_WARPS][16];
-  int8_t dct[32][32];
   ResTables tb;
 };
 
 // -------------------------------------------------------------------------------------------------
-// Residual of one TU by one warp.  TO_RES: write the int32 residual r(x,y) to res[x + y*nT]
-// (the caller adds it later); else dst(x,y) = Clip(dst + r) on samples at `dst` (row stride dstride, in
-// GLOBAL memory: each sample is read and written by the same lane exactly once).
-// co = the TU's coefficient list (global memory, or a shared-memory copy staged by the caller).
+// Residual of one LARGE TU (16x16 or 32x32) by one warp; smaller TUs take the sub-warp paths of
+// kernels_residual.cuh.  TO_RES: write the int32 residual r(x,y) to res[x + y*nT] (the caller adds it later); else
+// dst(x,y) = Clip(dst + r) on samples at `dst` (row stride dstride, in GLOBAL memory: each sample is read and written
+// by the same lane exactly once).
+//   coefT  dequantised coefficients, COLUMN-major int16: coefficient (row j, column c) at coefT[c*RC_GSTRIDE + j], so a
+//          32-bit word holds a vertical pair and one dp2a performs two MACs of the column pass;
+//   g      first-stage output, row-major int16 g[y*RC_GSTRIDE + j]: horizontal pairs for the row pass.
+// Both passes are register-blocked 4 outputs per lane (one 16-byte load of packed matrix bytes + two operand words per
+// 8 dp2a) and only touch the rows / columns up to the last significant coefficient.
 // -------------------------------------------------------------------------------------------------
 template <typename P, bool TO_RES>
 __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8_t* __restrict__ scaling, P* dst, int dstride, int32_t* res,
-                            int bd, int16_t* coef, int16_t* g, const int8_t (*dct)[32], int lane)
+                            int bd, int16_t* coefT, int16_t* g, const ResTables& tb, int lane)
 {
   const int log2 = tu.log2_size, nT = 1 << log2, n = tu.n_coeff;
   const int flags = tu.flags;
-  auto emit = [&](int x, int y, int r) {
-    if (TO_RES) res[x + (y << log2)] = r;
-    else dst[x + y * dstride] = (P)clip_bd((int)dst[x + y * dstride] + r, bd);
-  };
-  for (int i = lane; i < nT * nT; i += 32) coef[i] = 0;
-  __syncwarp();
-  // ---- dequant + scatter (transform.cc:452-525) ----
+  const bool special = flags & (B200_TU_BYPASS | B200_TU_TSKIP);
+  const Dequant dq = dequant_setup(tu, scaling, bd);
+  // ---- extent of the significant coefficients ----
   int max_row = 0, max_col = 0;
-  {
-    const bool bypass = flags & B200_TU_BYPASS;
-    const bool rotate = (flags & B200_TU_ROTATE) && (flags & (B200_TU_BYPASS | B200_TU_TSKIP));
-    const uint8_t* scl = nullptr;
-    if ((flags & B200_TU_SCALING_LIST) && scaling) {
-      int m = (nT == 32) ? 0 : tu.cidx;
-      if (flags & B200_TU_INTER_MATRIX) m += (nT < 32) ? 3 : 1;
-      const int base = (nT == 4) ? 0 : (nT == 8) ? 6 * 16 : (nT == 16) ? 6 * 16 + 6 * 64 : 6 * 16 + 6 * 64 + 6 * 256;
-      scl = scaling + base + m * nT * nT;
-    }
-    int bd_shift = bd + log2 - 5;
-    if (!scl) bd_shift -= 4;
-    const int qp = tu.qp, qm = qp % 6, qd = qp / 6;
-    const int ls = (qm == 0) ? 40 : (qm == 1) ? 45 : (qm == 2) ? 51 : (qm == 3) ? 57 : (qm == 4) ? 64 : 72;
+  if (special) {
+    max_row = max_col = nT - 1;
+  } else {
     for (int i = lane; i < n; i += 32) {
-      const b200_coeff c = co[i];
-      int v;
-      if (bypass) {
-        v = c.level;
-      } else {
-        const long long fact = (long long)((scl ? scl[c.pos] : 1) * ls) << qd;
-        long long q = ((long long)c.level * fact + (1ll << (bd_shift - 1))) >> bd_shift;
-        v = (int)max(-32768ll, min(32767ll, q));
-      }
-      const int pos = rotate ? (nT * nT - 1 - c.pos) : c.pos;
-      coef[pos] = (int16_t)v;
+      const int pos = co[i].pos;
       max_row = max(max_row, pos >> log2);
       max_col = max(max_col, pos & (nT - 1));
     }
-    max_row = __reduce_max_sync(RC_FULL, max_row);
-    max_col = __reduce_max_sync(RC_FULL, max_col);
+    max_row = __reduce_max_sync(RC_FULL, max_row) & (nT - 1);
+    max_col = __reduce_max_sync(RC_FULL, max_col) & (nT - 1);
+  }
+  const int nq = (max_row >> 2) + 1;  // groups of 4 coefficient rows in use
+  uint32_t* cw = reinterpret_cast<uint32_t*>(coefT);
+  uint32_t* gw = reinterpret_cast<uint32_t*>(g);
+  constexpr int CW = RC_GSTRIDE / 2;  // words per column / row (odd: conflict-free across columns)
+  for (int o = lane; o < (max_col + 1) * 2 * nq; o += 32) cw[(o / (2 * nq)) * CW + o % (2 * nq)] = 0;
+  __syncwarp();
+  // ---- dequant + scatter (transform.cc:452-525) ----
+  for (int i = lane; i < n; i += 32) {
+    const b200_coeff c = co[i];
+    const int v = dequant_level(dq, c);
+    const int pos = (dq.rotate ? (nT * nT - 1 - c.pos) : c.pos) & (nT * nT - 1);
+    coefT[(pos & (nT - 1)) * RC_GSTRIDE + (pos >> log2)] = (int16_t)v;
   }
   __syncwarp();
 
-  if (flags & (B200_TU_BYPASS | B200_TU_TSKIP)) {
+  auto emit4 = [&](int x, int y, const int (&r)[4]) {  // 4 horizontally adjacent samples, x % 4 == 0
+    if (TO_RES) *reinterpret_cast<int4*>(res + x + (y << log2)) = make_int4(r[0], r[1], r[2], r[3]);
+    else add_row<P, 4>(dst + x + (size_t)y * dstride, r, bd);
+  };
+
+  if (special) {
     // transform.cc:408-448 / :548-596 with fallback-dct.cc:81-91,161-225
     const bool ts = !(flags & B200_TU_BYPASS);
     const int bd_shift = 20 - bd, ts_shift = 5 + log2, rnd = 1 << (bd_shift - 1);
+    auto value = [&](int x, int y) {
+      int c = coefT[x * RC_GSTRIDE + y];
+      if (ts) c = ((int)((unsigned)c << ts_shift) + rnd) >> bd_shift;
+      return c;
+    };
     if (flags & (B200_TU_RDPCM_H | B200_TU_RDPCM_V)) {
       const bool vert = flags & B200_TU_RDPCM_V;
       if (lane < nT) {
         int sum = 0;
         for (int k = 0; k < nT; k++) {
           const int x = vert ? lane : k, y = vert ? k : lane;
-          int c = coef[x + y * nT];
-          if (ts) c = ((int)((unsigned)c << ts_shift) + rnd) >> bd_shift;
-          sum += c;
-          emit(x, y, sum);
+          sum += value(x, y);
+          if (TO_RES) res[x + (y << log2)] = sum;
+          else dst[x + (size_t)y * dstride] = (P)clip_bd((int)dst[x + (size_t)y * dstride] + sum, bd);
         }
       }
     } else {
-      for (int i = lane; i < nT * nT; i += 32) {
-        int c = coef[i];
-        if (ts) c = ((int)((unsigned)c << ts_shift) + rnd) >> bd_shift;
-        emit(i & (nT - 1), i >> log2, c);
+      for (int o = lane; o < nT * nT / 4; o += 32) {
+        const int x = (o & (nT / 4 - 1)) * 4, y = o >> (log2 - 2);
+        const int r[4] = {value(x, y), value(x + 1, y), value(x + 2, y), value(x + 3, y)};
+        emit4(x, y, r);
       }
     }
     __syncwarp();
     return;
   }
 
+  // ---- inverse DCT (fallback-dct.cc:550-691) ----
+  const uint32_t* mt = (nT == 32) ? &tb.m32[0][0] : &tb.m16[0][0];  // [jq][i], nT words per jq
   const int post_shift = 20 - bd, rnd2 = 1 << (post_shift - 1);
-  if (flags & B200_TU_DST) {
-    // fallback-dct.cc:269-407 (mat_8_357 :260-265); m(j,i) selected without a local-memory table
-    auto m = [](int j, int i) -> int {
-      const int t[16] = {29, 55, 74, 84, 74, 74, 0, -74, 84, -29, -74, 55, 55, -84, 74, -29};
-      int r = 0;
-#pragma unroll
-      for (int k = 0; k < 16; k++) r = (k == j * 4 + i) ? t[k] : r;
-      return r;
-    };
-    if (lane < 16) {
-      const int c = lane & 3, i = lane >> 2;
-      int sum = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) sum += m(j, i) * coef[c + j * 4];
-      g[i * RC_GSTRIDE + c] = (int16_t)clip3i(-32768, 32767, (sum + 64) >> 7);
+  // pass 1 (columns): item = (column c <= max_col, block ib of 4 output rows); lanes run over ib first
+  for (int o = lane; o < (max_col + 1) << (log2 - 2); o += 32) {
+    const int ib = o & (nT / 4 - 1), c = o >> (log2 - 2);
+    int acc[4] = {64, 64, 64, 64};
+    const uint32_t* cp = cw + c * CW;
+    for (int jq = 0; jq < nq; jq++) {
+      const uint32_t c0 = cp[2 * jq], c1 = cp[2 * jq + 1];
+      const uint4 m = *reinterpret_cast<const uint4*>(mt + jq * nT + 4 * ib);
+      acc[0] = dp2a_hi(c1, m.x, dp2a_lo(c0, m.x, acc[0]));
+      acc[1] = dp2a_hi(c1, m.y, dp2a_lo(c0, m.y, acc[1]));
+      acc[2] = dp2a_hi(c1, m.z, dp2a_lo(c0, m.z, acc[2]));
+      acc[3] = dp2a_hi(c1, m.w, dp2a_lo(c0, m.w, acc[3]));
     }
-    __syncwarp();
-    if (lane < 16) {
-      const int i = lane & 3, y = lane >> 2;
-      int sum = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) sum += m(j, i) * g[y * RC_GSTRIDE + j];
-      emit(i, y, clip3i(-32768, 32767, (sum + rnd2) >> post_shift));
-    }
-    __syncwarp();
-    return;
+    for (int r = 0; r < 4; r++) g[(4 * ib + r) * RC_GSTRIDE + c] = (int16_t)clip16(acc[r] >> 7);
   }
-
-  // ---- inverse DCT (fallback-dct.cc:550-691); zero rows/columns beyond the last coefficient are skipped ----
-  const int fact = 32 >> log2;
-  for (int o = lane; o < nT * nT; o += 32) {  // pass 1: columns.  o -> (i = output row, c = column)
-    const int c = o & (nT - 1), i = o >> log2;
-    int sum = 0;
-    if (c <= max_col)
-      for (int j = 0; j <= max_row; j++) sum += (int)dct[fact * j][i] * (int)coef[c + j * nT];
-    g[i * RC_GSTRIDE + c] = (int16_t)clip3i(-32768, 32767, (sum + 64) >> 7);
+  if ((max_col & 3) != 3) {  // the row pass reads whole groups of 4 columns: clear the rest of the last group
+    const int c0 = max_col + 1, nc = 3 - (max_col & 3);
+    for (int o = lane; o < nT * nc; o += 32) g[(o / nc) * RC_GSTRIDE + c0 + o % nc] = 0;
   }
   __syncwarp();
-  for (int o = lane; o < nT * nT; o += 32) {  // pass 2: rows.  lanes along x: g broadcast, dct row contiguous, dst contiguous
-    const int i = o & (nT - 1), y = o >> log2;
-    int sum = 0;
-    for (int j = 0; j <= max_col; j++) sum += (int)dct[fact * j][i] * (int)g[y * RC_GSTRIDE + j];
-    emit(i, y, (sum + rnd2) >> post_shift);
+  // pass 2 (rows): item = (row y, block ib of 4 output columns)
+  const int nq2 = (max_col >> 2) + 1;
+  for (int o = lane; o < nT << (log2 - 2); o += 32) {
+    const int ib = o & (nT / 4 - 1), y = o >> (log2 - 2);
+    int acc[4] = {rnd2, rnd2, rnd2, rnd2};
+    const uint32_t* gp = gw + y * CW;
+    for (int jq = 0; jq < nq2; jq++) {
+      const uint32_t g0 = gp[2 * jq], g1 = gp[2 * jq + 1];
+      const uint4 m = *reinterpret_cast<const uint4*>(mt + jq * nT + 4 * ib);
+      acc[0] = dp2a_hi(g1, m.x, dp2a_lo(g0, m.x, acc[0]));
+      acc[1] = dp2a_hi(g1, m.y, dp2a_lo(g0, m.y, acc[1]));
+      acc[2] = dp2a_hi(g1, m.z, dp2a_lo(g0, m.z, acc[2]));
+      acc[3] = dp2a_hi(g1, m.w, dp2a_lo(g0, m.w, acc[3]));
+    }
+    const int r[4] = {acc[0] >> post_shift, acc[1] >> post_shift, acc[2] >> post_shift, acc[3] >> post_shift};
+    emit4(4 * ib, y, r);
   }
   __syncwarp();
 }
@@ -474,7 +470,6 @@ __global__ void __launch_bounds__(RC_THREADS) k_residual(DevPic pic, ReconArgs a
 {
   __shared__ ResidualSmem sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 32 * 32; i += RC_THREADS) sm.dct[i >> 5][i & 31] = c_dct[i >> 5][i & 31];
   for (int i = tid; i < (int)(sizeof(ResTables) / 4); i += RC_THREADS) reinterpret_cast<uint32_t*>(&sm.tb)[i] = reinterpret_cast<const uint32_t*>(&c_res)[i];
   __syncthreads();
   const int n4 = args.n_list - args.n_listw - args.n_list8;
@@ -493,7 +488,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_residual(DevPic pic, ReconArgs a
         }
       } else {
         tu_residual<P, false>(tu, args.coeffs + tu.coeff_off, args.scaling, dst, dstride, nullptr, c ? pic.bd_c : pic.bd_y, sm.coef[warp], sm.g[warp],
-                              sm.dct, lane);
+                              sm.tb, lane);
       }
     } else if (wi < Ww + W8) {
       const int idx = Ww + (wi - Ww) * 4 + (lane >> 3);
@@ -556,7 +551,6 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
   extern __shared__ __align__(16) uint8_t smem_raw[];
   IntraSmem<P>& sm = *reinterpret_cast<IntraSmem<P>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 32 * 32; i += RC_THREADS) sm.dct[i >> 5][i & 31] = c_dct[i >> 5][i & 31];
   for (int i = tid; i < (int)(sizeof(ResTables) / 4); i += RC_THREADS) reinterpret_cast<uint32_t*>(&sm.tb)[i] = reinterpret_cast<const uint32_t*>(&c_res)[i];
   __syncthreads();
   b200_tu* tus = sm.tu_s[warp];
@@ -615,7 +609,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
         const int idx = __ffs(rem) - 1;
         const b200_tu& tu = tus[idx];
         const int rb = __shfl_sync(RC_FULL, my_rbase, idx);
-        tu_residual<P, true>(tu, args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rb, bd, sm.coef[warp], sm.g[warp], sm.dct, lane);
+        tu_residual<P, true>(tu, args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rb, bd, sm.coef[warp], sm.g[warp], sm.tb, lane);
       }
     }
     // ---- wait: one flag per distinct external neighbour unit, one lane each ----

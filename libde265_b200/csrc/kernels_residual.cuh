@@ -17,7 +17,7 @@
 #pragma once
 #include "dev_common.cuh"
 
-struct ResTables {
+struct __align__(16) ResTables {
   uint32_t m4[4];       // [i]      bytes (M4[0][i], M4[1][i], M4[2][i], M4[3][i]),  M_nT[j][i] = core[(32/nT) j][i]
   uint32_t m8[2][8];    // [jq][i]  bytes M8[4jq .. 4jq+3][i]
   uint32_t m16[4][16];

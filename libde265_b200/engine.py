@@ -90,3 +90,11 @@ class Engine:
 
     def stream(self):
         return self.lib.b200_engine_stream(self._h)
+
+    def set_streams(self, n):
+        """Number of CUDA streams pictures are pipelined over (results do not depend on it)."""
+        capi.check(self.lib.b200_engine_set_streams(self._h, n), "b200_engine_set_streams")
+
+    def join(self):
+        """Stream 0 waits for everything issued so far on the other streams."""
+        capi.check(self.lib.b200_engine_join(self._h), "b200_engine_join")
