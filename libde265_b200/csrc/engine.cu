@@ -128,6 +128,8 @@ struct b200_engine {
   Surface slot[B200_MAX_SLOTS];
   SlotSync ssync[B200_MAX_SLOTS];
   int num_sms = 148;
+  int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
+  int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
   bool timing = false;
   std::vector<cudaEvent_t> tev;  // timing ring: TIMING_RING pictures x 7 events
   unsigned tcount = 0;           // pictures recorded since enable / reset
@@ -244,6 +246,9 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   int rc = init_tables(device);
   if (rc) { delete en; return rc; }
   en->n_ctx = 4;
+  if (const char* e = getenv("B200_INTRA_CTAS")) en->intra_ctas = std::max(1, std::min(4, atoi(e)));
+  if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
+  if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
   if (const char* e = getenv("B200_STREAMS")) en->n_ctx = std::max(1, std::min(B200_MAX_CTX, atoi(e)));
   for (int k = 0; k < B200_MAX_CTX; k++) {
     PipeCtx& cx = en->ctx[k];
@@ -435,6 +440,8 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
     ra.coeffs = (const b200_coeff*)(dbase + off[5]);
     ra.scaling = L.has_scaling ? dbase + off[11] : nullptr;
     ra.ticket = (unsigned int*)cx.sync_buf;
+    ra.region = en->region;
+    ra.poll_ns = en->poll_ns;
     const size_t cw4 = (size_t)((dp.cw + 3) / 4), ch4 = (size_t)((dp.ch + 3) / 4);
     ra.pend[0] = cx.sync_buf + 256;
     ra.pend[1] = ra.pend[0] + (size_t)dp.w4 * dp.h4;
@@ -466,7 +473,7 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
       ra.task_start = (const uint32_t*)(dbase + off[13]);
       ra.n_task = L.n_task;
       int grid = (L.n_task + RC_WARPS - 1) / RC_WARPS;
-      const int cap = en->num_sms * 2;
+      const int cap = en->num_sms * en->intra_ctas;
       if (grid > cap) grid = cap;
       k_intra<P><<<grid, RC_THREADS, sizeof(IntraSmem<P>), st>>>(dp, ra);
       en->launches += 2;
@@ -603,7 +610,7 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
       for (uint32_t i = 0; i < pic->n_tu; i++) {
         const b200_tu& tu = pic->tus[i];
         if (!(tu.flags & B200_TU_INTRA)) continue;
-        const int c = tu.cidx, G = 16 >> (c ? 1 : 0), nT = 1 << tu.log2_size;
+        const int c = tu.cidx, G = en->region >> (c ? 1 : 0), nT = 1 << tu.log2_size;
         long long key = (nT >= G) ? -2 - (long long)i : (((long long)(tu.y / G)) << 20) | (tu.x / G);
         if (key != cur_key[c]) {
           cur_key[c] = key;

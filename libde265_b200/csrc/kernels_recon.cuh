@@ -35,6 +35,8 @@ struct ReconArgs {
   const b200_tu* tus;         // decode order, as recorded
   const uint32_t* list;       // TU indices this launch works on (k_residual: any order; k_intra: grouped by task)
   int n_list;
+  int poll_ns;                // k_intra: cap of the polling back-off
+  int region;                 // k_intra: luma size of a region task (16 or 8)
   int n_listw, n_list8;       // k_residual: list = [n_listw warp-per-TU entries | n_list8 8x8 TUs | the rest: 4x4 TUs]
   const uint32_t* task_start; // k_intra: [n_task + 1] offsets into list, tasks in topological order
   int n_task;
@@ -317,6 +319,109 @@ __device__ __forceinline__ void tu_intra_small(const b200_tu& tu, P* dst, int ts
 }
 
 // -------------------------------------------------------------------------------------------------
+// Fast path of the small TUs: when the left column, the corner and the top row of the TU are all available (every TU
+// that does not touch a picture / slice / tile boundary or a constrained-intra hole), the substitution process
+// (intrapred.h:637-674) degenerates to index clamping: a missing bottom-left part repeats border[-nT], a missing
+// top-right part repeats border[nT].  Every lane then reads the border samples its pixels need straight from the
+// shared-memory tile (no gather, ballot or shuffle chain); the [1 2 1] smoothing of 8x8 luma TUs is applied on the fly.
+// This is the dependent part of the intra DAG, so what counts is its latency: ~50 mostly independent instructions.
+// -------------------------------------------------------------------------------------------------
+template <typename P, int LOG2>
+__device__ __forceinline__ void tu_intra_fast(const b200_tu& tu, P* dst, int ts, int bd, bool filter_plane, const int32_t* res, int lane)
+{
+  constexpr int nT = 1 << LOG2;
+  const int mode = tu.intra_mode, cidx = tu.cidx;
+  const uint64_t avail = tu.avail;
+  const int lo = ((avail >> (nT / 4)) & 1) ? -2 * nT : -nT;                          // first bottom-left group available?
+  const int hi = ((avail >> (B200_AVAIL_TOP_BIT0 + nT / 4)) & 1) ? 2 * nT : nT;      // first top-right group available?
+  // (groups are 4 samples; for nT == 8 the second bottom-left / top-right group may be missing on its own)
+  const int lo2 = (nT == 8 && lo < -nT && !((avail >> 3) & 1)) ? -12 : lo;
+  const int hi2 = (nT == 8 && hi > nT && !((avail >> (B200_AVAIL_TOP_BIT0 + 3)) & 1)) ? 12 : hi;
+  auto S = [&](int i) -> int {  // substituted border sample
+    i = min(max(i, lo2), hi2);
+    return (int)dst[(i < 0) ? (-i - 1) * ts - 1 : i - 1 - ts];
+  };
+  bool smooth = false;
+  if (nT == 8 && filter_plane && mode != 1) smooth = min(abs(mode - 26), abs(mode - 10)) > 7;
+  auto B = [&](int i) -> int {  // border sample after the optional smoothing (intrapred.h:185-258)
+    if (nT == 8 && smooth && i > -2 * nT && i < 2 * nT) return (S(i - 1) + 2 * S(i) + S(i + 1) + 2) >> 2;
+    return S(i);
+  };
+  constexpr int NP = (nT == 4) ? 1 : 2;  // pixels per lane (4x4: lanes 16..31 idle)
+  int px[NP];
+  if (mode == 0) {  // planar, intrapred.h:261-285
+    const int tr = B(1 + nT), bl = B(-1 - nT);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const int o = lane + 32 * p, x = o & (nT - 1), y = (o >> LOG2) & (nT - 1);
+      px[p] = ((nT - 1 - x) * B(-1 - y) + (x + 1) * tr + (nT - 1 - y) * B(1 + x) + (y + 1) * bl + nT) >> (LOG2 + 1);
+    }
+  } else if (mode == 1) {  // DC, intrapred.h:288-322 (never smoothed)
+    const int i = lane - nT;  // lanes 0..2nT-1 <-> border[-nT..-1], border[1..nT]
+    const int mine = (lane < 2 * nT) ? S(i < 0 ? i : i + 1) : 0;
+    const int dc = (__reduce_add_sync(RC_FULL, mine) + nT) >> (LOG2 + 1);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const int o = lane + 32 * p, x = o & (nT - 1), y = (o >> LOG2) & (nT - 1);
+      int v = dc;
+      if (cidx == 0) {
+        if (x == 0 && y == 0) v = (S(-1) + 2 * dc + S(1) + 2) >> 2;
+        else if (y == 0) v = (S(x + 1) + 3 * dc + 2) >> 2;
+        else if (x == 0) v = (S(-y - 1) + 3 * dc + 2) >> 2;
+      }
+      px[p] = v;
+    }
+  } else {  // angular, intrapred.h:330-433
+    const int angle = k_intra_angle[mode];
+    const bool vert = mode >= 18;
+    const int sgn = vert ? 1 : -1;
+    const int inv = (angle < 0) ? (int)k_inv_angle[mode - 11] : 0;
+    const bool bfilt = (cidx == 0 && !(tu.flags & B200_TU_NO_BOUNDARY_FILTER) && (mode == 26 || mode == 10));
+    // ref[k] = border[sgn*k] for k >= 0, border[-sgn*((k*inv+128)>>8)] for the projected part k < 0
+    auto R = [&](int k) -> int { return B(k >= 0 ? sgn * k : -sgn * ((k * inv + 128) >> 8)); };
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const int o = lane + 32 * p, x = o & (nT - 1), y = (o >> LOG2) & (nT - 1);
+      const int a = vert ? y : x, b = vert ? x : y;
+      const int idx = ((a + 1) * angle) >> 5, fact = ((a + 1) * angle) & 31;
+      const int r1 = R(b + idx + 1), r2 = R(b + idx + 2);
+      int v = fact ? ((32 - fact) * r1 + fact * r2 + 16) >> 5 : r1;
+      if (bfilt) {
+        if (mode == 26 && x == 0) v = clip_bd(B(1) + ((B(-1 - y) - B(0)) >> 1), bd);
+        if (mode == 10 && y == 0) v = clip_bd(B(-1) + ((B(1 + x) - B(0)) >> 1), bd);
+      }
+      px[p] = v;
+    }
+  }
+  __syncwarp();  // all border reads done before the block is overwritten (the border does not overlap the block, but keeps the
+                 // read/write phases of consecutive TUs apart)
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const int o = lane + 32 * p, x = o & (nT - 1), y = (o >> LOG2) & (nT - 1);
+    if (o < nT * nT) {
+      int v = px[p];
+      if (res) v = clip_bd(v + res[o], bd);
+      dst[x + y * ts] = (P)v;
+    }
+  }
+  __syncwarp();
+}
+
+// fast path applicable?  left column, corner and top row (of the TU itself) available
+__device__ __forceinline__ bool intra_fast_ok(const b200_tu& tu)
+{
+  const int g = 1 << (tu.log2_size - 2);  // groups of 4 samples per side
+  const uint64_t need = ((1ull << g) - 1) | (1ull << B200_AVAIL_CORNER_BIT) | (((1ull << g) - 1) << B200_AVAIL_TOP_BIT0);
+  if ((tu.avail & need) != need) return false;
+  if (g == 2) {  // 8x8: the outer bottom-left / top-right group must not be available without the inner one (clamping
+                 // reproduces the substitution only for availability that ends once)
+    const unsigned bl = (unsigned)(tu.avail >> 2) & 3, tr = (unsigned)(tu.avail >> (B200_AVAIL_TOP_BIT0 + 2)) & 3;
+    if (bl == 2 || tr == 2) return false;
+  }
+  return true;
+}
+
+// -------------------------------------------------------------------------------------------------
 // Large TUs (nT = 16 or 32): neighbour samples straight from the picture plane in global memory (`gsrc` = the
 // TU's top-left sample, row stride gstride; .cg loads: written by other SMs during this launch), prediction to
 // `dst` in shared memory (row stride nT), border arrays in shared memory.
@@ -376,7 +481,7 @@ __device__ void tu_intra_large(const b200_tu& tu, const P* gsrc, int gstride, P*
   const P* bsrc = b0;
   if (filter_plane && mode != 1) {
     const int d = min(abs(mode - 26), abs(mode - 10));
-    const bool filt = (nT == 16) ? (d > 1) : (d > 0);
+    const bool filt = d > ((nT == 8) ? 7 : (nT == 16) ? 1 : 0);  // intraHorVerDistThres, intrapred.h:196-203
     if (filt) {
       const bool strong = (pic_flags & B200_PIC_STRONG_INTRA_SMOOTHING) && cidx == 0 && nT == 32 &&
                           abs((int)b0[0] + (int)b0[64] - 2 * (int)b0[32]) < (1 << (bd_luma - 5)) &&
@@ -571,8 +676,8 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     const b200_tu tu0 = tus[0];
     const int c = tu0.cidx, sh = c ? 1 : 0;
     const int bd = c ? pic.bd_c : pic.bd_y;
-    const int G = 16 >> sh;  // region size in this plane's samples
-    const bool region = (1 << tu0.log2_size) <= 8;
+    const int G = args.region >> sh;  // region size in this plane's samples
+    const bool region = (1 << tu0.log2_size) <= min(G, 8);  // small TUs on a shared-memory tile; larger ones straight from the picture
     const int rx = region ? tu0.x & ~(G - 1) : tu0.x, ry = region ? tu0.y & ~(G - 1) : tu0.y;  // dependency frame origin
     const bool filter_plane = !(pic.flags & B200_PIC_INTRA_SMOOTHING_OFF) && (c == 0 || pic.chroma == 3);
     const int pwid = c ? pic.cw : pic.w, phei = c ? pic.ch : pic.h;
@@ -631,7 +736,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
         const bool busy = (f && *f) || (f2 && *f2);
         if (!__any_sync(RC_FULL, busy)) break;
         __nanosleep(ns);
-        if (ns < 256) ns *= 2;
+        if (ns < (unsigned)args.poll_ns) ns *= 2;
       }
     }
     __threadfence();  // acquire: the neighbours' samples were published before their flags were cleared
@@ -667,7 +772,11 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
       int rbase = 0;
       for (uint32_t i = 0; i < count; i++) {
         const b200_tu& tu = tus[i];
-        tu_intra_small<P>(tu, tile + (tu.y - ry) * TS + (tu.x - rx), TS, bd, filter_plane, (tu.flags & B200_TU_CBF) ? res + rbase : nullptr, lane);
+        P* tdst = tile + (tu.y - ry) * TS + (tu.x - rx);
+        const int32_t* tres = (tu.flags & B200_TU_CBF) ? res + rbase : nullptr;
+        if (!intra_fast_ok(tu)) tu_intra_small<P>(tu, tdst, TS, bd, filter_plane, tres, lane);
+        else if (tu.log2_size == 2) tu_intra_fast<P, 2>(tu, tdst, TS, bd, filter_plane, tres, lane);
+        else tu_intra_fast<P, 3>(tu, tdst, TS, bd, filter_plane, tres, lane);
         rbase += 1 << (2 * tu.log2_size);
       }
       for (int o = lane; o < gw * gh; o += 32) {
