@@ -681,6 +681,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     const int rx = region ? tu0.x & ~(G - 1) : tu0.x, ry = region ? tu0.y & ~(G - 1) : tu0.y;  // dependency frame origin
     const bool filter_plane = !(pic.flags & B200_PIC_INTRA_SMOOTHING_OFF) && (c == 0 || pic.chroma == 3);
     const int pwid = c ? pic.cw : pic.w, phei = c ? pic.ch : pic.h;
+    int covered = 0;
     {
       // residuals of all the task's TUs, in parallel where the sizes allow: lane i owns TU i's record; 4x4 TUs run one
       // per lane, 8x8 TUs one per quarter-warp, larger ones one after the other on the whole warp.  res holds the TUs'
@@ -695,6 +696,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
         if (lane >= d) incl += up;
       }
       const int my_rbase = incl - sz;
+      covered = __shfl_sync(RC_FULL, incl, 31);  // samples this task writes
       const bool cbf = mine && (mytu.flags & B200_TU_CBF);
       const unsigned m8 = __ballot_sync(RC_FULL, cbf && l2 == 3), mw = __ballot_sync(RC_FULL, cbf && l2 > 3);
       uint32_t* scratch = reinterpret_cast<uint32_t*>(sm.coef[warp]);
@@ -756,11 +758,15 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     } else {
       // ---- a region of small TUs: stage region + top row (2G) + left column (2G) in shared memory, run the TUs in order ----
       const int TS = RC_TILE_STRIDE;
-      P* tile = blk + TS + 1;  // tile(0,0) = region origin; tile(-1,-1) is blk[0]
+      P* tile = blk + TS + 4;  // tile(0,0) = region origin, 4-byte aligned; tile(-1,-1) is blk[3]
       const int gw = min(G, pwid - rx), gh = min(G, phei - ry);
-      for (int o = lane; o < gw * gh; o += 32) {
-        const int x = o % gw, y = o / gw;
-        tile[y * TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx + x);
+      const bool full = (gw == G) && (gh == G);
+      // the interior is only needed where this task does not write it itself (regions partly covered by inter blocks)
+      if (covered < gw * gh) {
+        for (int o = lane; o < gw * gh; o += 32) {
+          const int x = o % gw, y = o / gw;
+          tile[y * TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx + x);
+        }
       }
       if (ry > 0)
         for (int x = lane - 1; x < 2 * G; x += 32)
@@ -779,18 +785,27 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
         else tu_intra_fast<P, 3>(tu, tdst, TS, bd, filter_plane, tres, lane);
         rbase += 1 << (2 * tu.log2_size);
       }
-      for (int o = lane; o < gw * gh; o += 32) {
-        const int x = o % gw, y = o / gw;
-        row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y)[rx + x] = tile[y * TS + x];
+      if (full) {  // whole rows as 4-byte words (tile rows are 4-byte aligned: TS * sizeof(P) and the origin offset are multiples of 4)
+        const int wpr = G * (int)sizeof(P) / 4;  // words per row
+        for (int o = lane; o < G * wpr; o += 32) {
+          const int y = o / wpr, u = o % wpr;  // wpr is a power of two
+          reinterpret_cast<uint32_t*>(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx)[u] = reinterpret_cast<const uint32_t*>(tile + y * TS)[u];
+        }
+      } else {
+        for (int o = lane; o < gw * gh; o += 32) {
+          const int x = o % gw, y = o / gw;
+          row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y)[rx + x] = tile[y * TS + x];
+        }
       }
     }
     __threadfence();  // release: samples before flags
     __syncwarp();
-    for (uint32_t i = 0; i < count; i++) {
-      const b200_tu& tu = tus[i];
+    if (lane < (int)count) {  // one lane per TU clears the TU's pending units
+      const b200_tu& tu = tus[lane];
       const int n4 = 1 << (tu.log2_size - 2), pw = args.pend_w[c];
-      uint8_t* pend = args.pend[c] + (tu.y >> 2) * pw + (tu.x >> 2);
-      for (int o = lane; o < n4 * n4; o += 32) *reinterpret_cast<volatile uint8_t*>(pend + (o / n4) * pw + (o % n4)) = 0;
+      volatile uint8_t* pend = args.pend[c] + (tu.y >> 2) * pw + (tu.x >> 2);
+      for (int j = 0; j < n4; j++)
+        for (int i = 0; i < n4; i++) pend[j * pw + i] = 0;
     }
     __syncwarp();
     if (args.trace && lane == 0) {
