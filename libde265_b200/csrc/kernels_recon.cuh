@@ -633,21 +633,22 @@ __global__ void k_mark_pending(ReconArgs args)
 // Dependency set of a task = the distinct 4x4 units OUTSIDE its frame (region, or the single large TU) that its
 // TUs' availability masks let them read: at most `span` units left of it (top-down), the corner and `span`
 // units above it (left-to-right), span = 2G/4 for a region, nT/2 for a large TU.
-__device__ __forceinline__ void dep_units_of(const b200_tu& tu, int rx, int ry, int span, uint64_t& left, bool& corner, uint64_t& top)
+// One TU's contribution (bit masks, span <= 16): left units bit u = unit row u left of the frame, top units bit u = unit
+// column u above it, corner.  Lanes compute their own TU's masks and the warp ORs them.
+__device__ __forceinline__ void dep_units_of(const b200_tu& tu, int rx, int ry, int span, unsigned& left, bool& corner, unsigned& top)
 {
-  const int nT = 1 << tu.log2_size, half = nT / 2;
+  const int half = 1 << (tu.log2_size - 1);  // availability groups per side (nT/2 groups of 4 samples = 2nT samples)
   const int ux0 = (tu.x - rx) >> 2, uy0 = (tu.y - ry) >> 2;  // TU position inside the frame, in units
   const uint64_t avail = tu.avail;
+  const unsigned gm = (half >= 32) ? 0xffffffffu : ((1u << half) - 1u), sm = (1u << span) - 1u;
+  const bool cb = (avail >> B200_AVAIL_CORNER_BIT) & 1;
   if (ux0 == 0) {  // left neighbours are outside the frame
-    for (int g = 0; g < half; g++)
-      if (((avail >> g) & 1) && uy0 + g < span) left |= 1ull << (uy0 + g);
-    if ((avail >> B200_AVAIL_CORNER_BIT) & 1) { if (uy0 == 0) corner = true; else left |= 1ull << (uy0 - 1); }
-  } else if (uy0 == 0 && ((avail >> B200_AVAIL_CORNER_BIT) & 1)) {
-    top |= 1ull << (ux0 - 1);
+    left |= (((unsigned)avail & gm) << uy0) & sm;
+    if (cb) { if (uy0 == 0) corner = true; else left |= 1u << (uy0 - 1); }
+  } else if (uy0 == 0 && cb) {
+    top |= 1u << (ux0 - 1);
   }
-  if (uy0 == 0)
-    for (int k = 0; k < half; k++)
-      if (((avail >> (B200_AVAIL_TOP_BIT0 + k)) & 1) && ux0 + k < span) top |= 1ull << (ux0 + k);
+  if (uy0 == 0) top |= (((unsigned)(avail >> B200_AVAIL_TOP_BIT0) & gm) << ux0) & sm;
 }
 
 template <typename P>
@@ -722,9 +723,12 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     // ---- wait: one flag per distinct external neighbour unit, one lane each ----
     {
       const int span = region ? (2 * G) >> 2 : (1 << tu0.log2_size) >> 1;
-      uint64_t left = 0, top = 0;
+      unsigned left = 0, top = 0;
       bool corner = false;
-      for (uint32_t i = 0; i < count; i++) dep_units_of(tus[i], rx, ry, span, left, corner, top);
+      if (lane < (int)count) dep_units_of(tus[lane], rx, ry, span, left, corner, top);
+      left = __reduce_or_sync(RC_FULL, left);
+      top = __reduce_or_sync(RC_FULL, top);
+      corner = __any_sync(RC_FULL, corner);
       const int pw = args.pend_w[c];
       const uint8_t* pend = args.pend[c] + (ry >> 2) * pw + (rx >> 2);
       const volatile uint8_t* f = nullptr;
