@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -135,6 +136,8 @@ struct b200_engine {
   unsigned tcount = 0;           // pictures recorded since enable / reset
   cudaEvent_t* ev = nullptr;     // events of the picture being submitted
   uint64_t launches = 0;
+  double host_s[4] = {0, 0, 0, 0};  // submit_picture host time: plan, staging wait, pack, launches (B200_HOST_PROF=1 prints at destroy)
+  uint64_t host_n = 0;
   // host scratch reused across pictures
   std::vector<uint32_t> ctb_count, tiles, list_a, list_a8, list_a4, list_b, diag_count, task_of, task_first, task_start, task_order;
 };
@@ -272,6 +275,10 @@ extern "C" void b200_engine_destroy(b200_engine* en)
   if (!en) return;
   cudaSetDevice(en->device);
   cudaDeviceSynchronize();
+  if (getenv("B200_HOST_PROF") && en->host_n)
+    fprintf(stderr, "[b200] submit_picture host ms/picture over %llu pictures: plan %.3f  staging-wait %.3f  pack %.3f  launch %.3f\n",
+            (unsigned long long)en->host_n, 1e3 * en->host_s[0] / en->host_n, 1e3 * en->host_s[1] / en->host_n, 1e3 * en->host_s[2] / en->host_n,
+            1e3 * en->host_s[3] / en->host_n);
   for (auto& s : en->slot) surface_free(s);
   for (auto& cx : en->ctx) {
     surface_free(cx.scratch);
@@ -814,20 +821,27 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
   if (!en || !pic) return set_err(B200_ERR_INVALID, "null argument");
   CU(cudaSetDevice(en->device));
   PicLayout L;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   int rc = plan_picture(en, pic, &L);
   if (rc) return rc;
+  const double t1 = now();
   const int k = pick_ctx(en);
   PipeCtx& cx = en->ctx[k];
   StagingSet& ss = cx.stage[cx.cur_stage];
   cx.cur_stage ^= 1;
   rc = ensure_staging(ss, L.total);
   if (rc) return rc;
+  const double t2 = now();
   rc = pack_picture(en, pic, L, ss.host);
   if (rc) return rc;
+  const double t3 = now();
   rc = run_layout(en, k, L, ss.dev, ss.host);
   if (rc) return rc;
   CU(cudaEventRecord(ss.done, cx.stream));
   ss.in_flight = true;
+  en->host_s[0] += t1 - t0; en->host_s[1] += t2 - t1; en->host_s[2] += t3 - t2; en->host_s[3] += now() - t3;
+  en->host_n++;
   return B200_OK;
 }
 
