@@ -122,7 +122,19 @@ EXPORTS = [
     "b200_rec_add_pu", "b200_rec_add_tu", "b200_rec_set_ctb", "b200_rec_bs_map", "b200_rec_qp_map",
     "b200_rec_nofilt_map", "b200_rec_set_scaling_factors", "b200_rec_end_picture",
     "b200_picture_serialized_size", "b200_picture_serialize", "b200_picture_deserialize",
+    # include/b200hevc_dsp.h (boundary B1)
+    "b200_dsp_create", "b200_dsp_destroy", "b200_dsp_run_batch",
 ]
+
+(DSP_QPEL, DSP_EPEL, DSP_PRED_UNI, DSP_PRED_AVG, DSP_PRED_WEIGHTED, DSP_PRED_WEIGHTED_BI, DSP_TRANSFORM_ADD, DSP_DST_ADD, DSP_INTRA_DC,
+ DSP_INTRA_PLANAR, DSP_INTRA_ANGULAR, DSP_DEBLOCK_LUMA, DSP_DEBLOCK_CHROMA) = range(1, 14)
+
+
+class DspCmd(C.Structure):
+    """b200_dsp_cmd (include/b200hevc_dsp.h)."""
+    _fields_ = [("op", C.c_int32), ("bit_depth", C.c_int32), ("dst", C.c_void_p), ("dststride", C.c_ssize_t), ("src", C.c_void_p),
+                ("src2", C.c_void_p), ("srcstride", C.c_ssize_t), ("w", C.c_int32), ("h", C.c_int32), ("a", C.c_int32 * 8)]
+
 
 _lib = None
 
@@ -158,6 +170,10 @@ def load(path=None):
     lib.b200_engine_launch_count.argtypes = [vp]
     lib.b200_engine_launch_count.restype = C.c_uint64
     lib.b200_engine_stream.argtypes = [vp]
+    lib.b200_dsp_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.b200_dsp_destroy.argtypes = [vp]
+    lib.b200_dsp_destroy.restype = None
+    lib.b200_dsp_run_batch.argtypes = [vp, C.POINTER(DspCmd), C.c_int]
     lib.b200_engine_set_streams.argtypes = [vp, C.c_int]
     lib.b200_engine_join.argtypes = [vp]
     lib.b200_engine_stream.restype = vp

@@ -986,3 +986,4 @@ extern "C" int b200_engine_slot_device_planes(b200_engine* en, int slot, void* p
   for (int c = 0; c < 3; c++) { planes[c] = s.plane[c]; strides[c] = (size_t)s.pitch[c]; }
   return B200_OK;
 }
+#include "dsp_table.cuh"

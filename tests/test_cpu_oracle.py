@@ -35,7 +35,7 @@ def load_records(lib):
 
 # ---- C-ABI boundary ---------------------------------------------------------------------------------
 def test_library_exports_every_declared_symbol(b200lib):
-    hdr = open(os.path.join(ROOT, "include", "b200hevc.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "b200hevc.h")).read() + open(os.path.join(ROOT, "include", "b200hevc_dsp.h")).read()
     import re
     declared = set(re.findall(r"B200_API\s+[\w\s\*]+?\s+\*?(b200_\w+)\s*\(", hdr))
     assert declared, "no declarations parsed"
