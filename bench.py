@@ -198,7 +198,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from libde265_b200 import capi, synth
+    from libde265_b200 import capi, shard, synth
     from libde265_b200.engine import Engine
 
     if world > 1:
@@ -207,9 +207,9 @@ def main():
     eng = Engine(local_rank)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
 
-    seq, gen_s = build_workload(a.width, a.height, a.bit_depth, seed0=1000 + 100 * rank)
+    seq, gen_s = build_workload(a.width, a.height, a.bit_depth, seed0=shard.stream_seed(rank))
     params = seq[0].params
-    ref0 = synth.random_planes(a.width, a.height, a.bit_depth, 7 + rank)
+    ref0 = synth.random_planes(a.width, a.height, a.bit_depth, shard.reference_seed(rank))
     eng.upload_slot(0, params, ref0)  # POC 0 reference
     prepared = [eng.prepare(p) for p in seq]
     h2d_bytes = sum(int(p.pus.nbytes + p.weights.nbytes + p.tus.nbytes + p.coeffs.nbytes + p.slices.nbytes + p.ctbs.nbytes + p.bs_map.nbytes +
@@ -236,12 +236,7 @@ def main():
         e1.record(stream)
         e1.synchronize()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return shard.max_over_ranks(e0.elapsed_time(e1), "cuda")  # the job takes as long as its slowest rank
 
     def step_resident():
         for h in prepared:
