@@ -8,6 +8,12 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -99,6 +105,62 @@ struct StagingSet {
   bool in_flight = false;
 };
 
+// A few host threads for the per-picture host work (validation / work-list building of the PUs next to that of the TUs,
+// copying the record arrays into the pinned staging buffer): submit_picture is host-bound on large pictures otherwise.
+struct HostPool {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv, done_cv;
+  std::deque<std::function<void()>> q;
+  int pending = 0;
+  bool stop = false;
+  void start(int n)
+  {
+    for (int i = 0; i < n; i++)
+      th.emplace_back([this] {
+        for (;;) {
+          std::function<void()> f;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [this] { return stop || !q.empty(); });
+            if (stop && q.empty()) return;
+            f = std::move(q.front());
+            q.pop_front();
+          }
+          f();
+          {
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) done_cv.notify_all();
+          }
+        }
+      });
+  }
+  void run(std::function<void()> f)
+  {
+    if (th.empty()) { f(); return; }
+    {
+      std::lock_guard<std::mutex> lk(m);
+      q.push_back(std::move(f));
+      pending++;
+    }
+    cv.notify_one();
+  }
+  void wait()
+  {
+    std::unique_lock<std::mutex> lk(m);
+    done_cv.wait(lk, [this] { return pending == 0; });
+  }
+  ~HostPool()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+  }
+};
+
 // One pipeline context = one CUDA stream with everything a picture in flight needs privately.  Pictures are issued
 // round-robin onto the contexts; cross-context ordering comes from per-slot events (SlotSync): a picture waits for the
 // writers of its reference slots and for every earlier reader / writer of its destination slot.  So pictures that do
@@ -128,6 +190,7 @@ struct b200_engine {
   int n_ctx = 1, next_ctx = 0;
   Surface slot[B200_MAX_SLOTS];
   SlotSync ssync[B200_MAX_SLOTS];
+  HostPool pool;
   int num_sms = 148;
   int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
   int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
@@ -139,13 +202,14 @@ struct b200_engine {
   double host_s[4] = {0, 0, 0, 0};  // submit_picture host time: plan, staging wait, pack, launches (B200_HOST_PROF=1 prints at destroy)
   uint64_t host_n = 0;
   // host scratch reused across pictures
-  std::vector<uint32_t> ctb_count, tiles, list_a, list_a8, list_a4, list_b, diag_count, task_of, task_first, task_start, task_order;
+  std::vector<uint32_t> part_a[4][3];  // plan_tus_validate: per part, per k_residual class
+  std::vector<uint32_t> ctb_count, tiles, list_a, list_a8, list_a4, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
 };
 
 #define TIMING_RING 256
 
 struct PicLayout {
-  size_t off[14] = {}, total = 0;
+  size_t off[14] = {}, total = 0, raw_total = 0, unit_cap = 0;
   uint32_t ref_mask = 0;  // slots the picture's PUs read
   int n_tiles = 0, n_a = 0, n_aw = 0, n_a8 = 0, n_b = 0, n_task = 0;
   bool run_deblock = false, run_sao = false, has_scaling = false;
@@ -249,6 +313,11 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   int rc = init_tables(device);
   if (rc) { delete en; return rc; }
   en->n_ctx = 4;
+  {
+    int nt = 8;
+    if (const char* e = getenv("B200_HOST_THREADS")) nt = std::max(0, std::min(16, atoi(e)));
+    en->pool.start(nt);
+  }
   if (const char* e = getenv("B200_INTRA_CTAS")) en->intra_ctas = std::max(1, std::min(4, atoi(e)));
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
@@ -276,7 +345,7 @@ extern "C" void b200_engine_destroy(b200_engine* en)
   cudaSetDevice(en->device);
   cudaDeviceSynchronize();
   if (getenv("B200_HOST_PROF") && en->host_n)
-    fprintf(stderr, "[b200] submit_picture host ms/picture over %llu pictures: plan %.3f  staging-wait %.3f  pack %.3f  launch %.3f\n",
+    fprintf(stderr, "[b200] submit_picture host ms/picture over %llu pictures: validate+staging-wait %.3f  plan+pack (threaded) %.3f  (unused %.3f)  launch %.3f\n",
             (unsigned long long)en->host_n, 1e3 * en->host_s[0] / en->host_n, 1e3 * en->host_s[1] / en->host_n, 1e3 * en->host_s[2] / en->host_n,
             1e3 * en->host_s[3] / en->host_n);
   for (auto& s : en->slot) surface_free(s);
@@ -528,7 +597,14 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
 
 // Validates the records, groups TUs by CTB, cuts PUs into MC tiles and packs everything into `hb`
 // (which must hold L->total bytes; call with hb == nullptr first to size it).
-static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
+// Section order in the staging buffer / device arena: the raw record arrays first (their offsets depend only on the
+// counts, so copying them can start before the work lists exist), then the lists the planner builds.
+//   0 pus, 1 weights, 2 tus, 5 coeffs, 6 slices, 7 ctbs, 8 bs_map, 9 qp_map, 10 nofilt_map, 11 scaling |
+//   3 list_a (non-intra TU indices by k_residual class), 4 list_b (intra TU indices by task), 12 MC units / tiles, 13 task_start
+static const int k_raw_sections[10] = {0, 1, 2, 5, 6, 7, 8, 9, 10, 11};
+static const int k_list_sections[4] = {3, 4, 12, 13};
+
+static int plan_begin(b200_engine* en, const b200_picture* pic, PicLayout* L, size_t* cap_total)
 {
   const b200_pic_params& p = pic->params;
   int rc = check_params(p);
@@ -546,6 +622,32 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
   L->run_deblock = !(p.flags & B200_PIC_SKIP_DEBLOCK) && pic->bs_map && (p.stop_after_stage == B200_STAGE_ALL || p.stop_after_stage == B200_STAGE_DEBLOCK);
   L->run_sao = (p.flags & B200_PIC_SAO_ENABLED) && !(p.flags & B200_PIC_SKIP_SAO) && p.stop_after_stage == B200_STAGE_ALL;
 
+  for (int i = 0; i < n_ctb; i++)
+    if (pic->ctbs[i].slice_idx >= pic->n_slices) return set_err(B200_ERR_INVALID, "CTB %d slice index", i);
+  size_t sz[14] = {};
+  sz[0] = sizeof(b200_pu) * pic->n_pu;
+  sz[1] = sizeof(b200_weight_entry) * pic->n_weights;
+  sz[2] = sizeof(b200_tu) * pic->n_tu;
+  sz[5] = sizeof(b200_coeff) * pic->n_coeff;
+  sz[6] = sizeof(b200_slice_info) * pic->n_slices;
+  sz[7] = sizeof(b200_ctb_info) * (size_t)n_ctb;
+  sz[8] = L->run_deblock ? (size_t)w4 * h4 : 0;
+  sz[9] = (size_t)w8 * h8;
+  sz[10] = (size_t)w8 * h8;
+  sz[11] = L->has_scaling ? B200_SCALING_FACTOR_BYTES : 0;
+  size_t total = 0;
+  for (int i : k_raw_sections) { L->off[i] = total; total += align_up(sz[i], 256); }
+  L->raw_total = total;
+  // upper bound of the lists: every TU in one list, one task per TU; MC units cannot outnumber 4x8 blocks unless PUs overlap
+  L->unit_cap = (size_t)w4 * h4 / 2 + 64;
+  *cap_total = total + 3 * align_up(sizeof(uint32_t) * ((size_t)pic->n_tu + 1), 256) + align_up(sizeof(uint32_t) * L->unit_cap, 256) + 256;
+  return B200_OK;
+}
+
+// PU validation + MC work list (runs on a pool thread next to plan_tus)
+static int plan_pus(b200_engine* en, const b200_picture* pic, PicLayout* L)
+{
+  const b200_pic_params& p = pic->params;
   std::vector<uint32_t>& tiles = en->tiles;
   tiles.clear();
   const bool wide = p.bit_depth_luma > 8;  // same rule as the launch_picture<P> dispatch
@@ -567,44 +669,54 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
         for (int ux = 0; ux * MC8_UW < pu.w; ux++) tiles.push_back(MC8_UNIT(i, ux, uy));
     }
   }
+  if (tiles.size() > L->unit_cap) return set_err(B200_ERR_INVALID, "PUs overlap (more MC units than the picture has 4x8 blocks)");
   L->n_tiles = (int)tiles.size();
-  // ---- TU validation + work lists: list_a = non-intra TUs with work, list_b = intra TUs in topological order
-  //      (CTB anti-diagonal x + 2y, then CTB raster, then decode order) ----
+  return B200_OK;
+}
+
+// TU validation + the k_residual work classes for the TU range [i0, i1) into the part's own lists (two parts run on pool
+// threads; plan_and_pack concatenates them).  Classes: warp per TU (16x16, 32x32, PCM) | quarter-warp per 8x8 | lane per 4x4.
+#define PLAN_TU_PARTS 4
+static int plan_tus_validate(b200_engine* en, const b200_picture* pic, int part, uint32_t i0, uint32_t i1)
+{
+  const b200_pic_params& p = pic->params;
+  std::vector<uint32_t>&la = en->part_a[part][0], &la8 = en->part_a[part][1], &la4 = en->part_a[part][2];
+  la.clear();
+  la8.clear();
+  la4.clear();
+  for (uint32_t i = i0; i < i1; i++) {
+    const b200_tu& tu = pic->tus[i];
+    const int nT = 1 << tu.log2_size;
+    const int pw = tu.cidx ? p.width / 2 : p.width, ph = tu.cidx ? p.height / 2 : p.height;
+    if (tu.log2_size < 2 || tu.log2_size > 5 || tu.cidx > 2 || (tu.cidx && !p.chroma_format_idc) || tu.x + nT > pw || tu.y + nT > ph ||
+        (tu.x & 3) || (tu.y & 3) || (tu.x & (nT - 1)) || (tu.y & (nT - 1)))
+      return set_err(B200_ERR_INVALID, "TU %u out of range", i);
+    if ((size_t)tu.coeff_off + tu.n_coeff > pic->n_coeff || tu.n_coeff > nT * nT) return set_err(B200_ERR_INVALID, "TU %u coefficient range", i);
+    if ((tu.flags & B200_TU_PCM) && tu.n_coeff != nT * nT) return set_err(B200_ERR_INVALID, "PCM TU %u sample count", i);
+    if (tu.flags & B200_TU_INTRA) {
+      if (tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
+    } else if (tu.flags & (B200_TU_CBF | B200_TU_PCM)) {
+      if ((tu.flags & B200_TU_PCM) || tu.log2_size > 3) la.push_back(i);
+      else if (tu.log2_size == 3) la8.push_back(i);
+      else la4.push_back(i);
+    }
+  }
+  return B200_OK;
+}
+
+// Intra work list (runs next to plan_tus_validate, so it must not trust the records: malformed TUs are skipped here and
+// rejected there).
+static int plan_tus_intra(b200_engine* en, const b200_picture* pic, PicLayout* L)
+{
+  const b200_pic_params& p = pic->params;
+  const int S = 1 << p.log2_ctb_size;
+  const int wctb = (p.width + S - 1) / S, hctb = (p.height + S - 1) / S;
   {
-    std::vector<uint32_t>& la = en->list_a;
     std::vector<uint32_t>& lb = en->list_b;
     std::vector<uint32_t>& dc = en->diag_count;
-    std::vector<uint32_t>&la8 = en->list_a8, &la4 = en->list_a4;
-    la.clear();
-    la8.clear();
-    la4.clear();
     const int n_diag = wctb + 2 * hctb;
-    dc.assign((size_t)n_diag + 1, 0);
-    uint32_t n_intra = 0;
-    for (uint32_t i = 0; i < pic->n_tu; i++) {
-      const b200_tu& tu = pic->tus[i];
-      const int sh = tu.cidx ? 1 : 0;
-      const int nT = 1 << tu.log2_size;
-      const int pw = tu.cidx ? p.width / 2 : p.width, ph = tu.cidx ? p.height / 2 : p.height;
-      if (tu.log2_size < 2 || tu.log2_size > 5 || tu.cidx > 2 || (tu.cidx && !p.chroma_format_idc) || tu.x + nT > pw || tu.y + nT > ph ||
-          (tu.x & 3) || (tu.y & 3) || (tu.x & (nT - 1)) || (tu.y & (nT - 1)))
-        return set_err(B200_ERR_INVALID, "TU %u out of range", i);
-      if ((size_t)tu.coeff_off + tu.n_coeff > pic->n_coeff || tu.n_coeff > nT * nT) return set_err(B200_ERR_INVALID, "TU %u coefficient range", i);
-      if ((tu.flags & B200_TU_PCM) && tu.n_coeff != nT * nT) return set_err(B200_ERR_INVALID, "PCM TU %u sample count", i);
-      if (tu.flags & B200_TU_INTRA) {
-        if (tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
-        n_intra++;
-      } else if (tu.flags & (B200_TU_CBF | B200_TU_PCM)) {
-        // k_residual work classes: warp per TU (16x16, 32x32, PCM) | quarter-warp per 8x8 TU | lane per 4x4 TU
-        if ((tu.flags & B200_TU_PCM) || tu.log2_size > 3) la.push_back(i);
-        else if (tu.log2_size == 3) la8.push_back(i);
-        else la4.push_back(i);
-      }
-    }
-    L->n_aw = (int)la.size();
-    L->n_a8 = (int)la8.size();
-    la.insert(la.end(), la8.begin(), la8.end());
-    la.insert(la.end(), la4.begin(), la4.end());
+    std::vector<uint32_t>& intra_idx = en->intra_idx;  // intra TUs in decode order
+    intra_idx.clear();
     // ---- intra tasks: the TUs of one plane inside one aligned 16x16-luma / 8x8-chroma region (contiguous per plane in
     //      decode order); a TU at least as large as the region is a task of its own ----
     std::vector<uint32_t>& task_of = en->task_of;        // per intra TU (in decode order): task id
@@ -617,6 +729,10 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
       for (uint32_t i = 0; i < pic->n_tu; i++) {
         const b200_tu& tu = pic->tus[i];
         if (!(tu.flags & B200_TU_INTRA)) continue;
+        if (tu.cidx > 2 || tu.log2_size < 2 || tu.log2_size > 5 || (((size_t)tu.x << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)wctb ||
+            (((size_t)tu.y << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)hctb)
+          continue;
+        intra_idx.push_back(i);
         const int c = tu.cidx, G = en->region >> (c ? 1 : 0), nT = 1 << tu.log2_size;
         long long key = (nT >= G) ? -2 - (long long)i : (((long long)(tu.y / G)) << 20) | (tu.x / G);
         if (key != cur_key[c]) {
@@ -627,7 +743,7 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
         task_of.push_back(cur_task[c]);
       }
     }
-    const uint32_t n_task = (uint32_t)task_first.size();
+    const uint32_t n_task = (uint32_t)task_first.size(), n_intra = (uint32_t)intra_idx.size();
     // topological order of tasks: CTB anti-diagonal x + 2y, ties in decode order of the first TU
     dc.assign((size_t)n_diag + 1, 0);
     auto diag_of = [&](uint32_t tu_idx) {
@@ -649,64 +765,57 @@ static int plan_picture(b200_engine* en, const b200_picture* pic, PicLayout* L)
     {
       std::vector<uint32_t>& fill = en->ctb_count;  // reuse as per-task fill cursor
       fill.assign(ts.begin(), ts.end() - 1);
-      uint32_t k = 0;
-      for (uint32_t i = 0; i < pic->n_tu; i++) {
-        if (!(pic->tus[i].flags & B200_TU_INTRA)) continue;
-        lb[fill[order[task_of[k]]]++] = i;
-        k++;
-      }
+      for (uint32_t k = 0; k < n_intra; k++) lb[fill[order[task_of[k]]]++] = intra_idx[k];
     }
     L->n_task = (int)n_task;
-    L->n_a = (int)la.size();
     L->n_b = (int)lb.size();
   }
-  // section order: 0 pus, 1 weights, 2 tus, 3 list_a (non-intra TU indices), 4 list_b (intra TU indices), 5 coeffs, 6 slices, 7 ctbs,
-  //                8 bs_map, 9 qp_map, 10 nofilt_map, 11 scaling, 12 tiles
-  size_t sz[14];
-  sz[0] = sizeof(b200_pu) * pic->n_pu;
-  sz[1] = sizeof(b200_weight_entry) * pic->n_weights;
-  sz[2] = sizeof(b200_tu) * pic->n_tu;
-  sz[3] = sizeof(uint32_t) * (size_t)L->n_a;
-  sz[4] = sizeof(uint32_t) * (size_t)L->n_b;
-  sz[5] = sizeof(b200_coeff) * pic->n_coeff;
-  sz[6] = sizeof(b200_slice_info) * pic->n_slices;
-  sz[7] = sizeof(b200_ctb_info) * (size_t)n_ctb;
-  sz[8] = L->run_deblock ? (size_t)w4 * h4 : 0;
-  sz[9] = (size_t)w8 * h8;
-  sz[10] = (size_t)w8 * h8;
-  sz[11] = L->has_scaling ? B200_SCALING_FACTOR_BYTES : 0;
-  sz[12] = sizeof(uint32_t) * (size_t)L->n_tiles;
-  sz[13] = L->n_task ? sizeof(uint32_t) * (size_t)(L->n_task + 1) : 0;
-  size_t total = 0;
-  for (int i = 0; i < 14; i++) { L->off[i] = total; total += align_up(sz[i], 256); }
-  L->total = total ? total : 256;
   return B200_OK;
 }
 
-static int pack_picture(b200_engine* en, const b200_picture* pic, const PicLayout& L, uint8_t* hb)
+static void plan_finish(PicLayout* L)
+{
+  size_t sz[14] = {};
+  sz[3] = sizeof(uint32_t) * (size_t)L->n_a;
+  sz[4] = sizeof(uint32_t) * (size_t)L->n_b;
+  sz[12] = sizeof(uint32_t) * (size_t)L->n_tiles;
+  sz[13] = L->n_task ? sizeof(uint32_t) * (size_t)(L->n_task + 1) : 0;
+  size_t total = L->raw_total;
+  for (int i : k_list_sections) { L->off[i] = total; total += align_up(sz[i], 256); }
+  L->total = total ? total : 256;
+}
+
+// part 0..2: the raw record arrays in three roughly equal shares (pool threads)
+static void pack_raw(const b200_picture* pic, const PicLayout& L, uint8_t* hb, int part)
 {
   const b200_pic_params& p = pic->params;
   const size_t* off = L.off;
   const int S = 1 << p.log2_ctb_size;
   const int wctb = (p.width + S - 1) / S, hctb = (p.height + S - 1) / S, n_ctb = wctb * hctb;
   const int w4 = (p.width + 3) / 4, h4 = (p.height + 3) / 4, w8 = (p.width + 7) / 8, h8 = (p.height + 7) / 8;
-  if (pic->n_pu) memcpy(hb + off[0], pic->pus, sizeof(b200_pu) * pic->n_pu);
-  if (pic->n_weights) memcpy(hb + off[1], pic->weights, sizeof(b200_weight_entry) * pic->n_weights);
-  if (pic->n_tu) memcpy(hb + off[2], pic->tus, sizeof(b200_tu) * pic->n_tu);
+  if (part == 0) {
+    if (pic->n_coeff) memcpy(hb + off[5], pic->coeffs, sizeof(b200_coeff) * pic->n_coeff);
+  } else if (part == 1) {
+    if (pic->n_tu) memcpy(hb + off[2], pic->tus, sizeof(b200_tu) * pic->n_tu);
+    memcpy(hb + off[6], pic->slices, sizeof(b200_slice_info) * pic->n_slices);
+    memcpy(hb + off[7], pic->ctbs, sizeof(b200_ctb_info) * (size_t)n_ctb);
+  } else {
+    if (pic->n_pu) memcpy(hb + off[0], pic->pus, sizeof(b200_pu) * pic->n_pu);
+    if (pic->n_weights) memcpy(hb + off[1], pic->weights, sizeof(b200_weight_entry) * pic->n_weights);
+    if (L.run_deblock) memcpy(hb + off[8], pic->bs_map, (size_t)w4 * h4);
+    memcpy(hb + off[9], pic->qp_map, (size_t)w8 * h8);
+    memcpy(hb + off[10], pic->nofilt_map, (size_t)w8 * h8);
+    if (L.has_scaling) memcpy(hb + off[11], pic->scaling_factors, B200_SCALING_FACTOR_BYTES);
+  }
+}
+
+static void pack_lists(b200_engine* en, const PicLayout& L, uint8_t* hb)
+{
+  const size_t* off = L.off;
   if (L.n_a) memcpy(hb + off[3], en->list_a.data(), sizeof(uint32_t) * (size_t)L.n_a);
   if (L.n_b) memcpy(hb + off[4], en->list_b.data(), sizeof(uint32_t) * (size_t)L.n_b);
   if (L.n_task) memcpy(hb + off[13], en->task_start.data(), sizeof(uint32_t) * (size_t)(L.n_task + 1));
-  if (pic->n_coeff) memcpy(hb + off[5], pic->coeffs, sizeof(b200_coeff) * pic->n_coeff);
-  memcpy(hb + off[6], pic->slices, sizeof(b200_slice_info) * pic->n_slices);
-  for (int i = 0; i < n_ctb; i++)
-    if (pic->ctbs[i].slice_idx >= pic->n_slices) return set_err(B200_ERR_INVALID, "CTB %d slice index", i);
-  memcpy(hb + off[7], pic->ctbs, sizeof(b200_ctb_info) * (size_t)n_ctb);
-  if (L.run_deblock) memcpy(hb + off[8], pic->bs_map, (size_t)w4 * h4);
-  memcpy(hb + off[9], pic->qp_map, (size_t)w8 * h8);
-  memcpy(hb + off[10], pic->nofilt_map, (size_t)w8 * h8);
-  if (L.has_scaling) memcpy(hb + off[11], pic->scaling_factors, B200_SCALING_FACTOR_BYTES);
   if (L.n_tiles) memcpy(hb + off[12], en->tiles.data(), sizeof(uint32_t) * (size_t)L.n_tiles);
-  return B200_OK;
 }
 
 static int ensure_staging(StagingSet& ss, size_t total)
@@ -720,6 +829,57 @@ static int ensure_staging(StagingSet& ss, size_t total)
     CU(cudaMallocHost(&ss.host, ss.cap));
     CU(cudaMalloc(&ss.dev, ss.cap));
   }
+  return B200_OK;
+}
+
+// Host side of one picture: validate, build the work lists, fill the pinned staging buffer.  The raw record arrays are
+// copied by pool threads and the PUs are planned on a pool thread while this thread plans the TUs.
+static int plan_and_pack(b200_engine* en, const b200_picture* pic, PicLayout* L, StagingSet& ss, double* t_plan_pack)
+{
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  size_t cap = 0;
+  int rc = plan_begin(en, pic, L, &cap);
+  if (rc) return rc;
+  rc = ensure_staging(ss, cap);
+  if (rc) return rc;
+  const double t1 = now();
+  uint8_t* hb = ss.host;
+  int rc_pu = B200_OK;
+  std::string err_pu;
+  en->pool.run([&] {
+    rc_pu = plan_pus(en, pic, L);
+    if (rc_pu) err_pu = g_err;  // the worker's thread-local message
+  });
+  int rc_tv[PLAN_TU_PARTS] = {};
+  std::string err_tv[PLAN_TU_PARTS];
+  for (int part = 0; part < PLAN_TU_PARTS; part++) {
+    const uint32_t i0 = (uint32_t)((uint64_t)pic->n_tu * part / PLAN_TU_PARTS), i1 = (uint32_t)((uint64_t)pic->n_tu * (part + 1) / PLAN_TU_PARTS);
+    en->pool.run([&, part, i0, i1] {
+      rc_tv[part] = plan_tus_validate(en, pic, part, i0, i1);
+      if (rc_tv[part]) err_tv[part] = g_err;
+    });
+  }
+  for (int part = 0; part < 3; part++) en->pool.run([=] { pack_raw(pic, *L, hb, part); });
+  rc = plan_tus_intra(en, pic, L);
+  en->pool.wait();
+  for (int part = 0; part < PLAN_TU_PARTS; part++)
+    if (rc_tv[part]) return set_err(rc_tv[part], "%s", err_tv[part].c_str());
+  if (rc) return rc;
+  {  // list_a = class by class, parts in order
+    std::vector<uint32_t>& la = en->list_a;
+    la.clear();
+    for (int cls = 0; cls < 3; cls++) {
+      for (int part = 0; part < PLAN_TU_PARTS; part++) la.insert(la.end(), en->part_a[part][cls].begin(), en->part_a[part][cls].end());
+      if (cls == 0) L->n_aw = (int)la.size();
+      if (cls == 1) L->n_a8 = (int)la.size() - L->n_aw;
+    }
+    L->n_a = (int)la.size();
+  }
+  if (rc_pu) return set_err(rc_pu, "%s", err_pu.c_str());
+  plan_finish(L);
+  pack_lists(en, *L, hb);
+  if (t_plan_pack) { t_plan_pack[0] = t1 - t0; t_plan_pack[1] = now() - t1; }
   return B200_OK;
 }
 
@@ -822,25 +982,19 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
   CU(cudaSetDevice(en->device));
   PicLayout L;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t0 = now();
-  int rc = plan_picture(en, pic, &L);
-  if (rc) return rc;
-  const double t1 = now();
   const int k = pick_ctx(en);
   PipeCtx& cx = en->ctx[k];
   StagingSet& ss = cx.stage[cx.cur_stage];
   cx.cur_stage ^= 1;
-  rc = ensure_staging(ss, L.total);
-  if (rc) return rc;
-  const double t2 = now();
-  rc = pack_picture(en, pic, L, ss.host);
+  double tp[2] = {0, 0};
+  int rc = plan_and_pack(en, pic, &L, ss, tp);
   if (rc) return rc;
   const double t3 = now();
   rc = run_layout(en, k, L, ss.dev, ss.host);
   if (rc) return rc;
   CU(cudaEventRecord(ss.done, cx.stream));
   ss.in_flight = true;
-  en->host_s[0] += t1 - t0; en->host_s[1] += t2 - t1; en->host_s[2] += t3 - t2; en->host_s[3] += now() - t3;
+  en->host_s[0] += tp[0]; en->host_s[1] += tp[1]; en->host_s[3] += now() - t3;
   en->host_n++;
   return B200_OK;
 }
@@ -851,13 +1005,10 @@ extern "C" int b200_engine_prepare_picture(b200_engine* en, const b200_picture* 
   CU(cudaSetDevice(en->device));
   b200_prepared* pp = new (std::nothrow) b200_prepared();
   if (!pp) return set_err(B200_ERR_NOMEM, "out of memory");
-  int rc = plan_picture(en, pic, &pp->L);
-  if (rc) { delete pp; return rc; }
   PipeCtx& cx = en->ctx[0];
   StagingSet& ss = cx.stage[cx.cur_stage];
   cx.cur_stage ^= 1;
-  rc = ensure_staging(ss, pp->L.total);
-  if (!rc) rc = pack_picture(en, pic, pp->L, ss.host);
+  int rc = plan_and_pack(en, pic, &pp->L, ss, nullptr);
   if (rc) { delete pp; return rc; }
   cudaError_t e = cudaMalloc(&pp->dev, pp->L.total);
   if (e == cudaSuccess) e = cudaMemcpyAsync(pp->dev, ss.host, pp->L.total, cudaMemcpyHostToDevice, cx.stream);
