@@ -767,9 +767,17 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
       const bool full = (gw == G) && (gh == G);
       // the interior is only needed where this task does not write it itself (regions partly covered by inter blocks)
       if (covered < gw * gh) {
-        for (int o = lane; o < gw * gh; o += 32) {
-          const int x = o % gw, y = o / gw;
-          tile[y * TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx + x);
+        if (full) {  // whole rows as 4-byte words, like the store below
+          const int wpr = G * (int)sizeof(P) / 4;
+          for (int o = lane; o < G * wpr; o += 32) {
+            const int y = o / wpr, u = o % wpr;  // wpr is a power of two
+            reinterpret_cast<uint32_t*>(tile + y * TS)[u] = __ldcg(reinterpret_cast<const uint32_t*>(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx) + u);
+          }
+        } else {
+          for (int o = lane; o < gw * gh; o += 32) {
+            const int x = o % gw, y = o / gw;
+            tile[y * TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx + x);
+          }
         }
       }
       if (ry > 0)

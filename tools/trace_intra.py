@@ -10,8 +10,12 @@ os.environ["B200_TRACE_INTRA"] = path
 from libde265_b200 import synth
 from libde265_b200.engine import Engine
 W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3840, 2160)
-p = synth.make_picture(W, H, "I", seed=1000)
+PT = sys.argv[3] if len(sys.argv) > 3 else "I"
+p = synth.make_picture(W, H, PT, seed=1000, dst_slot=2, ref_slots=(0, 1)) if PT != "I" else synth.make_picture(W, H, "I", seed=1000)
 eng = Engine(0)
+if PT != "I":
+    for s_ in (0, 1):
+        eng.upload_slot(s_, p.params, synth.random_planes(W, H, 8, s_))
 eng.enable_timing(True)
 for _ in range(2):
     eng.submit(p); eng.sync()
@@ -22,6 +26,9 @@ n = struct.unpack_from("<Q", raw, 0)[0]
 rec = np.frombuffer(raw[-(8 * 4 * n):], dtype=np.uint64).reshape(n, 4)
 t0 = rec[:, 0].astype(np.int64); wait = rec[:, 1].astype(np.int64); work = rec[:, 2].astype(np.int64); meta = rec[:, 3]
 cnt = (meta & 0xff).astype(int); plane = ((meta >> 8) & 0xff).astype(int); lg = ((meta >> 16) & 0xff).astype(int)
+print("claim time percentiles us (rel. to first):", [round(float(x) / 1e3, 1) for x in np.percentile(t0 - t0.min(), [10, 50, 90, 99, 100])])
+end = t0 + ((wait + work) / 1.9).astype(np.int64)
+print("end time percentiles us:", [round(float(x) / 1e3, 1) for x in np.percentile(end - t0.min(), [10, 50, 90, 99, 100])])
 print("tasks", n, "TUs", cnt.sum(), "span ms (claim first..last)", (t0.max() - t0.min()) / 1e6)
 clk = 1.9e3  # cycles per us (approx)
 print("work us: mean %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f" % (work.mean()/clk, np.percentile(work,50)/clk, np.percentile(work,90)/clk, np.percentile(work,99)/clk, work.max()/clk))
