@@ -549,7 +549,8 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
       ra.task_start = (const uint32_t*)(dbase + off[13]);
       ra.n_task = L.n_task;
       int grid = (L.n_task + RC_WARPS - 1) / RC_WARPS;
-      const int cap = en->num_sms * en->intra_ctas;
+      // an intra picture's DAG is latency-bound (one CTA per SM is as fast) and should leave room for the pictures it overlaps with
+      const int cap = en->num_sms * (L.ref_mask == 0 && en->n_ctx > 1 ? 1 : en->intra_ctas);
       if (grid > cap) grid = cap;
       k_intra<P><<<grid, RC_THREADS, sizeof(IntraSmem<P>), st>>>(dp, ra);
       en->launches += 2;
@@ -968,9 +969,12 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
 }
 
 // Per-stage timing needs the stages of consecutive pictures not to overlap: one stream while it is on.
-static int pick_ctx(b200_engine* en)
+// Pictures that read no reference (intra pictures) go to a stream of their own: nothing queued in front of them, so the
+// long intra DAG of the next intra period's I picture runs in the background of the current period's P/B pictures.
+static int pick_ctx(b200_engine* en, bool independent)
 {
   if (en->timing || en->n_ctx <= 1) return 0;
+  if (independent && en->n_ctx < B200_MAX_CTX) return en->n_ctx;
   const int k = en->next_ctx;
   en->next_ctx = (en->next_ctx + 1) % en->n_ctx;
   return k;
@@ -982,7 +986,7 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
   CU(cudaSetDevice(en->device));
   PicLayout L;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const int k = pick_ctx(en);
+  const int k = pick_ctx(en, pic->n_pu == 0);
   PipeCtx& cx = en->ctx[k];
   StagingSet& ss = cx.stage[cx.cur_stage];
   cx.cur_stage ^= 1;
@@ -1026,7 +1030,7 @@ extern "C" int b200_engine_run_prepared(b200_engine* en, b200_prepared* pp)
 {
   if (!en || !pp) return set_err(B200_ERR_INVALID, "null argument");
   CU(cudaSetDevice(en->device));
-  return run_layout(en, pick_ctx(en), pp->L, pp->dev, nullptr);
+  return run_layout(en, pick_ctx(en, pp->L.ref_mask == 0), pp->L, pp->dev, nullptr);
 }
 
 extern "C" void b200_engine_free_prepared(b200_engine* en, b200_prepared* pp)
