@@ -117,33 +117,56 @@ class ClockSampler:
         return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
+METRIC = "decoded frames/sec at 4K Main profile, bit-exact YUV; MC kernel HBM GB/s"  # BASELINE.json
+
+
 def cpu_replay_worker(args):
-    """One host core: generates one 4K B picture and replays it `reps` times with the CPU restatement; returns (pictures, seconds)."""
-    seed0, width, height, bd, reps = args
+    """One host core: generates one 4K picture of the given type and replays it `reps` times with the CPU restatement;
+    returns (type, pictures, seconds) — generation excluded."""
+    seed0, width, height, bd, reps, ptype = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib  # CPU baseline leg: the only place bench.py touches the oracle
     from libde265_b200 import synth
     orc = oracle_lib.Oracle()
-    pic = synth.make_picture(width, height, "B", seed=seed0, bit_depth=bd, ref_slots=(0, 1), dst_slot=2)
-    for s in (0, 1):
-        orc.upload_slot(s, pic.params, synth.random_planes(width, height, bd, s + 1))
+    if ptype == "I":
+        pic = synth.make_picture(width, height, "I", seed=seed0, bit_depth=bd, dst_slot=2)
+    else:
+        pic = synth.make_picture(width, height, ptype, seed=seed0, bit_depth=bd, ref_slots=(0, 1) if ptype == "B" else (0,), dst_slot=2)
+        for s in (0, 1):
+            orc.upload_slot(s, pic.params, synth.random_planes(width, height, bd, s + 1))
     t0 = time.time()
     for _ in range(reps):
         orc.reconstruct(pic)
     dt = time.time() - t0
     orc.close()
-    return reps, dt
+    return ptype, reps, dt
 
 
 def cpu_baseline_parallel(width, height, bd, cores, reps):
-    """All host cores, one independent stream per core (the CPU analogue of one stream per GPU)."""
+    """All host cores busy at once, one independent picture per core (the CPU analogue of one stream per GPU).  Cores time
+    I, P and B pictures (every 16th / 8th core an I / P picture, the rest B); the job rate is `cores` streams of the step's own mix
+    (1 I + 3 P + 28 B per 32 pictures) at the measured per-type seconds per picture under that full load."""
     import multiprocessing as mp
+    types = ["I" if i % 16 == 1 else "P" if i % 8 == 2 else "B" for i in range(cores)] if cores >= 3 else ["B"] * cores
+    if cores >= 3 and "I" not in types:
+        types[1] = "I"
+    if cores >= 3 and "P" not in types:
+        types[2] = "P"
     with mp.get_context("spawn").Pool(cores) as pool:
-        res = pool.map(cpu_replay_worker, [(1002 + i % 4, width, height, bd, reps) for i in range(cores)])
-    wall = max(r[1] for r in res)  # replay time of the slowest worker (generation excluded)
-    n = sum(r[0] for r in res)
-    return {"value": round(n / wall, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n} replays of synthetic 4K B pictures ({reps}/core, {cores} processes) by the CPU restatement oracle/hevc_oracle.c (scalar C, -O2)"}
+        res = pool.map(cpu_replay_worker, [(1002 + i % 4, width, height, bd, reps, types[i]) for i in range(cores)])
+    sec = {}
+    for t in ("I", "P", "B"):
+        rs = [r for r in res if r[0] == t]
+        if rs:
+            sec[t] = sum(r[2] for r in rs) / sum(r[1] for r in rs)  # seconds per picture on one core, all cores loaded
+    sec.setdefault("I", sec["B"])
+    sec.setdefault("P", sec["B"])
+    step_s = sec["I"] + 3 * sec["P"] + 28 * sec["B"]
+    n = sum(r[1] for r in res)
+    return {"value": round(cores * 32 / step_s, 3), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} replays of synthetic 4K pictures ({reps}/core on {cores} processes: {types.count('I')} I, {types.count('P')} P, {types.count('B')} B cores; "
+                      f"{sec['I']:.2f}/{sec['P']:.2f}/{sec['B']:.2f} s per I/P/B picture and core), combined in the step's mix 1 I + 3 P + 28 B, by the CPU "
+                      "restatement oracle/hevc_oracle.c (scalar C, -O3)"}
 
 
 def cpu_baseline_inline(seq, ref0, n_pics):
@@ -158,7 +181,7 @@ def cpu_baseline_inline(seq, ref0, n_pics):
     dt = time.time() - t0
     orc.close()
     return {"value": round(n_pics / dt, 3), "unit": "frames/s", "cores": 1, "kind": "port",
-            "sample": f"first {n_pics} pictures of the step (decode order: P,B,B,...) replayed by the CPU restatement oracle/hevc_oracle.c (scalar C, -O2)"}
+            "sample": f"first {n_pics} pictures of the step (decode order: P,B,B,...) replayed by the CPU restatement oracle/hevc_oracle.c (scalar C, -O3)"}
 
 
 def main():
@@ -188,7 +211,7 @@ def main():
         for _ in range(max(1, min(a.steps, 2))):
             vals.append(cpu_baseline_parallel(a.width, a.height, a.bit_depth, cores, reps))
         best = max(vals, key=lambda v: v["value"])
-        line = {"impl": "reference", "metric": "decoded frames/sec at 4K Main profile, bit-exact YUV", "value": best["value"], "unit": "frames/s",
+        line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": "frames/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1000.0 * 32 / best["value"], 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if a.bit_depth == 8 else "u16", "data": "synthetic",
                 "config": config, "cpu_baseline": best,
@@ -306,7 +329,7 @@ def main():
                     "algorithmic_bytes_per_launch": int(alg[k] / launches_per_step),
                     "timing": "CUDA events per stage on the launching stream, one-stream pass of %d steps right after the timed region" % stage_steps}
 
-        line = {"metric": "decoded frames/sec at 4K Main profile, bit-exact YUV; MC kernel HBM GB/s", "value": round(fps, 2), "unit": "frames/s",
+        line = {"metric": METRIC, "value": round(fps, 2), "unit": "frames/s",
                 "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": round(ms_res / a.steps, 4), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8" if a.bit_depth == 8 else "u16", "data": "synthetic", "config": config,
                 "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 * pic_bytes,
