@@ -48,8 +48,8 @@ def build_workload(width, height, bd, seed0=1000):
         for off in GOP:
             poc = g * 8 + off
             r0, r1 = GOP_REFS[off]
-            ref_a = (g * 8 + r0) % 16
-            ref_b = (g * 8 + (r1 if r1 is not None else r0)) % 16
+            ref_a = (g * 8 + r0) % DPB_SLOTS
+            ref_b = (g * 8 + (r1 if r1 is not None else r0)) % DPB_SLOTS
             if off == 8:
                 kind = "I" if g == 3 else "P"  # one intra picture per 32
             else:
@@ -62,7 +62,7 @@ def build_workload(width, height, bd, seed0=1000):
                 rs = pus["ref_slot"]
                 pus["ref_slot"] = np.where(rs >= 0, lut[np.clip(rs, 0, 1)], rs)
             params = type(b.params).from_buffer_copy(b.params)
-            params.dst_slot = poc % 16
+            params.dst_slot = poc % DPB_SLOTS
             params.poc = poc
             seq.append(synth.SynthPicture(params, pus, b.weights, b.tus, b.coeffs, b.slices, b.ctbs, b.bs_map, b.qp_map, b.nofilt_map))
     return seq, time.time() - t0
@@ -117,6 +117,9 @@ class ClockSampler:
         return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
+# DPB slot of a picture = POC mod 32 (libde265 keeps up to 30 images, dpb.h:101): a slot is reused one intra period later, when its
+# old content has long stopped being referenced, so a new picture never waits for readers of the picture it overwrites.
+DPB_SLOTS = 32
 METRIC = "decoded frames/sec at 4K Main profile, bit-exact YUV; MC kernel HBM GB/s"  # BASELINE.json
 
 
@@ -200,7 +203,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     config = {"workload": f"{a.width}x{a.height} {a.bit_depth}-bit 4:2:0 synthetic command records, hierarchical-B GOP8, intra period 32 "
                           "(1 I + 3 P + 28 B per step), deblock+SAO on, one independent stream per GPU",
-              "pictures_per_step": 32, "l2_policy": "per-step working set (16 DPB surfaces x 12.4 MB + records) exceeds the 126 MB L2"}
+              "pictures_per_step": 32, "l2_policy": "per-step working set (32 DPB surfaces x 12.4 MB + records) exceeds the 126 MB L2"}
 
     if a.impl == "reference":
         if rank != 0:
