@@ -32,8 +32,18 @@ GOP = [8, 4, 2, 6, 1, 3, 5, 7]  # decode order inside a hierarchical-B GOP (POC 
 GOP_REFS = {8: (0, None), 4: (0, 8), 2: (0, 4), 6: (4, 8), 1: (0, 2), 3: (2, 4), 5: (4, 6), 7: (6, 8)}
 
 
+# DPB slot policy of the synthetic decoder (what dpb.cc's "first unused image" does for libde265, which keeps up to 30
+# images, dpb.h:101): 32 slots in three rotating pools — key pictures (POC % 8 == 0) 8 slots, reference B pictures (POC % 8 in
+# 2,4,6) 8 slots, non-reference B pictures (odd POC) 16 slots.  A slot is reused only long after its old content stopped being
+# referenced or read out, so a new picture never waits for readers of the picture it overwrites (no WAR stalls), and the
+# assignment repeats every two intra periods: the workload is 64 prepared pictures, a step alternates between its halves.
+KEY_SLOTS, REFB_SLOTS, NONREF_SLOTS = 8, 8, 16
+STEP_VARIANTS = 2
+
+
 def build_workload(width, height, bd, seed0=1000):
-    """32 pictures in decode order from 6 generated base pictures (slots are patched per use)."""
+    """2 x 32 pictures in decode order from 6 generated base pictures (slots are patched per use).
+    Returns (pictures, slot of the key picture the very first GOP references, generation seconds)."""
     from libde265_b200 import synth
     t0 = time.time()
     base = {
@@ -44,14 +54,26 @@ def build_workload(width, height, bd, seed0=1000):
         base[f"B{i}"] = synth.make_picture(width, height, "B", seed=seed0 + 2 + i, bit_depth=bd, ref_slots=(0, 1), weighted=(i == 3))
     seq = []
     bcount = 0
-    for g in range(4):  # pocs g*8+1 .. g*8+8, previous key picture at g*8
+    n_key = n_refb = n_nonref = 0
+    slot_of = {0: (KEY_SLOTS - 1)}  # POC -> slot; POC 0 = the key picture before the first GOP
+    first_key_slot = slot_of[0]
+    for g in range(4 * STEP_VARIANTS):  # pocs g*8+1 .. g*8+8, previous key picture at g*8
         for off in GOP:
             poc = g * 8 + off
-            r0, r1 = GOP_REFS[off]
-            ref_a = (g * 8 + r0) % DPB_SLOTS
-            ref_b = (g * 8 + (r1 if r1 is not None else r0)) % DPB_SLOTS
             if off == 8:
-                kind = "I" if g == 3 else "P"  # one intra picture per 32
+                slot_of[poc] = n_key % KEY_SLOTS
+                n_key += 1
+            elif off % 2 == 0:
+                slot_of[poc] = KEY_SLOTS + n_refb % REFB_SLOTS
+                n_refb += 1
+            else:
+                slot_of[poc] = KEY_SLOTS + REFB_SLOTS + n_nonref % NONREF_SLOTS
+                n_nonref += 1
+            r0, r1 = GOP_REFS[off]
+            ref_a = slot_of[g * 8 + r0]
+            ref_b = slot_of[g * 8 + (r1 if r1 is not None else r0)]
+            if off == 8:
+                kind = "I" if g % 4 == 3 else "P"  # one intra picture per 32
             else:
                 kind = f"B{bcount % 4}"
                 bcount += 1
@@ -62,10 +84,11 @@ def build_workload(width, height, bd, seed0=1000):
                 rs = pus["ref_slot"]
                 pus["ref_slot"] = np.where(rs >= 0, lut[np.clip(rs, 0, 1)], rs)
             params = type(b.params).from_buffer_copy(b.params)
-            params.dst_slot = poc % DPB_SLOTS
+            params.dst_slot = slot_of[poc]
             params.poc = poc
             seq.append(synth.SynthPicture(params, pus, b.weights, b.tus, b.coeffs, b.slices, b.ctbs, b.bs_map, b.qp_map, b.nofilt_map))
-    return seq, time.time() - t0
+    assert slot_of[32 * STEP_VARIANTS] == first_key_slot, "the slot assignment must repeat after the last variant"
+    return seq, first_key_slot, time.time() - t0
 
 
 def algorithmic_bytes(seq, bd):
@@ -117,9 +140,6 @@ class ClockSampler:
         return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
-# DPB slot of a picture = POC mod 32 (libde265 keeps up to 30 images, dpb.h:101): a slot is reused one intra period later, when its
-# old content has long stopped being referenced, so a new picture never waits for readers of the picture it overwrites.
-DPB_SLOTS = 32
 METRIC = "decoded frames/sec at 4K Main profile, bit-exact YUV; MC kernel HBM GB/s"  # BASELINE.json
 
 
@@ -172,12 +192,12 @@ def cpu_baseline_parallel(width, height, bd, cores, reps):
                       "restatement oracle/hevc_oracle.c (scalar C, -O3)"}
 
 
-def cpu_baseline_inline(seq, ref0, n_pics):
+def cpu_baseline_inline(seq, ref0, ref_slot, n_pics):
     """Rank 0, one core: replays the first pictures of the very workload the GPU ran."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib  # CPU baseline leg: the only place bench.py touches the oracle
     orc = oracle_lib.Oracle()
-    orc.upload_slot(0, seq[0].params, ref0)
+    orc.upload_slot(ref_slot, seq[0].params, ref0)
     t0 = time.time()
     for p in seq[:n_pics]:
         orc.reconstruct(p)
@@ -203,7 +223,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     config = {"workload": f"{a.width}x{a.height} {a.bit_depth}-bit 4:2:0 synthetic command records, hierarchical-B GOP8, intra period 32 "
                           "(1 I + 3 P + 28 B per step), deblock+SAO on, one independent stream per GPU",
-              "pictures_per_step": 32, "l2_policy": "per-step working set (32 DPB surfaces x 12.4 MB + records) exceeds the 126 MB L2"}
+              "pictures_per_step": 32, "l2_policy": "per-step working set (32 DPB surfaces x 12.4 MB + 2 x 32 record sets) exceeds the 126 MB L2"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -233,13 +253,13 @@ def main():
     eng = Engine(local_rank)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
 
-    seq, gen_s = build_workload(a.width, a.height, a.bit_depth, seed0=shard.stream_seed(rank))
+    seq, key_slot, gen_s = build_workload(a.width, a.height, a.bit_depth, seed0=shard.stream_seed(rank))
     params = seq[0].params
     ref0 = synth.random_planes(a.width, a.height, a.bit_depth, shard.reference_seed(rank))
-    eng.upload_slot(0, params, ref0)  # POC 0 reference
+    eng.upload_slot(key_slot, params, ref0)  # POC 0 reference
     prepared = [eng.prepare(p) for p in seq]
     h2d_bytes = sum(int(p.pus.nbytes + p.weights.nbytes + p.tus.nbytes + p.coeffs.nbytes + p.slices.nbytes + p.ctbs.nbytes + p.bs_map.nbytes +
-                        p.qp_map.nbytes + p.nofilt_map.nbytes) for p in seq)
+                        p.qp_map.nbytes + p.nofilt_map.nbytes) for p in seq) // STEP_VARIANTS
     bps = 2 if a.bit_depth > 8 else 1
     pic_bytes = a.width * a.height * 3 // 2 * bps
     # pinned host output buffers for the e2e leg (two, alternating)
@@ -264,12 +284,18 @@ def main():
         barrier()
         return shard.max_over_ranks(e0.elapsed_time(e1), "cuda")  # the job takes as long as its slowest rank
 
-    def step_resident():
-        for h in prepared:
+    counter = {"step": 0}  # shared: the DPB state continues from one step to the next whatever leg runs it
+
+    def step_resident():  # one intra period; consecutive steps alternate between the workload's variants
+        v = counter["step"] % STEP_VARIANTS
+        counter["step"] += 1
+        for h in prepared[32 * v:32 * (v + 1)]:
             eng.run_prepared(h)
 
     def step_e2e():
-        for i, p in enumerate(seq):
+        v = counter["step"] % STEP_VARIANTS
+        counter["step"] += 1
+        for i, p in enumerate(seq[32 * v:32 * (v + 1)]):
             eng.submit(p)
             o = outs[i & 1]
             capi.check(eng.lib.b200_engine_read_slot_async(eng.handle, p.params.dst_slot, capi.PlaneArray(*[t.data_ptr() for t in o]),
@@ -309,7 +335,7 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        alg = algorithmic_bytes(seq, a.bit_depth)
+        alg = algorithmic_bytes(seq[:32], a.bit_depth)
         per_stage = {}
         for k in ("inter_pred", "recon", "deblock", "sao"):
             ms = stage_ms[k] / max(1, n_timed) * 32  # per step
@@ -342,7 +368,7 @@ def main():
                                                     "note": "same steps with picture pipelining off (per-stage timing pass)"},
                 "workload_gen_s": round(gen_s, 1)}
         if not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_inline(seq, ref0, 16 if a.width * a.height > 1920 * 1080 else 32)
+            line["cpu_baseline"] = cpu_baseline_inline(seq, ref0, key_slot, 16 if a.width * a.height > 1920 * 1080 else 32)
         print(json.dumps(line))
     for h in prepared:
         eng.free_prepared(h)
