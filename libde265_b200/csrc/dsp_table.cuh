@@ -25,11 +25,10 @@ __device__ void dsp_mc(const DspDevCmd& c, uint8_t* arena, int16_t* strip_all, b
   const int pw = c.w + (xf ? (luma ? 7 : 3) : 0), ph = c.h + (yf ? (luma ? 7 : 3) : 0);
   int16_t* strip = strip_all + warp * MC_STRIP;
   int16_t* out = reinterpret_cast<int16_t*>(arena + c.io);
-  const int tiles_x = (c.w + MC_TILE - 1) / MC_TILE, tiles_y = (c.h + MC_TILE - 1) / MC_TILE;
-  constexpr int TW = MC_TILE;  // luma strip row stride; the chroma helpers use MC_TILE / 2, so chroma runs on 8-wide tiles
+  const int tiles_y = (c.h + MC_TILE - 1) / MC_TILE;
+  // luma tiles are MC_TILE wide (the strip row stride of the luma helpers); the chroma helpers use MC_TILE / 2
   const int tile_w = luma ? MC_TILE : MC_TILE / 2;
   const int ntx = (c.w + tile_w - 1) / tile_w;
-  (void)tiles_x; (void)TW;
   for (int t = warp; t < ntx * tiles_y; t += 4) {
     const int tx = (t % ntx) * tile_w, ty = (t / ntx) * MC_TILE;
     const int tw = min(tile_w, c.w - tx), th = min(MC_TILE, c.h - ty);

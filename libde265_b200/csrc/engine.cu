@@ -1,8 +1,10 @@
 // engine.cu — host side of the B200 reconstruction engine (b200hevc.h part 2) + kernel launches.
 //
-// Per picture: group TUs by CTB, cut PUs into MC tiles, pack everything into one pinned staging
-// buffer, ONE host->device copy, then  k_inter_pred -> k_recon -> k_deblock<V> -> k_deblock<H> -> k_sao
-// on the engine's stream.  Reference pictures never leave the device (DPB slots are device surfaces).
+// Per picture: validate the records, build the work lists (MC units, k_residual classes, intra tasks in topological
+// order) and pack everything into one pinned staging buffer on a small host thread pool, ONE host->device copy, then
+//   k_inter_pred8 -> k_residual -> k_mark_pending + k_intra -> k_deblock<V> -> k_deblock<H> -> k_sao_prep + k_sao
+// on one of the engine's streams; pictures are pipelined over the streams with per-slot event ordering.
+// Reference pictures never leave the device (DPB slots are device surfaces).
 // There is no CPU fallback: without a CUDA device b200_engine_create fails with B200_ERR_NO_DEVICE.
 
 #include <cuda_runtime.h>
@@ -199,11 +201,11 @@ struct b200_engine {
   unsigned tcount = 0;           // pictures recorded since enable / reset
   cudaEvent_t* ev = nullptr;     // events of the picture being submitted
   uint64_t launches = 0;
-  double host_s[4] = {0, 0, 0, 0};  // submit_picture host time: plan, staging wait, pack, launches (B200_HOST_PROF=1 prints at destroy)
+  double host_s[4] = {0, 0, 0, 0};  // submit_picture host time: [0] validate + staging wait, [1] plan + pack, [3] launches (B200_HOST_PROF=1 prints at destroy)
   uint64_t host_n = 0;
   // host scratch reused across pictures
   std::vector<uint32_t> part_a[4][3];  // plan_tus_validate: per part, per k_residual class
-  std::vector<uint32_t> ctb_count, tiles, list_a, list_a8, list_a4, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
+  std::vector<uint32_t> ctb_count, tiles, list_a, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
 };
 
 #define TIMING_RING 256
@@ -345,9 +347,8 @@ extern "C" void b200_engine_destroy(b200_engine* en)
   cudaSetDevice(en->device);
   cudaDeviceSynchronize();
   if (getenv("B200_HOST_PROF") && en->host_n)
-    fprintf(stderr, "[b200] submit_picture host ms/picture over %llu pictures: validate+staging-wait %.3f  plan+pack (threaded) %.3f  (unused %.3f)  launch %.3f\n",
-            (unsigned long long)en->host_n, 1e3 * en->host_s[0] / en->host_n, 1e3 * en->host_s[1] / en->host_n, 1e3 * en->host_s[2] / en->host_n,
-            1e3 * en->host_s[3] / en->host_n);
+    fprintf(stderr, "[b200] submit_picture host ms/picture over %llu pictures: validate+staging-wait %.3f  plan+pack (threaded) %.3f  launch %.3f\n",
+            (unsigned long long)en->host_n, 1e3 * en->host_s[0] / en->host_n, 1e3 * en->host_s[1] / en->host_n, 1e3 * en->host_s[3] / en->host_n);
   for (auto& s : en->slot) surface_free(s);
   for (auto& cx : en->ctx) {
     surface_free(cx.scratch);

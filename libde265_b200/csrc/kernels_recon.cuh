@@ -28,7 +28,6 @@
 #define RC_GSTRIDE 34      // int16 row stride of the first-stage buffer
 #define RC_TILE_STRIDE 40  // region tile: rows -1..2G-1 (only column -1 below row G-1), columns -1..2G-1 (G <= 16)
 #define RC_BLK (33 * RC_TILE_STRIDE + 8)
-#define RC_CO_STAGE 256
 #define RC_FULL 0xffffffffu
 
 struct ReconArgs {
