@@ -192,6 +192,44 @@ def cpu_baseline_parallel(width, height, bd, cores, reps):
                       "restatement oracle/hevc_oracle.c (scalar C, -O3)"}
 
 
+def calibrate_port():
+    """How the scalar port relates to the REAL reference on this host: the reference's own decoder (oracle/_ref/dec265, built
+    from /root/reference; full decode incl. parsing, 1 thread, SIMD and scalar tables) and the port's replay of the same
+    stream's records (reconstruction only), on the golden stream — the only bitstream that exists offline.  Reported next
+    to cpu_baseline so the port's number can be read for what it is; never used to scale any value."""
+    import re
+    import subprocess
+    out = {"stream": "tests/golden/girlshy.h265 (416x240, 75 pictures), one core"}
+    stream = os.path.join(ROOT, "tests", "golden", "girlshy.h265")
+    dec = os.path.join(ROOT, "oracle", "_ref", "dec265")
+    try:
+        if os.path.exists(dec):
+            for key, extra in (("reference_simd_fps_incl_parsing", []), ("reference_scalar_fps_incl_parsing", ["-0"])):
+                best = 0.0
+                for _ in range(3):
+                    r = subprocess.run([dec, "-q"] + extra + ["-o", "/dev/null", stream], capture_output=True, text=True, timeout=60)
+                    m = re.search(r"@ ([0-9.]+) fps", r.stdout + r.stderr)
+                    if m:
+                        best = max(best, float(m.group(1)))
+                out[key] = best or None
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        from libde265_b200 import capi
+        from test_cpu_oracle import load_records
+        pics, _keep = load_records(capi.load())
+        orc = oracle_lib.Oracle()
+        for p in pics:
+            orc.reconstruct(p)
+        t0 = time.time()
+        for p in pics:
+            orc.reconstruct(p)
+        out["port_replay_fps_reconstruction_only"] = round(len(pics) / (time.time() - t0), 1)
+        orc.close()
+    except Exception as e:  # calibration is informative only
+        out["error"] = str(e)[:200]
+    return out
+
+
 def cpu_baseline_inline(seq, ref0, ref_slot, n_pics):
     """Rank 0, one core: replays the first pictures of the very workload the GPU ran."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -234,6 +272,7 @@ def main():
         for _ in range(max(1, min(a.steps, 2))):
             vals.append(cpu_baseline_parallel(a.width, a.height, a.bit_depth, cores, reps))
         best = max(vals, key=lambda v: v["value"])
+        best["calibration"] = calibrate_port()
         line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": "frames/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1000.0 * 32 / best["value"], 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if a.bit_depth == 8 else "u16", "data": "synthetic",
@@ -369,6 +408,7 @@ def main():
                 "workload_gen_s": round(gen_s, 1)}
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_inline(seq, ref0, key_slot, 16 if a.width * a.height > 1920 * 1080 else 32)
+            line["cpu_baseline"]["calibration"] = calibrate_port()
         print(json.dumps(line))
     for h in prepared:
         eng.free_prepared(h)
