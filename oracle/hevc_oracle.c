@@ -80,16 +80,23 @@ void orc_idct_add(orc_pixel* dst, ptrdiff_t stride, int nT, const int16_t* coeff
   const int rnd2 = 1 << (post_shift - 1);
   const int fact = 32 / nT;
   int16_t g[32 * 32];
+  /* zero rows / columns beyond the last significant coefficient contribute nothing; skipping them is the reference's own
+   * optimisation (fallback-dct.cc:614-617,667-670) */
+  int max_row = 0, max_col = 0;
+  for (int j = 0; j < nT; j++)
+    for (int c = 0; c < nT; c++)
+      if (coeffs[c + j * nT]) { if (j > max_row) max_row = j; if (c > max_col) max_col = c; }
   for (int c = 0; c < nT; c++)
     for (int i = 0; i < nT; i++) {
       int sum = 0;
-      for (int j = 0; j < nT; j++) sum += dct_mat[fact * j][i] * coeffs[c + j * nT];
+      if (c <= max_col)
+        for (int j = 0; j <= max_row; j++) sum += dct_mat[fact * j][i] * coeffs[c + j * nT];
       g[c + i * nT] = (int16_t)clip3(-32768, 32767, (sum + 64) >> 7);
     }
   for (int y = 0; y < nT; y++)
     for (int i = 0; i < nT; i++) {
       int sum = 0;
-      for (int j = 0; j < nT; j++) sum += dct_mat[fact * j][i] * g[y * nT + j];
+      for (int j = 0; j <= max_col; j++) sum += dct_mat[fact * j][i] * g[y * nT + j];
       int out = (sum + rnd2) >> post_shift;
       dst[y * stride + i] = (orc_pixel)clip_bd(dst[y * stride + i] + out, bit_depth);
     }
@@ -188,33 +195,52 @@ static void mc_generic(int16_t* out, int out_stride, const orc_pixel* ref, ptrdi
   }
   const int after = ntaps - 1 - before;
   int16_t tmp[(64 + 7) * 64];
-  for (int y = -before; y < h + after; y++) {
-    int ya = clip3(0, ph - 1, y + y_int);
-    for (int x = 0; x < w; x++) {
-      int v;
-      if (x_frac == 0) {
-        v = ref[clip3(0, pw - 1, x + x_int) + ya * ref_stride];
-      } else {
-        int sum = 0;
-        for (int k = 0; k < ntaps; k++) sum += taps_h[k] * ref[clip3(0, pw - 1, x + x_int + k - before) + ya * ref_stride];
-        v = sum >> shift1;
+  /* The H pass works on one source row gathered with the clamped coordinates (same samples as clamping per tap,
+   * motion.cc:147-153; a straight copy when the window lies inside the picture), which keeps the tap loops free of
+   * address arithmetic. Rows the V pass does not need are skipped (the reference filters them too: no effect). */
+  const int y_lo = y_frac ? -before : 0, y_hi = y_frac ? h + after : h;
+  const int x_lo = x_frac ? -before : 0, x_n = w + (x_frac ? ntaps - 1 : 0);
+  const int inside = (x_int + x_lo >= 0) && (x_int + x_lo + x_n <= pw);
+  for (int y = y_lo; y < y_hi; y++) {
+    const orc_pixel* rowp = ref + (ptrdiff_t)clip3(0, ph - 1, y + y_int) * ref_stride;
+    orc_pixel line[64 + 8];
+    const orc_pixel* r;
+    if (inside) {
+      r = rowp + x_int + x_lo;
+    } else {
+      for (int x = 0; x < x_n; x++) line[x] = rowp[clip3(0, pw - 1, x_int + x_lo + x)];
+      r = line;
+    }
+    int16_t* t = tmp + (y + before) * w;
+    if (x_frac == 0) {
+      for (int x = 0; x < w; x++) t[x] = (int16_t)r[x];
+    } else if (ntaps == 8) {
+      for (int x = 0; x < w; x++) {
+        int sum = taps_h[0] * r[x] + taps_h[1] * r[x + 1] + taps_h[2] * r[x + 2] + taps_h[3] * r[x + 3] + taps_h[4] * r[x + 4] +
+                  taps_h[5] * r[x + 5] + taps_h[6] * r[x + 6] + taps_h[7] * r[x + 7];
+        t[x] = (int16_t)(sum >> shift1);
       }
-      tmp[(y + before) * w + x] = (int16_t)v;
+    } else {
+      for (int x = 0; x < w; x++) {
+        int sum = taps_h[0] * r[x] + taps_h[1] * r[x + 1] + taps_h[2] * r[x + 2] + taps_h[3] * r[x + 3];
+        t[x] = (int16_t)(sum >> shift1);
+      }
     }
   }
   const int vshift = (x_frac == 0) ? shift1 : 6;
-  for (int y = 0; y < h; y++)
-    for (int x = 0; x < w; x++) {
-      int v;
-      if (y_frac == 0) {
-        v = tmp[(y + before) * w + x];
-      } else {
+  for (int y = 0; y < h; y++) {
+    int16_t* o = out + (ptrdiff_t)y * out_stride;
+    if (y_frac == 0) {
+      for (int x = 0; x < w; x++) o[x] = tmp[(y + before) * w + x];
+    } else {
+      const int16_t* t = tmp + y * w;
+      for (int x = 0; x < w; x++) {
         int sum = 0;
-        for (int k = 0; k < ntaps; k++) sum += taps_v[k] * tmp[(y + k) * w + x];
-        v = sum >> vshift;
+        for (int k = 0; k < ntaps; k++) sum += taps_v[k] * t[k * w + x];
+        o[x] = (int16_t)(sum >> vshift);
       }
-      out[y * out_stride + x] = (int16_t)v;
     }
+  }
 }
 
 void orc_mc_luma(int16_t* out, int out_stride, const orc_pixel* ref, ptrdiff_t ref_stride, int pic_w, int pic_h,
