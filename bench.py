@@ -187,7 +187,7 @@ def cpu_baseline_parallel(width, height, bd, cores, reps):
     step_s = sec["I"] + 3 * sec["P"] + 28 * sec["B"]
     n = sum(r[1] for r in res)
     return {"value": round(cores * 32 / step_s, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n} replays of synthetic 4K pictures ({reps}/core on {cores} processes: {types.count('I')} I, {types.count('P')} P, {types.count('B')} B cores; "
+            "sample": f"{n} replays of synthetic {width}x{height} pictures ({reps}/core on {cores} processes: {types.count('I')} I, {types.count('P')} P, {types.count('B')} B cores; "
                       f"{sec['I']:.2f}/{sec['P']:.2f}/{sec['B']:.2f} s per I/P/B picture and core), combined in the step's mix 1 I + 3 P + 28 B, by the CPU "
                       "restatement oracle/hevc_oracle.c (scalar C, -O3)"}
 

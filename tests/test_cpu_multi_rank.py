@@ -60,3 +60,20 @@ def test_reference_arm_only_rank0_works():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                         env=dict(env, RANK="1", LOCAL_RANK="1"), capture_output=True, text=True, timeout=120)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_reference_arm_json_line():
+    """The CPU arm's JSON line: same metric / unit / config keys as the GPU arm, impl = reference, a cpu_baseline that says
+    what was timed, e2e with zero transfer bytes (small picture size so the test is quick)."""
+    import json
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--width", "256",
+                        "--height", "128"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert line["impl"] == "reference" and line["metric"] == base["metric"] and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb and "calibration" in cb
+    assert "workload" in line["config"] and "model" not in line["config"]
