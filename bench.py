@@ -301,10 +301,10 @@ def main():
                         p.qp_map.nbytes + p.nofilt_map.nbytes) for p in seq) // STEP_VARIANTS
     bps = 2 if a.bit_depth > 8 else 1
     pic_bytes = a.width * a.height * 3 // 2 * bps
-    # pinned host output buffers for the e2e leg (two, alternating)
+    # pinned host output buffers for the e2e leg (a ring of 8: more than the engine keeps pictures in flight)
     outs = [[torch.empty((a.height, a.width), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory(),
              torch.empty((a.height // 2, a.width // 2), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory(),
-             torch.empty((a.height // 2, a.width // 2), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory()] for _ in range(2)]
+             torch.empty((a.height // 2, a.width // 2), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory()] for _ in range(8)]
 
     def barrier():
         if world > 1:
@@ -336,7 +336,7 @@ def main():
         counter["step"] += 1
         for i, p in enumerate(seq[32 * v:32 * (v + 1)]):
             eng.submit(p)
-            o = outs[i & 1]
+            o = outs[i & 7]
             capi.check(eng.lib.b200_engine_read_slot_async(eng.handle, p.params.dst_slot, capi.PlaneArray(*[t.data_ptr() for t in o]),
                                                            capi.StrideArray(*[t.stride(0) * bps for t in o])), "read_slot_async")
 
