@@ -275,6 +275,17 @@ B200_API void* b200_engine_stream(b200_engine*);
 /* ... after making stream 0 wait for everything issued so far on the other streams. */
 B200_API int  b200_engine_join(b200_engine*);
 
+/* Host-side planner without a device (diagnostics / tests of the host logic on machines without a GPU): validates the
+ * records exactly as b200_engine_submit_picture does and returns the work lists the kernels would consume.
+ * counts[8] = { n_mc_units, n_list_a, n_list_a_warp_class, n_list_a_8x8_class, n_list_b, n_tasks, ref_slot_mask, 0 }.
+ * Each output array may be NULL; otherwise it must hold cap_* entries and receives min(count, cap) of them:
+ *   mc_units   one word per <= 8x16 (8 bit) / <= 16x16 (> 8 bit) MC unit: bits 0-19 PU index, the rest the unit's position in the PU
+ *   list_a     indices of the non-intra TUs with work: warp class | 8x8 class | 4x4 class
+ *   list_b     indices of the intra TUs grouped by task, tasks in the order the intra kernel claims them (topological)
+ *   task_start n_tasks + 1 offsets into list_b */
+B200_API int  b200_plan_picture_host(const b200_picture*, uint32_t counts[8], uint32_t* mc_units, size_t cap_units, uint32_t* list_a,
+                                     size_t cap_a, uint32_t* list_b, size_t cap_b, uint32_t* task_start, size_t cap_tasks);
+
 B200_API const char* b200_last_error(void);
 B200_API int  b200_abi_version(void);
 

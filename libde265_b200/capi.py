@@ -116,7 +116,7 @@ EXPORTS = [
     "b200_engine_upload_slot", "b200_engine_read_slot", "b200_engine_read_slot_async", "b200_engine_sync",
     "b200_engine_slot_device_planes", "b200_engine_enable_timing", "b200_engine_last_timing",
     "b200_engine_launch_count", "b200_engine_stream", "b200_engine_prepare_picture", "b200_engine_run_prepared",
-    "b200_engine_free_prepared", "b200_engine_timing_sum", "b200_engine_set_streams", "b200_engine_join", "b200_last_error",
+    "b200_engine_free_prepared", "b200_engine_timing_sum", "b200_engine_set_streams", "b200_engine_join", "b200_plan_picture_host", "b200_last_error",
     "b200_abi_version",
     "b200_rec_create", "b200_rec_destroy", "b200_rec_begin_picture", "b200_rec_add_slice", "b200_rec_add_weights",
     "b200_rec_add_pu", "b200_rec_add_tu", "b200_rec_set_ctb", "b200_rec_bs_map", "b200_rec_qp_map",
@@ -170,6 +170,7 @@ def load(path=None):
     lib.b200_engine_launch_count.argtypes = [vp]
     lib.b200_engine_launch_count.restype = C.c_uint64
     lib.b200_engine_stream.argtypes = [vp]
+    lib.b200_plan_picture_host.argtypes = [C.POINTER(Picture), C.POINTER(C.c_uint32 * 8)] + [C.POINTER(C.c_uint32), C.c_size_t] * 4
     lib.b200_dsp_create.argtypes = [C.POINTER(vp), C.c_int]
     lib.b200_dsp_destroy.argtypes = [vp]
     lib.b200_dsp_destroy.restype = None

@@ -834,6 +834,19 @@ static int ensure_staging(StagingSet& ss, size_t total)
   return B200_OK;
 }
 
+// list_a = class by class (warp | 8x8 | 4x4), the validation parts in order
+static void merge_list_a(b200_engine* en, PicLayout* L)
+{
+  std::vector<uint32_t>& la = en->list_a;
+  la.clear();
+  for (int cls = 0; cls < 3; cls++) {
+    for (int part = 0; part < PLAN_TU_PARTS; part++) la.insert(la.end(), en->part_a[part][cls].begin(), en->part_a[part][cls].end());
+    if (cls == 0) L->n_aw = (int)la.size();
+    if (cls == 1) L->n_a8 = (int)la.size() - L->n_aw;
+  }
+  L->n_a = (int)la.size();
+}
+
 // Host side of one picture: validate, build the work lists, fill the pinned staging buffer.  The raw record arrays are
 // copied by pool threads and the PUs are planned on a pool thread while this thread plans the TUs.
 static int plan_and_pack(b200_engine* en, const b200_picture* pic, PicLayout* L, StagingSet& ss, double* t_plan_pack)
@@ -868,21 +881,43 @@ static int plan_and_pack(b200_engine* en, const b200_picture* pic, PicLayout* L,
   for (int part = 0; part < PLAN_TU_PARTS; part++)
     if (rc_tv[part]) return set_err(rc_tv[part], "%s", err_tv[part].c_str());
   if (rc) return rc;
-  {  // list_a = class by class, parts in order
-    std::vector<uint32_t>& la = en->list_a;
-    la.clear();
-    for (int cls = 0; cls < 3; cls++) {
-      for (int part = 0; part < PLAN_TU_PARTS; part++) la.insert(la.end(), en->part_a[part][cls].begin(), en->part_a[part][cls].end());
-      if (cls == 0) L->n_aw = (int)la.size();
-      if (cls == 1) L->n_a8 = (int)la.size() - L->n_aw;
-    }
-    L->n_a = (int)la.size();
-  }
+  merge_list_a(en, L);
   if (rc_pu) return set_err(rc_pu, "%s", err_pu.c_str());
   plan_finish(L);
   pack_lists(en, *L, hb);
   if (t_plan_pack) { t_plan_pack[0] = t1 - t0; t_plan_pack[1] = now() - t1; }
   return B200_OK;
+}
+
+extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8], uint32_t* mc_units, size_t cap_units, uint32_t* list_a, size_t cap_a,
+                                      uint32_t* list_b, size_t cap_b, uint32_t* task_start, size_t cap_tasks)
+{
+  if (!pic || !counts) return set_err(B200_ERR_INVALID, "null argument");
+  b200_engine* en = new (std::nothrow) b200_engine();  // no CUDA call is made on this path
+  if (!en) return set_err(B200_ERR_NOMEM, "out of memory");
+  if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
+  PicLayout L;
+  size_t cap = 0;
+  int rc = plan_begin(en, pic, &L, &cap);
+  if (!rc) rc = plan_pus(en, pic, &L);
+  for (int part = 0; part < PLAN_TU_PARTS && !rc; part++)
+    rc = plan_tus_validate(en, pic, part, (uint32_t)((uint64_t)pic->n_tu * part / PLAN_TU_PARTS), (uint32_t)((uint64_t)pic->n_tu * (part + 1) / PLAN_TU_PARTS));
+  if (!rc) rc = plan_tus_intra(en, pic, &L);
+  if (!rc) {
+    merge_list_a(en, &L);
+    plan_finish(&L);
+    counts[0] = (uint32_t)L.n_tiles; counts[1] = (uint32_t)L.n_a; counts[2] = (uint32_t)L.n_aw; counts[3] = (uint32_t)L.n_a8;
+    counts[4] = (uint32_t)L.n_b; counts[5] = (uint32_t)L.n_task; counts[6] = L.ref_mask; counts[7] = 0;
+    auto copy = [](uint32_t* dst, size_t cap_, const std::vector<uint32_t>& v, size_t n) {
+      if (dst) memcpy(dst, v.data(), sizeof(uint32_t) * std::min(cap_, n));
+    };
+    copy(mc_units, cap_units, en->tiles, (size_t)L.n_tiles);
+    copy(list_a, cap_a, en->list_a, (size_t)L.n_a);
+    copy(list_b, cap_b, en->list_b, (size_t)L.n_b);
+    copy(task_start, cap_tasks, en->task_start, L.n_task ? (size_t)L.n_task + 1 : 0);
+  }
+  delete en;
+  return rc;
 }
 
 // Cross-stream ordering for a picture issued on context `k` (SlotSync): wait for the writers of its reference slots and
