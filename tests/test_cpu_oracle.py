@@ -138,6 +138,43 @@ def test_unmodified_reference_reproduces_golden_md5():
     assert n == 75 and md.hexdigest() == GOLDEN_MD5
 
 
+# ---- second golden vector: a real 1080p intra-only stream made with the reference's own encoder (config 2's size) ----
+INTRA1080 = json.load(open(os.path.join(GOLDEN, "intra1080_expected.json")))
+
+
+@pytest.mark.skipif(oracle_lib.ref_path("libde265_ref.so") is None, reason="oracle/_ref not built")
+def test_unmodified_reference_reproduces_intra1080_md5():
+    dec = de265.Decoder(oracle_lib.ref_path("libde265_ref.so"))
+    md = hashlib.md5()
+    n = dec.decode_stream(open(os.path.join(GOLDEN, "intra1080.h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
+    dec.close()
+    assert n == INTRA1080["pictures"] and md.hexdigest() == INTRA1080["md5_of_all_planes_in_output_order"]
+
+
+@pytest.mark.skipif(oracle_lib.ref_path("libde265_hooked.so") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_parser_plus_oracle_reproduces_intra1080_md5(b200lib, oracle_mod):
+    """1920x1080 (33.75 CTB rows of 32: partial CTBs), every intra mode / partition / TU split a real encoder chose, DST, deblock, SAO."""
+    orc = oracle_mod.Oracle()
+    dec = de265.Decoder(oracle_lib.ref_path("libde265_hooked.so"))
+    stats = {"tus": 0, "pics": 0}
+
+    def sink(pic, planes, strides):
+        stats["tus"] += pic.n_tu
+        stats["pics"] += 1
+        orc.reconstruct(pic)
+        orc.lib.orc_read_slot(orc.ctx, pic.params.dst_slot, capi.PlaneArray(planes[0], planes[1], planes[2]),
+                              capi.StrideArray(strides[0], strides[1], strides[2]))
+        return 0
+
+    dec.attach(sink)
+    md = hashlib.md5()
+    n = dec.decode_stream(open(os.path.join(GOLDEN, "intra1080.h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
+    dec.close()
+    orc.close()
+    assert n == INTRA1080["pictures"] and stats["pics"] == n and stats["tus"] > 50000
+    assert md.hexdigest() == INTRA1080["md5_of_all_planes_in_output_order"]
+
+
 # ---- synthetic generator sanity (host logic) ---------------------------------------------------------
 def test_synth_is_deterministic_and_legal():
     a = synth.make_picture(128, 72, "B", seed=7, dst_slot=1, ref_slots=(0,), weighted=True, n_slices=2)
