@@ -109,3 +109,32 @@ def test_planner_rejects_malformed_records(b200lib):
     q.tus["coeff_off"][-1] = 10 ** 7
     with pytest.raises(capi.B200Error):
         plan(b200lib, q)
+
+
+def test_planner_on_the_real_1080p_intra_stream(b200lib):
+    """The records the reference parser emits for tests/golden/intra1080.h265 (availability masks from the reference's own
+    intra_border_computer): ~76k intra TUs in ~23k tasks per picture, task order topological."""
+    import os
+    import oracle_lib
+    from libde265_b200 import de265
+    hooked = oracle_lib.ref_path("libde265_hooked.so")
+    if hooked is None:
+        pytest.skip("oracle/_ref not built")
+    dec = de265.Decoder(hooked)
+    tasks = []
+
+    class Rec:
+        pass
+
+    def sink(pic, planes, strides):
+        r = Rec()
+        r.c, r.params = pic, pic.params
+        r.tus = np.ctypeslib.as_array(C.cast(pic.tus, C.POINTER(C.c_uint8)), shape=(pic.n_tu * 24,)).view(synth.TU_DT).copy()
+        r.pus = np.zeros(0, synth.PU_DT)
+        tasks.append(check_picture(b200lib, r))
+        return 0
+
+    dec.attach(sink)
+    n = dec.decode_stream(open(os.path.join(os.path.dirname(__file__), "golden", "intra1080.h265"), "rb").read(), lambda img: None)
+    dec.close()
+    assert n == 2 and all(t > 20000 for t in tasks)
