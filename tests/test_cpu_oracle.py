@@ -139,21 +139,25 @@ def test_unmodified_reference_reproduces_golden_md5():
 
 
 # ---- second golden vector: a real 1080p intra-only stream made with the reference's own encoder (config 2's size) ----
-INTRA1080 = json.load(open(os.path.join(GOLDEN, "intra1080_expected.json")))
+REAL_STREAMS = {name: json.load(open(os.path.join(GOLDEN, name + "_expected.json"))) for name in ("intra1080", "intra4k")}
 
 
+@pytest.mark.parametrize("name", sorted(REAL_STREAMS))
 @pytest.mark.skipif(oracle_lib.ref_path("libde265_ref.so") is None, reason="oracle/_ref not built")
-def test_unmodified_reference_reproduces_intra1080_md5():
+def test_unmodified_reference_reproduces_real_intra_stream_md5(name):
+    exp = REAL_STREAMS[name]
     dec = de265.Decoder(oracle_lib.ref_path("libde265_ref.so"))
     md = hashlib.md5()
-    n = dec.decode_stream(open(os.path.join(GOLDEN, "intra1080.h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
+    n = dec.decode_stream(open(os.path.join(GOLDEN, name + ".h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
     dec.close()
-    assert n == INTRA1080["pictures"] and md.hexdigest() == INTRA1080["md5_of_all_planes_in_output_order"]
+    assert n == exp["pictures"] and md.hexdigest() == exp["md5_of_all_planes_in_output_order"]
 
 
+@pytest.mark.parametrize("name", sorted(REAL_STREAMS))
 @pytest.mark.skipif(oracle_lib.ref_path("libde265_hooked.so") is None, reason="oracle/_ref not built (needs /root/reference)")
-def test_reference_parser_plus_oracle_reproduces_intra1080_md5(b200lib, oracle_mod):
-    """1920x1080 (33.75 CTB rows of 32: partial CTBs), every intra mode / partition / TU split a real encoder chose, DST, deblock, SAO."""
+def test_reference_parser_plus_oracle_reproduces_real_intra_stream_md5(b200lib, oracle_mod, name):
+    """1920x1080 and 3840x2160 (33.75 / 67.5 CTB rows of 32: partial CTBs), every intra mode / partition / TU split a real encoder chose, DST."""
+    exp = REAL_STREAMS[name]
     orc = oracle_mod.Oracle()
     dec = de265.Decoder(oracle_lib.ref_path("libde265_hooked.so"))
     stats = {"tus": 0, "pics": 0}
@@ -168,11 +172,11 @@ def test_reference_parser_plus_oracle_reproduces_intra1080_md5(b200lib, oracle_m
 
     dec.attach(sink)
     md = hashlib.md5()
-    n = dec.decode_stream(open(os.path.join(GOLDEN, "intra1080.h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
+    n = dec.decode_stream(open(os.path.join(GOLDEN, name + ".h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
     dec.close()
     orc.close()
-    assert n == INTRA1080["pictures"] and stats["pics"] == n and stats["tus"] > 50000
-    assert md.hexdigest() == INTRA1080["md5_of_all_planes_in_output_order"]
+    assert n == exp["pictures"] and stats["pics"] == n and stats["tus"] > 50000
+    assert md.hexdigest() == exp["md5_of_all_planes_in_output_order"]
 
 
 # ---- synthetic generator sanity (host logic) ---------------------------------------------------------

@@ -64,11 +64,13 @@ def test_girlshy_end_to_end_through_libde265_api(b200lib):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["intra1080", "intra4k"])
 @pytest.mark.skipif(oracle_lib.ref_path("libde265_hooked.so") is None, reason="oracle/_ref not shipped")
-def test_intra1080_real_stream_end_to_end(b200lib):
-    """BASELINE config 2's size on a REAL bitstream (made with the reference's own encoder, tests/golden/make_intra1080.py):
-    reference parser -> records -> B200 engine; md5 of the output must equal the unmodified reference decoder's."""
-    exp = json.load(open(os.path.join(GOLDEN, "intra1080_expected.json")))
+def test_real_intra_stream_end_to_end(b200lib, name):
+    """BASELINE config 2's size (1080p intra) and the 4K size on REAL bitstreams (made with the reference's own encoder,
+    tests/golden/make_intra_streams.py): reference parser -> records -> B200 engine; md5 of the output must equal the
+    unmodified reference decoder's."""
+    exp = json.load(open(os.path.join(GOLDEN, name + "_expected.json")))
     eng = Engine(0)
     dec = de265.Decoder(oracle_lib.ref_path("libde265_hooked.so"))
 
@@ -79,7 +81,7 @@ def test_intra1080_real_stream_end_to_end(b200lib):
 
     dec.attach(sink)
     md = hashlib.md5()
-    n = dec.decode_stream(open(os.path.join(GOLDEN, "intra1080.h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
+    n = dec.decode_stream(open(os.path.join(GOLDEN, name + ".h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)])
     dec.close()
     eng.close()
     assert n == exp["pictures"] and md.hexdigest() == exp["md5_of_all_planes_in_output_order"]
