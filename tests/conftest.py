@@ -14,8 +14,9 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def b200lib():
-    from libde265_b200 import capi
-    return capi.load()  # raises when the CUDA library has not been built: never silently skipped
+    from libde265_b200 import build, capi
+    build.build_library()  # in-tree nvcc build for sm_100a if missing / stale (cross-compiles without a GPU); raises on failure
+    return capi.load()  # raises when the CUDA library is missing: never silently skipped
 
 
 @pytest.fixture(scope="session")
