@@ -230,54 +230,61 @@ def calibrate_port():
     return out
 
 
-REAL_STREAM = os.path.join(ROOT, "tests", "golden", "intra1080.h265")  # 1920x1080 intra-only, made with the reference's encoder
+# real intra-only streams made with the reference's own encoder (tests/golden/make_intra_streams.py)
+REAL_STREAMS = {"1080p_intra": ("intra1080.h265", "1920x1080 intra, 2 pictures"), "4k_intra": ("intra4k.h265", "3840x2160 intra, 1 picture")}
 
 
 def real_stream_reference(repeats=3):
-    """BASELINE config 2's size on a real bitstream, the REAL reference: oracle/_ref/libde265_ref.so (SIMD table) decoding
-    tests/golden/intra1080.h265 through the de265.h API, one thread (the stream has one slice and no WPP)."""
+    """Real bitstreams at BASELINE config 2's size and at 4K, the REAL reference: oracle/_ref/libde265_ref.so (SIMD table)
+    decoding them through the de265.h API, one thread (the streams have one slice per picture and no WPP)."""
     from libde265_b200 import de265
     lib = os.path.join(ROOT, "oracle", "_ref", "libde265_ref.so")
     if not os.path.exists(lib):
         return {"error": "oracle/_ref/libde265_ref.so not shipped"}
-    data = open(REAL_STREAM, "rb").read()
-    best = 0.0
-    for _ in range(repeats):
-        dec = de265.Decoder(lib)
-        t0 = time.time()
-        n = dec.decode_stream(data, lambda img: None)
-        dt = time.time() - t0
-        dec.close()
-        best = max(best, n / dt)
-    return {"stream": "tests/golden/intra1080.h265 (1920x1080 intra, 2 pictures)", "value": round(best, 2), "unit": "frames/s", "kind": "reference",
-            "cores": 1, "note": "full decode incl. parsing"}
+    out = {}
+    for key, (fname, what) in REAL_STREAMS.items():
+        data = open(os.path.join(ROOT, "tests", "golden", fname), "rb").read()
+        best = 0.0
+        for _ in range(repeats):
+            dec = de265.Decoder(lib)
+            t0 = time.time()
+            n = dec.decode_stream(data, lambda img: None)
+            dt = time.time() - t0
+            dec.close()
+            best = max(best, n / dt)
+        out[key] = {"stream": f"tests/golden/{fname} ({what})", "value": round(best, 2), "unit": "frames/s", "kind": "reference", "cores": 1,
+                    "note": "full decode incl. parsing"}
+    return out
 
 
 def real_stream_b200(eng, repeats=3):
-    """The same stream through the drop-in path: reference parser with the B2 hooks (oracle/_ref/libde265_hooked.so) on one
+    """The same streams through the drop-in path: reference parser with the B2 hooks (oracle/_ref/libde265_hooked.so) on one
     host thread -> records -> b200_engine_submit_picture -> D2H into the decoder's pictures."""
     from libde265_b200 import de265
     lib = os.path.join(ROOT, "oracle", "_ref", "libde265_hooked.so")
     if not os.path.exists(lib):
         return {"error": "oracle/_ref/libde265_hooked.so not shipped"}
-    data = open(REAL_STREAM, "rb").read()
 
     def sink(pic, planes, strides):
         eng.submit(pic)
         eng.read_slot_into(pic.params.dst_slot, [planes[0], planes[1], planes[2]], [strides[0], strides[1], strides[2]])
         return 0
 
-    best = 0.0
-    for _ in range(repeats):
-        dec = de265.Decoder(lib)
-        dec.attach(sink)
-        t0 = time.time()
-        n = dec.decode_stream(data, lambda img: None)
-        dt = time.time() - t0
-        dec.close()
-        best = max(best, n / dt)
-    return {"stream": "tests/golden/intra1080.h265 (1920x1080 intra, 2 pictures)", "value": round(best, 2), "unit": "frames/s",
-            "note": "host parsing (reference parser, one thread) + recording + GPU reconstruction + D2H; parsing bounds it"}
+    out = {}
+    for key, (fname, what) in REAL_STREAMS.items():
+        data = open(os.path.join(ROOT, "tests", "golden", fname), "rb").read()
+        best = 0.0
+        for _ in range(repeats):
+            dec = de265.Decoder(lib)
+            dec.attach(sink)
+            t0 = time.time()
+            n = dec.decode_stream(data, lambda img: None)
+            dt = time.time() - t0
+            dec.close()
+            best = max(best, n / dt)
+        out[key] = {"stream": f"tests/golden/{fname} ({what})", "value": round(best, 2), "unit": "frames/s",
+                    "note": "host parsing (reference parser, one thread) + recording + GPU reconstruction + D2H; parsing bounds it"}
+    return out
 
 
 def cpu_baseline_inline(seq, ref0, ref_slot, n_pics):
@@ -331,7 +338,7 @@ def main():
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1000.0 * 32 / best["value"], 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if a.bit_depth == 8 else "u16", "data": "synthetic",
                 "config": config, "cpu_baseline": best,
-                "e2e": {"value": best["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "real_stream_1080p_intra": real}
+                "e2e": {"value": best["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "real_streams": real}
         print(json.dumps(line))
         return 0
 
@@ -461,9 +468,9 @@ def main():
                                                     "note": "same steps with picture pipelining off (per-stage timing pass)"},
                 "workload_gen_s": round(gen_s, 1)}
         try:
-            line["real_stream_1080p_intra"] = real_stream_b200(eng)
+            line["real_streams"] = real_stream_b200(eng)
         except Exception as e:  # informative extra, never fatal
-            line["real_stream_1080p_intra"] = {"error": str(e)[:200]}
+            line["real_streams"] = {"error": str(e)[:200]}
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_inline(seq, ref0, key_slot, 16 if a.width * a.height > 1920 * 1080 else 32)
             line["cpu_baseline"]["calibration"] = calibrate_port()
