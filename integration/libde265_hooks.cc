@@ -9,6 +9,9 @@
 
 #include "libde265_hooks.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <map>
 #include <tuple>
 #include <vector>
@@ -87,10 +90,11 @@ void begin_picture_if_needed(hook_state* st, base_context* ctx, de265_image* img
 }
 
 template <class pixel_t>
-uint64_t intra_avail_mask(const de265_image* img, int xB, int yB, int nT, int cIdx)
+uint64_t intra_avail_mask_via_border_computer(const de265_image* img, int xB, int yB, int nT, int cIdx)
 {
   // Runs the reference's own availability derivation (intrapred.h:436-633) and packs `available[]`.
-  // The sample values it gathers from the (unreconstructed) host planes are ignored.
+  // The sample values it gathers from the (unreconstructed) host planes are ignored.  Slow (it copies 4nT+1 samples per
+  // TU); kept as the cross-check of intra_avail_mask below (environment B200_HOOK_CHECK=1).
   pixel_t border_mem[4 * MAX_INTRA_PRED_BLOCK_SIZE + 1];
   intra_border_computer<pixel_t> c;
   c.init(&border_mem[2 * MAX_INTRA_PRED_BLOCK_SIZE], img, nT, cIdx, xB, yB);
@@ -102,6 +106,51 @@ uint64_t intra_avail_mask(const de265_image* img, int xB, int yB, int nT, int cI
     if (c.available[4 * k + 1]) m |= 1ull << (B200_AVAIL_TOP_BIT0 + k);
   }
   if (c.available[0]) m |= 1ull << B200_AVAIL_CORNER_BIT;
+  return m;
+}
+
+// The same decisions without touching a sample: the side flags of intra_border_computer::preproc (intrapred.h:436-526:
+// picture border, slice address and tile id of the neighbouring CTBs) and, per group of 4 border samples, the tests of
+// fill_from_image (intrapred.h:529-633: the neighbour's minimum-TB z-scan address must not exceed the current block's;
+// with constrained_intra_pred the neighbour must be intra).  One group = one bit of b200_tu.avail.
+uint64_t intra_avail_mask(const de265_image* img, int xB, int yB, int nT, int cIdx)
+{
+  const seq_parameter_set& sps = img->get_sps();
+  const pic_parameter_set& pps = img->get_pps();
+  const int SW = (cIdx == 0) ? 1 : sps.SubWidthC, SH = (cIdx == 0) ? 1 : sps.SubHeightC;
+  const int xL = xB * SW, yL = yB * SH;
+  bool aL = true, aT = true, aTR = true, aTL = true;
+  if (xL == 0) aL = aTL = false;
+  if (yL == 0) aT = aTL = aTR = false;
+  if (xL + nT * SW >= sps.pic_width_in_luma_samples) aTR = false;
+  const int l2c = sps.Log2CtbSizeY, wC = sps.PicWidthInCtbsY;
+  const int xC = xL >> l2c, yC = yL >> l2c, xLc = (xL - 1) >> l2c, xRc = (xL + nT * SW) >> l2c, yTc = (yL - 1) >> l2c;
+  const int sl = img->get_SliceAddrRS(xC, yC);
+  const uint32_t tile = pps.scan->TileIdRS[xC + yC * wC];
+  auto same = [&](int cx, int cy) { return img->get_SliceAddrRS(cx, cy) == sl && pps.scan->TileIdRS[cx + cy * wC] == tile; };
+  if (aL && !same(xLc, yC)) aL = false;
+  if (aT && !same(xC, yTc)) aT = false;
+  if (aTL && !same(xLc, yTc)) aTL = false;
+  if (aTR && !same(xRc, yTc)) aTR = false;
+  int nBottom = (sps.pic_height_in_luma_samples - yL + SH - 1) / SH;
+  if (nBottom > 2 * nT) nBottom = 2 * nT;
+  int nRight = (sps.pic_width_in_luma_samples - xL + SW - 1) / SW;
+  if (nRight > 2 * nT) nRight = 2 * nT;
+  const int l2t = sps.Log2MinTrafoSize, wT = sps.PicWidthInTbsY;
+  const int cur = pps.scan->MinTbAddrZS[(xL >> l2t) + (yL >> l2t) * wT];
+  const bool cip = pps.constrained_intra_pred_flag;
+  auto ok = [&](int xs, int ys) {  // component coordinates of a neighbouring sample
+    const int xl = xs * SW, yl = ys * SH;
+    if (pps.scan->MinTbAddrZS[(xl >> l2t) + (yl >> l2t) * wT] > cur) return false;
+    return !cip || img->get_pred_mode(xl, yl) == MODE_INTRA;
+  };
+  uint64_t m = 0;
+  if (aL)
+    for (int y = nBottom - 1; y >= 0; y -= 4)
+      if (ok(xB - 1, yB + y)) m |= 1ull << (y >> 2);
+  if (aTL && ok(xB - 1, yB - 1)) m |= 1ull << B200_AVAIL_CORNER_BIT;
+  for (int x = 0; x < nRight; x += 4)
+    if (((x < nT) ? aT : aTR) && ok(xB + x, yB - 1)) m |= 1ull << (B200_AVAIL_TOP_BIT0 + (x >> 2));
   return m;
 }
 
@@ -150,7 +199,17 @@ bool b200_hook_decode_TU(thread_context* tctx, int x0, int y0, int nT, int cIdx,
     if (mode < 0 || mode >= 35) mode = INTRA_DC;
     tu.intra_mode = (uint8_t)mode;
     tu.flags |= B200_TU_INTRA;
-    tu.avail = img->high_bit_depth(cIdx) ? intra_avail_mask<uint16_t>(img, x0, y0, nT, cIdx) : intra_avail_mask<uint8_t>(img, x0, y0, nT, cIdx);
+    tu.avail = intra_avail_mask(img, x0, y0, nT, cIdx);
+    static const bool check = getenv("B200_HOOK_CHECK") != nullptr;
+    if (check) {
+      const uint64_t ref = img->high_bit_depth(cIdx) ? intra_avail_mask_via_border_computer<uint16_t>(img, x0, y0, nT, cIdx)
+                                                     : intra_avail_mask_via_border_computer<uint8_t>(img, x0, y0, nT, cIdx);
+      if (ref != tu.avail) {
+        fprintf(stderr, "b200 hook: availability mask mismatch at (%d,%d) nT %d cIdx %d: %llx vs reference %llx\n", x0, y0, nT, cIdx,
+                (unsigned long long)tu.avail, (unsigned long long)ref);
+        abort();
+      }
+    }
     if (sps.range_extension.implicit_rdpcm_enabled_flag && img->get_cu_transquant_bypass(x0, y0))  // intrapred.cc:308-310
       tu.flags |= B200_TU_NO_BOUNDARY_FILTER;
     if (sps.range_extension.implicit_rdpcm_enabled_flag && (tctx->cu_transquant_bypass_flag || tctx->transform_skip_flag[cIdx]) &&

@@ -205,3 +205,25 @@ def test_oracle_synthetic_idempotent(oracle_mod):
     orc.reconstruct(p1)
     again = orc.read_slot(1, p1.params)
     assert all((x == y).all() for x, y in zip(first, again))
+
+
+@pytest.mark.skipif(oracle_lib.ref_path("libde265_hooked.so") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_hook_availability_masks_match_the_reference_border_computer():
+    """integration/libde265_hooks.cc derives b200_tu.avail without touching samples; with B200_HOOK_CHECK=1 every TU's mask is
+    compared against the reference's own intra_border_computer (preproc + fill_from_image) and a mismatch aborts.  All three
+    golden streams (inter pictures with intra blocks, 1080p and 4K intra pictures)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import oracle_lib\n"
+        "from libde265_b200 import de265\n"
+        "for name, n_exp in (('girlshy', 75), ('intra1080', 2), ('intra4k', 1)):\n"
+        "    dec = de265.Decoder(oracle_lib.ref_path('libde265_hooked.so'))\n"
+        "    dec.attach(lambda pic, planes, strides: 0)\n"
+        "    n = dec.decode_stream(open(%r + '/' + name + '.h265', 'rb').read(), lambda img: None)\n"
+        "    dec.close()\n"
+        "    assert n == n_exp, (name, n)\n"
+        "print('masks ok')\n") % (ROOT, os.path.join(ROOT, "tests"), GOLDEN)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200_HOOK_CHECK="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "masks ok" in r.stdout, r.stderr[-800:]
