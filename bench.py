@@ -283,7 +283,7 @@ def real_stream_b200(eng, repeats=3):
             dec.close()
             best = max(best, n / dt)
         out[key] = {"stream": f"tests/golden/{fname} ({what})", "value": round(best, 2), "unit": "frames/s",
-                    "note": "host parsing (reference parser, one thread) + recording + GPU reconstruction + D2H; parsing bounds it"}
+                    "note": "the host application here is the reference decoder built with the B2 hooks (test artefact oracle/_ref/libde265_hooked.so): its parser on one thread + recording + GPU reconstruction + D2H; parsing bounds it. Extra leg, not part of value / e2e"}
     return out
 
 
