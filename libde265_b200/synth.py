@@ -88,8 +88,15 @@ class SynthPicture:
 
 def make_picture(width, height, pic_type="B", seed=1, bit_depth=8, dst_slot=0, ref_slots=(), log2_ctb=6, intra_frac=None,
                  weighted=False, deblock=True, sao=True, special_frac=0.01, cbf_prob=0.6, n_slices=1, scaling_list=False,
-                 size_area=(0.10, 0.25, 0.35, 0.30), qp_range=(22, 37), far_mv_frac=0.01):
-    """Generate one picture.  ``size_area`` = fraction of the picture area coded as 64/32/16/8 CUs."""
+                 size_area=(0.10, 0.25, 0.35, 0.30), qp_range=(22, 37), far_mv_frac=0.01, tiles=(1, 1), lf_across_tiles=True,
+                 rdpcm_frac=0.0, rotate_frac=0.0, tskip_max_log2=2):
+    """Generate one picture.  ``size_area`` = fraction of the picture area coded as 64/32/16/8 CUs.
+    ``tiles`` = (columns, rows) of uniformly spaced tiles (pps.cc uniform_spacing rule): CTBs are then coded in tile-scan
+    order and intra availability stops at tile borders (intrapred.h:488-503); ``lf_across_tiles`` False also removes the
+    deblocking edges on tile borders (deblock.cc:185-230) and lets SAO treat the neighbour tile as unavailable (sao.cc:157).
+    ``rdpcm_frac`` / ``rotate_frac``: share of the transform-skip / bypass TUs that use RDPCM (RExt implicit/explicit rdpcm,
+    transform.cc:425-432,566-578) resp. coefficient rotation (4x4 TUs of intra CUs, transform.cc:402-404);
+    ``tskip_max_log2``: largest transform-skip TU (RExt log2_max_transform_skip_block_size)."""
     assert width % 8 == 0 and height % 8 == 0
     rng = np.random.default_rng(seed)
     S = 1 << log2_ctb
@@ -107,7 +114,7 @@ def make_picture(width, height, pic_type="B", seed=1, bit_depth=8, dst_slot=0, r
     params.chroma_format_idc = 1
     params.bit_depth_luma = params.bit_depth_chroma = bit_depth
     params.log2_ctb_size = log2_ctb
-    flags = capi.PIC_STRONG_INTRA_SMOOTHING | capi.PIC_LF_ACROSS_TILES
+    flags = capi.PIC_STRONG_INTRA_SMOOTHING | (capi.PIC_LF_ACROSS_TILES if lf_across_tiles else 0)
     if sao:
         flags |= capi.PIC_SAO_ENABLED
     if not deblock:
@@ -119,21 +126,36 @@ def make_picture(width, height, pic_type="B", seed=1, bit_depth=8, dst_slot=0, r
     params.dst_slot = dst_slot
     params.poc = seed
 
-    # ---- slices: contiguous CTB ranges in raster order ----
+    # ---- tiles: uniform spacing; CTB coding order = tiles in raster order, CTBs in raster order inside a tile ----
     n_ctb = wctb * hctb
+    tcols, trows = max(1, min(tiles[0], wctb)), max(1, min(tiles[1], hctb))
+    col_bd = [(i * wctb) // tcols for i in range(tcols + 1)]
+    row_bd = [(j * hctb) // trows for j in range(trows + 1)]
+    ctb_tile = np.zeros(n_ctb, np.int32)
+    ctb_order = []  # raster addresses in coding (tile-scan) order
+    for tj in range(trows):
+        for ti in range(tcols):
+            for cy in range(row_bd[tj], row_bd[tj + 1]):
+                for cx in range(col_bd[ti], col_bd[ti + 1]):
+                    ctb_tile[cx + cy * wctb] = ti + tj * tcols
+                    ctb_order.append(cx + cy * wctb)
+    ts_of = np.zeros(n_ctb, np.int64)
+    ts_of[np.array(ctb_order)] = np.arange(n_ctb)
+
+    # ---- slices: contiguous CTB ranges in coding order ----
     n_slices = max(1, min(n_slices, n_ctb))
     bounds = [0] + sorted(rng.choice(np.arange(1, n_ctb), size=n_slices - 1, replace=False).tolist()) + [n_ctb] if n_slices > 1 else [0, n_ctb]
     slices = np.zeros(n_slices, SL_DT)
     ctb_slice = np.zeros(n_ctb, np.int32)
     for i in range(n_slices):
-        slices[i]["slice_addr_rs"] = bounds[i]
+        slices[i]["slice_addr_rs"] = ctb_order[bounds[i]]
         slices[i]["beta_offset"] = 2 * int(rng.integers(-3, 4))
         slices[i]["tc_offset"] = 2 * int(rng.integers(-3, 4))
         f = capi.SLICE_SAO_LUMA | capi.SLICE_SAO_CHROMA
         if n_slices == 1 or rng.random() < 0.5:
             f |= capi.SLICE_LF_ACROSS_SLICES
         slices[i]["flags"] = f
-        ctb_slice[bounds[i]:bounds[i + 1]] = i
+        ctb_slice[np.array(ctb_order[bounds[i]:bounds[i + 1]])] = i
 
     # ---- weights ----
     weights = np.zeros(0, WT_DT)
@@ -189,18 +211,18 @@ def make_picture(width, height, pic_type="B", seed=1, bit_depth=8, dst_slot=0, r
         return pos.astype(np.uint16), lv.astype(np.int16)
 
     def avail_mask(xB, yB, nT, cidx, ctb_addr, cur_slice):
-        """intrapred.h:436-633 for a single tile: picture bounds, slice of the neighbouring CTB, z-order of the min-TB."""
+        """intrapred.h:436-633: picture bounds, slice and tile of the neighbouring CTB, coding order of the min-TB."""
         sh = 1 if cidx else 0
         xL, yL = xB << sh, yB << sh
-        cur_z = (ctb_addr << 8) + int(_Z[(yL & (S - 1)) >> 2, (xL & (S - 1)) >> 2])
+        cur_z = (int(ts_of[ctb_addr]) << 8) + int(_Z[(yL & (S - 1)) >> 2, (xL & (S - 1)) >> 2])
 
         def ok(xn, yn):  # luma coordinates of the neighbour sample
             if xn < 0 or yn < 0 or xn >= width or yn >= height:
                 return False
             ca = (xn >> log2_ctb) + (yn >> log2_ctb) * wctb
-            if ctb_slice[ca] != cur_slice:
+            if ctb_slice[ca] != cur_slice or ctb_tile[ca] != ctb_tile[ctb_addr]:
                 return False
-            return (ca << 8) + int(_Z[(yn & (S - 1)) >> 2, (xn & (S - 1)) >> 2]) <= cur_z
+            return (int(ts_of[ca]) << 8) + int(_Z[(yn & (S - 1)) >> 2, (xn & (S - 1)) >> 2]) <= cur_z
 
         m = 0
         n_bottom = min(2 * nT, ((height - (yB << sh)) + sh) >> sh)
@@ -249,8 +271,13 @@ def make_picture(width, height, pic_type="B", seed=1, bit_depth=8, dst_slot=0, r
             if bypass:
                 flags |= capi.TU_BYPASS
                 lv = np.clip(lv, -255, 255).astype(np.int16)
-            elif nT == 4 and rng.random() < special_frac * 4:
+            elif log2 <= tskip_max_log2 and rng.random() < special_frac * 4:
                 flags |= capi.TU_TSKIP
+            if flags & (capi.TU_BYPASS | capi.TU_TSKIP):
+                if rng.random() < rdpcm_frac:
+                    flags |= capi.TU_RDPCM_H if rng.random() < 0.5 else capi.TU_RDPCM_V
+                if nT == 4 and cu_intra and rng.random() < rotate_frac:
+                    flags |= capi.TU_ROTATE
             if nT == 4 and cidx == 0 and cu_intra and not (flags & (capi.TU_BYPASS | capi.TU_TSKIP)):
                 flags |= capi.TU_DST
             if scaling_list and not bypass:
@@ -383,10 +410,8 @@ def make_picture(width, height, pic_type="B", seed=1, bit_depth=8, dst_slot=0, r
         else:
             coding_unit(x, y, log2, ctb_addr, cur_slice)
 
-    for cy in range(hctb):
-        for cx in range(wctb):
-            ca = cx + cy * wctb
-            coding_quadtree(cx * S, cy * S, log2_ctb, ca, int(ctb_slice[ca]))
+    for ca in ctb_order:
+        coding_quadtree((ca % wctb) * S, (ca // wctb) * S, log2_ctb, ca, int(ctb_slice[ca]))
 
     pus_a = np.array([(a, b, c, d, e, f, tuple(g), h, tuple(map(tuple, i)), j) for a, b, c, d, e, f, g, h, i, j in pus], PU_DT) if pus else np.zeros(0, PU_DT)
     tus_a = np.array(tus, TU_DT) if tus else np.zeros(0, TU_DT)
@@ -403,8 +428,14 @@ def make_picture(width, height, pic_type="B", seed=1, bit_depth=8, dst_slot=0, r
             edge = te | pe
             if vertical:
                 edge[:, 0] = False
+                if not lf_across_tiles:  # filterLeftCbEdge = 0 on tile borders (deblock.cc:196-203)
+                    for cb in col_bd[1:-1]:
+                        edge[:, (cb * S) >> 2] = False
             else:
                 edge[0, :] = False
+                if not lf_across_tiles:
+                    for rb in row_bd[1:-1]:
+                        edge[(rb * S) >> 2, :] = False
 
             def shift(a):  # value of the P-side unit (left / above)
                 r = np.empty_like(a)
@@ -438,6 +469,7 @@ def make_picture(width, height, pic_type="B", seed=1, bit_depth=8, dst_slot=0, r
     # ---- SAO ----
     ctbs = np.zeros(n_ctb, CTB_DT)
     ctbs["slice_idx"] = ctb_slice
+    ctbs["tile_id"] = ctb_tile
     if sao:
         lim = 7 if bit_depth == 8 else 31
         for i in range(n_ctb):

@@ -155,3 +155,143 @@ EXPORT void ref_deblock_luma_16(uint16_t* ptr, ptrdiff_t stride, int vertical, i
 { deblock_luma_kernel<uint16_t>(ptr, stride, vertical, dE, dEp, dEq, tc, fP, fQ, bd); }
 EXPORT void ref_deblock_chroma_16(uint16_t* ptr, ptrdiff_t stride, int vertical, int tc, int fP, int fQ, int bd)
 { deblock_chroma_kernel<uint16_t>(ptr, stride, vertical, tc, fP, fQ, bd); }
+
+// ---- picture-level post-filter DRIVERS of the reference on a synthetic de265_image --------------------------------
+// Pins the oracle's deblocking driver (orc_deblock_picture) and SAO driver (orc_sao_picture) — the part no table entry
+// reaches — to the reference's own edge_filtering_luma / edge_filtering_chroma (deblock.cc:608-617,764-774; V pass over
+// the whole picture, then H, as apply_deblocking_filter deblock.cc:908-946 orders them) and
+// apply_sample_adaptive_offset_sequential (sao.cc:327-382).  The image metadata is filled from the b200 records: bS from
+// bs_map (what derive_boundaryStrength would have stored, image.h:832-842), QP_Y and the no-filter bit per 8x8
+// (cu_transquant_bypass: deblock.cc:576-592, sao.cc:112-117), slice headers, SAO parameters, tiles (uniform spacing).
+#include "b200hevc.h"
+#include "libde265/deblock.h"
+#include "libde265/image.h"
+#include "libde265/pps.h"
+#include "libde265/sao.h"
+#include "libde265/slice.h"
+
+#include <memory>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+// non-static in deblock.cc but not declared in deblock.h
+void edge_filtering_luma(de265_image* img, bool vertical, int yStart, int yEnd, int xStart, int xEnd);
+void edge_filtering_chroma(de265_image* img, bool vertical, int yStart, int yEnd, int xStart, int xEnd);
+
+#include "libde265/decctx.h"
+
+// A decoder context only as the holder of the DSP table the drivers dispatch through (deblock.cc:595,736,752):
+// simd=0 the scalar fallback table, simd=1 whatever de265_acceleration_AUTO selects on this CPU (SSE4.1 + AVX2 + AVX-512).
+static decoder_context* filter_ctx(int simd)
+{
+  static decoder_context* ctx[2] = {nullptr, nullptr};
+  decoder_context*& c = ctx[simd ? 1 : 0];
+  if (!c) {
+    c = new decoder_context();
+    c->set_acceleration_functions(simd ? de265_acceleration_AUTO : de265_acceleration_SCALAR);
+  }
+  return c;
+}
+
+// planes: in/out, strides in BYTES.  stages: bit 0 deblock, bit 1 SAO, bit 2 use the SIMD table.
+EXPORT int ref_postfilter(const b200_picture* pic, void* const planes[3], const size_t strides[3], int stages, int tile_cols, int tile_rows)
+{
+  const b200_pic_params& p = pic->params;
+  auto sps = std::make_shared<seq_parameter_set>();
+  sps->set_defaults();
+  sps->pic_width_in_luma_samples = p.width;
+  sps->pic_height_in_luma_samples = p.height;
+  sps->chroma_format_idc = p.chroma_format_idc;
+  sps->bit_depth_luma = p.bit_depth_luma;
+  sps->bit_depth_chroma = p.bit_depth_chroma;
+  sps->log2_min_luma_coding_block_size = 3;
+  sps->log2_diff_max_min_luma_coding_block_size = p.log2_ctb_size - 3;
+  sps->log2_min_transform_block_size = 2;
+  sps->log2_diff_max_min_transform_block_size = (p.log2_ctb_size < 5 ? p.log2_ctb_size : 5) - 2;
+  sps->max_transform_hierarchy_depth_inter = 1;
+  sps->max_transform_hierarchy_depth_intra = 1;
+  sps->sample_adaptive_offset_enabled_flag = (p.flags & B200_PIC_SAO_ENABLED) != 0;
+  sps->pcm_loop_filter_disable_flag = 0;  // the records fold (pcm && pcm_loop_filter_disable) into the no-filter bit
+  if (sps->compute_derived_values(true) != DE265_OK) return -1;
+  auto pps = std::make_shared<pic_parameter_set>();
+  pps->set_defaults();
+  pps->pic_cb_qp_offset = p.pps_cb_qp_offset;
+  pps->pic_cr_qp_offset = p.pps_cr_qp_offset;
+  pps->loop_filter_across_tiles_enabled_flag = (p.flags & B200_PIC_LF_ACROSS_TILES) != 0;
+  pps->tiles_enabled_flag = tile_cols * tile_rows > 1;
+  pps->num_tile_columns = tile_cols;
+  pps->num_tile_rows = tile_rows;
+  pps->uniform_spacing_flag = 1;
+  pps->set_derived_values(sps.get());
+
+  de265_image img;
+  const de265_chroma chroma = p.chroma_format_idc == 0 ? de265_chroma_mono : p.chroma_format_idc == 1 ? de265_chroma_420 : p.chroma_format_idc == 2 ? de265_chroma_422 : de265_chroma_444;
+  if (img.alloc_image(p.width, p.height, chroma, sps, true, filter_ctx(stages & 4), 0, nullptr, false) != DE265_OK) return -2;
+  img.set_headers(nullptr, sps, pps);
+  img.clear_metadata();
+  const int nc = p.chroma_format_idc ? 3 : 1;
+  for (int c = 0; c < nc; c++) {
+    const int bpp = (c ? p.bit_depth_chroma : p.bit_depth_luma) > 8 ? 2 : 1;
+    for (int y = 0; y < img.get_height(c); y++)
+      memcpy(img.get_image_plane(c) + (size_t)y * img.get_image_stride(c) * bpp, (const uint8_t*)planes[c] + y * strides[c], (size_t)img.get_width(c) * bpp);
+  }
+  std::vector<std::unique_ptr<slice_segment_header>> hdrs;
+  for (uint32_t i = 0; i < pic->n_slices; i++) {
+    const b200_slice_info& s = pic->slices[i];
+    hdrs.emplace_back(new slice_segment_header());
+    slice_segment_header* h = hdrs.back().get();
+    h->SliceAddrRS = s.slice_addr_rs;
+    h->slice_segment_address = s.slice_addr_rs;
+    h->slice_beta_offset = s.beta_offset;
+    h->slice_tc_offset = s.tc_offset;
+    h->slice_deblocking_filter_disabled_flag = (s.flags & B200_SLICE_DEBLOCK_DISABLED) != 0;
+    h->slice_loop_filter_across_slices_enabled_flag = (s.flags & B200_SLICE_LF_ACROSS_SLICES) != 0;
+    h->slice_sao_luma_flag = (s.flags & B200_SLICE_SAO_LUMA) != 0;
+    h->slice_sao_chroma_flag = (s.flags & B200_SLICE_SAO_CHROMA) != 0;
+    img.add_slice_segment_header(h);
+  }
+  const int S = 1 << p.log2_ctb_size, wctb = sps->PicWidthInCtbsY, hctb = sps->PicHeightInCtbsY;
+  const int w8 = (p.width + 7) / 8, h8 = (p.height + 7) / 8, w4 = (p.width + 3) / 4, h4 = (p.height + 3) / 4;
+  for (int cy = 0; cy < hctb; cy++)
+    for (int cx = 0; cx < wctb; cx++) {
+      const b200_ctb_info& ci = pic->ctbs[cx + cy * wctb];
+      if (ci.slice_idx >= pic->n_slices) return -3;
+      if (ci.tile_id != pps->scan->TileIdRS[cx + cy * wctb]) return -4;  // the records' tile ids must be the uniform-spacing ones
+      img.set_SliceHeaderIndex(cx * S, cy * S, ci.slice_idx);
+      img.set_SliceAddrRS(cx, cy, pic->slices[ci.slice_idx].slice_addr_rs);
+      sao_info sao;
+      sao.SaoTypeIdx = ci.sao_type;
+      sao.SaoEoClass = ci.sao_eo_class;
+      for (int c = 0; c < 3; c++) {
+        sao.sao_band_position[c] = ci.sao_band_pos[c];
+        for (int k = 0; k < 4; k++) sao.saoOffsetVal[c][k] = ci.sao_offset[c][k];
+      }
+      img.set_sao_info(cx, cy, &sao);
+    }
+  for (int y = 0; y < h8; y++)
+    for (int x = 0; x < w8; x++) {
+      img.set_QPY(8 * x, 8 * y, 3, pic->qp_map[x + y * w8]);
+      if (pic->nofilt_map[x + y * w8] & 1) img.set_cu_transquant_bypass(8 * x, 8 * y, 3, 1);
+    }
+  if ((stages & 1) && pic->bs_map) {
+    for (int pass = 0; pass < 2; pass++) {
+      const bool vertical = pass == 0;
+      for (int y = 0; y < h4; y++)
+        for (int x = 0; x < w4; x++) {
+          const uint8_t b = pic->bs_map[x + y * w4];
+          img.set_deblk_bS(4 * x, 4 * y, vertical ? B200_BS_V(b) : B200_BS_H(b));
+        }
+      edge_filtering_luma(&img, vertical, 0, img.get_deblk_height(), 0, img.get_deblk_width());
+      if (p.chroma_format_idc) edge_filtering_chroma(&img, vertical, 0, img.get_deblk_height(), 0, img.get_deblk_width());
+    }
+  }
+  if (stages & 2) apply_sample_adaptive_offset_sequential(&img);
+  for (int c = 0; c < nc; c++) {
+    const int bpp = (c ? p.bit_depth_chroma : p.bit_depth_luma) > 8 ? 2 : 1;
+    for (int y = 0; y < img.get_height(c); y++)
+      memcpy((uint8_t*)planes[c] + y * strides[c], img.get_image_plane(c) + (size_t)y * img.get_image_stride(c) * bpp, (size_t)img.get_width(c) * bpp);
+  }
+  img.slices.clear();  // owned by hdrs
+  return 0;
+}

@@ -154,16 +154,22 @@ def test_1080p_intra_and_4k_b_frame(eng, oracle_mod):
     orc.close()
 
 
-def test_4k_main10_determinism_and_prepared_path(eng):
-    """Size-independent properties at BASELINE config 4's full size: replaying the same records gives identical
-    pictures (idempotence), and the prepared (HBM-resident) path equals the submit path."""
+def test_4k_main10_against_oracle_and_prepared_path(eng, oracle_mod):
+    """BASELINE config 4 at full size (3840x2160, 10 bit): one B picture (explicit weights on, both lists, far MVs) and one I
+    picture against the oracle, sample by sample; then the size-independent properties on top: replaying the same records is
+    idempotent and the prepared (HBM-resident) path equals the submit path."""
     W, H = 3840, 2160
+    orc = oracle_mod.Oracle()
     refs = [synth.random_planes(W, H, 10, s) for s in (3, 4)]
-    b = synth.make_picture(W, H, "B", seed=23, dst_slot=2, ref_slots=(0, 1), bit_depth=10)
+    b = synth.make_picture(W, H, "B", seed=23, dst_slot=2, ref_slots=(0, 1), bit_depth=10, weighted=True)
     for s, r in enumerate(refs):
         eng.upload_slot(s, b.params, r)
+        orc.upload_slot(s, b.params, r)
     eng.submit(b)
-    first = md5_planes(eng.read_slot(2, b.params))
+    orc.reconstruct(b)
+    got = eng.read_slot(2, b.params)
+    assert_same(got, orc.read_slot(2, b.params), "4K Main10 B")
+    first = md5_planes(got)
     eng.submit(b)
     assert md5_planes(eng.read_slot(2, b.params)) == first
     h = eng.prepare(b)
@@ -171,6 +177,33 @@ def test_4k_main10_determinism_and_prepared_path(eng):
     eng.run_prepared(h)
     assert md5_planes(eng.read_slot(2, b.params)) == first
     eng.free_prepared(h)
+    i = synth.make_picture(W, H, "I", seed=24, dst_slot=3, bit_depth=10)
+    eng.submit(i)
+    orc.reconstruct(i)
+    assert_same(eng.read_slot(3, i.params), orc.read_slot(3, i.params), "4K Main10 I")
+    orc.close()
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_rdpcm_rotation_and_large_transform_skip(eng, oracle_mod, bd):
+    """RExt residual variants the hooks can record (transform.cc:402-448, 548-596): horizontal / vertical RDPCM on
+    transform-skip and bypass TUs of every size, coefficient rotation on 4x4 TUs of intra CUs, transform skip up to 32x32;
+    stage by stage against the oracle (whose RDPCM / rotation / skip functions are pinned to the reference's table entries
+    in test_oracle_vs_ref.py)."""
+    orc = oracle_mod.Oracle()
+    run_sequence(eng, orc, 320, 192, bd, stages=True, special_frac=0.2, cbf_prob=0.9, rdpcm_frac=0.5, rotate_frac=0.5, tskip_max_log2=5)
+    orc.close()
+
+
+@pytest.mark.parametrize("bd,tiles,across,n_slices", [(8, (3, 2), False, 1), (8, (2, 3), True, 3), (10, (4, 1), False, 2), (8, (1, 4), False, 4)])
+def test_tiles(eng, oracle_mod, bd, tiles, across, n_slices):
+    """Multi-tile pictures: CTBs recorded in tile-scan order, intra availability cut at tile borders (intrapred.h:488-503),
+    no deblocking edge and no SAO neighbour across a tile border when loop_filter_across_tiles is off (deblock.cc:196-203,
+    sao.cc:157-163); with several slices on top.  Stage by stage against the oracle."""
+    orc = oracle_mod.Oracle()
+    run_sequence(eng, orc, 448, 256, bd, stages=True, tiles=tiles, lf_across_tiles=across, n_slices=n_slices)
+    run_sequence(eng, orc, 200, 136, bd, log2_ctb=4, tiles=tiles, lf_across_tiles=across, n_slices=n_slices, size_area=(0.0, 0.0, 0.5, 0.5))
+    orc.close()
 
 
 def test_pipelined_streams_match_serial_and_oracle(oracle_mod):

@@ -331,3 +331,56 @@ def test_deblock_segments(ref, orc, bd):
                                     r = base.astype(np.uint16)
                                     ref.ref_deblock_chroma_16(C.cast(r.ctypes.data + 2 * off, u16p), C.c_ssize_t(stride), vertical, tc, fP, fQ, bd)
                                 assert (o == r).all()
+
+
+# ---- picture-level post-filter drivers (no table entry reaches them) --------------------------------------
+POSTFILTER_CASES = [
+    # (bit depth, size, log2 CTB, tiles, loop filter across tiles, slices, special_frac (PCM / bypass blocks), picture type)
+    (8, (416, 240), 6, (1, 1), True, 1, 0.01, "B"),
+    (10, (416, 240), 6, (1, 1), True, 1, 0.01, "B"),
+    (8, (320, 200), 5, (1, 1), True, 4, 0.10, "B"),
+    (10, (320, 200), 5, (1, 1), True, 4, 0.10, "I"),
+    (8, (448, 256), 6, (3, 2), False, 1, 0.05, "B"),
+    (10, (448, 256), 6, (2, 3), False, 3, 0.05, "B"),
+    (8, (200, 136), 4, (4, 1), True, 2, 0.05, "I"),
+    (12, (200, 136), 4, (1, 4), False, 2, 0.05, "B"),
+]
+
+
+@pytest.mark.parametrize("bd,size,log2_ctb,tiles,across,n_slices,special,ptype", POSTFILTER_CASES)
+def test_postfilter_drivers_against_reference(ref, bd, size, log2_ctb, tiles, across, n_slices, special, ptype):
+    """The oracle's deblocking DRIVER (edge walk, QP averaging, tc / beta from the Q sample's slice, chroma QP mapping,
+    pcm / bypass exemptions) and SAO DRIVER (edge + band classes, picture / slice / tile boundary suppression, bypass skip,
+    out-of-place input) at 8, 10 and 12 bit against the reference's own edge_filtering_luma / edge_filtering_chroma
+    (deblock.cc:412-774, V pass then H pass as deblock.cc:908-946) and apply_sample_adaptive_offset_sequential
+    (sao.cc:327-382) run on a synthetic de265_image built from the same records (oracle/ref_shim.cc ref_postfilter)."""
+    from libde265_b200 import capi, synth
+    W, H = size
+    o = oracle_lib.Oracle()
+    refs = [synth.random_planes(W, H, bd, s) for s in (7, 8)]
+    pic = synth.make_picture(W, H, ptype, seed=900 + bd + n_slices, dst_slot=2, ref_slots=(0, 1) if ptype != "I" else (), bit_depth=bd,
+                             log2_ctb=log2_ctb, tiles=tiles, lf_across_tiles=across, n_slices=n_slices, special_frac=special,
+                             size_area=(0.1, 0.25, 0.35, 0.3) if log2_ctb == 6 else (0.0, 0.3 if log2_ctb == 5 else 0.0, 0.4, 0.3))
+    for s, r in enumerate(refs):
+        o.upload_slot(s, pic.params, r)
+    stage_out = {}
+    for st in (capi.STAGE_RECON, capi.STAGE_DEBLOCK, capi.STAGE_ALL):
+        pic.c.params.stop_after_stage = st
+        o.reconstruct(pic)
+        stage_out[st] = o.read_slot(2, pic.params)
+    pic.c.params.stop_after_stage = 0
+    o.close()
+    ref.ref_postfilter.argtypes = [C.POINTER(capi.Picture), capi.PlaneArray, capi.StrideArray, C.c_int, C.c_int, C.c_int]
+    dt = np.uint16 if bd > 8 else np.uint8
+    # bit 2 = the same drivers dispatching through the reference's SIMD table (what the CPU arm of bench.py times)
+    for stages, want in ((1, capi.STAGE_DEBLOCK), (3, capi.STAGE_ALL), (5, capi.STAGE_DEBLOCK), (7, capi.STAGE_ALL)):
+        planes = [np.ascontiguousarray(p.astype(dt)) for p in stage_out[capi.STAGE_RECON]]
+        rc = ref.ref_postfilter(C.byref(pic.c), capi.PlaneArray(*[p.ctypes.data for p in planes]), capi.StrideArray(*[p.strides[0] for p in planes]),
+                                stages, tiles[0], tiles[1])
+        assert rc == 0
+        for c in range(3):
+            diff = np.argwhere(planes[c] != stage_out[want][c])
+            assert len(diff) == 0, f"stages {stages} plane {c}: {len(diff)} samples differ, first at {diff[0]}"
+    # the filters did something: otherwise the comparison proves nothing
+    assert any((a != b).any() for a, b in zip(stage_out[capi.STAGE_RECON], stage_out[capi.STAGE_DEBLOCK]))
+    assert any((a != b).any() for a, b in zip(stage_out[capi.STAGE_DEBLOCK], stage_out[capi.STAGE_ALL]))
