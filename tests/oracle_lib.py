@@ -79,3 +79,42 @@ class Oracle:
         strides = [o.strides[0] for o in out] + [0] * (3 - len(out))
         assert self.lib.orc_read_slot(self.ctx, slot, capi.PlaneArray(*ptrs), capi.StrideArray(*strides)) == 0
         return out
+
+
+REPLAY_SO = os.path.join(REF_DIR, "libref_replay.so")
+_rr = None
+
+
+def ref_replay_lib():
+    """oracle/_ref/libref_replay.so: b200 records replayed through the REFERENCE's own reconstruction functions
+    (oracle/ref_replay.cc); None when oracle/_ref was not built / shipped."""
+    global _rr
+    if _rr is None and os.path.exists(REPLAY_SO):
+        lib = C.CDLL(REPLAY_SO)
+        vp = C.c_void_p
+        lib.rr_create.restype = vp
+        lib.rr_create.argtypes = [C.c_int]
+        lib.rr_destroy.argtypes = [vp]
+        lib.rr_destroy.restype = None
+        lib.rr_reconstruct.argtypes = [vp, C.POINTER(capi.Picture)]
+        lib.rr_fill_slot.argtypes = [vp, C.c_int, C.POINTER(capi.PicParams), C.c_int, C.c_int]
+        lib.rr_upload_slot.argtypes = [vp, C.c_int, C.POINTER(capi.PicParams), capi.PlaneArray, capi.StrideArray]
+        lib.rr_read_slot.argtypes = [vp, C.c_int, capi.PlaneArray, capi.StrideArray]
+        _rr = lib
+    return _rr
+
+
+class RefReplay(Oracle):
+    """Same interface as Oracle, executed by the reference's own code (simd=True: the table de265_acceleration_AUTO selects,
+    i.e. SSE4.1 + AVX2 + AVX-512 where the host has them; False: the scalar fallback table)."""
+
+    def __init__(self, simd=True):
+        lib = ref_replay_lib()
+        if lib is None:
+            raise RuntimeError("oracle/_ref/libref_replay.so not built (make -C oracle ref; needs /root/reference)")
+
+        class _Shim:  # present the rr_* entry points under the orc_* names the base class calls
+            orc_destroy, orc_reconstruct, orc_upload_slot, orc_fill_slot, orc_read_slot = (lib.rr_destroy, lib.rr_reconstruct, lib.rr_upload_slot,
+                                                                                           lib.rr_fill_slot, lib.rr_read_slot)
+        self.lib = _Shim
+        self.ctx = lib.rr_create(1 if simd else 0)

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #define CK(x)                                                                         \
@@ -47,7 +48,7 @@ __device__ __forceinline__ void tma3d(void* dst, const CUtensorMap* m, int x, in
 
 #define WARPS 4
 #define DEPTH 4
-#define BUF_BYTES 2048  // >= 80 * 23, 128-byte aligned slots
+#define BUF_BYTES 2304  // >= 96 * 23 (the ldg variant stages 16 extra bytes per row), 128-byte aligned slots
 
 __device__ __forceinline__ uint32_t hash32(uint32_t v)
 {
@@ -56,10 +57,13 @@ __device__ __forceinline__ uint32_t hash32(uint32_t v)
 }
 
 // mode 0: 2-D TMA of one box per op; mode 1: 3-D TMA (bw x bh x 2 planes); mode 2: per-lane 16-byte loads + STS.128
-template <int MODE>
-__global__ void __launch_bounds__(WARPS * 32) k_probe(const CUtensorMap* __restrict__ map, const uint8_t* __restrict__ base, int pitch, int W, int H, int bw,
-                                                       int bh, int iters, unsigned* sink)
+__constant__ CUtensorMap c_maps[4];
+
+template <int MODE, int SRC>  // SRC: where the tensor map lives: 0 global memory, 1 __grid_constant__ kernel parameter, 2 __constant__ array
+__global__ void __launch_bounds__(WARPS * 32) k_probe(const CUtensorMap* gmap, const __grid_constant__ CUtensorMap pmap, const uint8_t* __restrict__ base,
+                                                       int pitch, int W, int H, int bw, int bh, int iters, unsigned* sink)
 {
+  const CUtensorMap* map = SRC == 0 ? gmap : SRC == 1 ? &pmap : &c_maps[1];
   __shared__ __align__(128) uint8_t buf[WARPS][DEPTH][BUF_BYTES];
   __shared__ uint64_t bar[WARPS][DEPTH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,8 +122,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_probe(const CUtensorMap* __restr
   if (acc == 0x12345678u) *sink = acc;
 }
 
-int main()
+template <int SRC>
+static void launch(int mode, int grid, const CUtensorMap* dmap, const CUtensorMap& m, const uint8_t* d, int W, int H, int bw, int bh, int iters, unsigned* sink)
 {
+  if (mode == 0) k_probe<0, SRC><<<grid, WARPS * 32>>>(dmap, m, d, W, W, H, bw, bh, iters, sink);
+  else if (mode == 1) k_probe<1, SRC><<<grid, WARPS * 32>>>(dmap, m, d, W, W, H, bw, bh, iters, sink);
+  else k_probe<2, SRC><<<grid, WARPS * 32>>>(dmap, m, d, W, W, H, bw, bh, iters, sink);
+}
+
+int main(int argc, char** argv)
+{
+  const int src = argc > 1 ? atoi(argv[1]) : 1, only = argc > 2 ? atoi(argv[2]) : -1;
   const int W = 4096, H = 2320;  // padded 4K luma surface
   uint8_t* d;
   CK(cudaMalloc(&d, (size_t)W * H * 2));
@@ -134,16 +147,20 @@ int main()
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   int clk = 0;
   CK(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0));
-  printf("SMs %d, clock %d kHz\n", sms, clk);
+  printf("SMs %d, clock %d kHz, tensor map source %d (0 global, 1 grid_constant param, 2 __constant__)\n", sms, clk, src);
   struct Case { int mode, bw, bh; const char* name; };
   const Case cases[] = {{0, 32, 23, "tma2d 32x23"}, {0, 48, 23, "tma2d 48x23"}, {0, 80, 23, "tma2d 80x23"}, {0, 32, 15, "tma2d 32x15"}, {0, 16, 11, "tma2d 16x11"},
                         {1, 16, 11, "tma3d 16x11x2"}, {1, 48, 11, "tma3d 48x11x2"}, {0, 80, 71, "tma2d 80x71 (5.7 KB: needs BUF 8 KB: skipped)"},
                         {2, 32, 23, "ldg128 32(+16)x23"}, {2, 48, 23, "ldg128 48(+16)x23"}, {2, 80, 23, "ldg128 80(+16)x23"}, {2, 16, 11, "ldg128 16(+16)x11"}};
   CUtensorMap* dmap;
   CK(cudaMalloc(&dmap, sizeof(CUtensorMap)));
+  int ci = -1;
   for (const Case& c : cases) {
+    ci++;
+    if (only >= 0 && ci != only) continue;
     if (c.bw * c.bh * (c.mode == 1 ? 2 : 1) > BUF_BYTES) continue;
     CUtensorMap m;
+    memset(&m, 0, sizeof(m));
     if (c.mode == 0) {
       cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H}, strides[1] = {(cuuint64_t)W};
       cuuint32_t box[2] = {(cuuint32_t)c.bw, (cuuint32_t)c.bh}, es[2] = {1, 1};
@@ -158,6 +175,7 @@ int main()
       if (r) { printf("%s: encode failed %d\n", c.name, (int)r); continue; }
     }
     CK(cudaMemcpy(dmap, &m, sizeof(m), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyToSymbol(c_maps, &m, sizeof(m), sizeof(m)));  // slot 1
     for (int ctas_per_sm = 1; ctas_per_sm <= 4; ctas_per_sm *= 2) {
       const int iters = 2000, grid = sms * ctas_per_sm;
       cudaEvent_t e0, e1;
@@ -165,9 +183,9 @@ int main()
       CK(cudaEventCreate(&e1));
       for (int rep = 0; rep < 2; rep++) {
         CK(cudaEventRecord(e0));
-        if (c.mode == 0) k_probe<0><<<grid, WARPS * 32>>>(dmap, d, W, W, H, c.bw, c.bh, iters, sink);
-        else if (c.mode == 1) k_probe<1><<<grid, WARPS * 32>>>(dmap, d, W, W, H, c.bw, c.bh, iters, sink);
-        else k_probe<2><<<grid, WARPS * 32>>>(dmap, d, W, W, H, c.bw, c.bh, iters, sink);
+        if (src == 0) launch<0>(c.mode, grid, dmap, m, d, W, H, c.bw, c.bh, iters, sink);
+        else if (src == 1) launch<1>(c.mode, grid, dmap, m, d, W, H, c.bw, c.bh, iters, sink);
+        else launch<2>(c.mode, grid, dmap, m, d, W, H, c.bw, c.bh, iters, sink);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
       }
