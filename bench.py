@@ -143,91 +143,100 @@ class ClockSampler:
 METRIC = "decoded frames/sec at 4K Main profile, bit-exact YUV; MC kernel HBM GB/s"  # BASELINE.json
 
 
+def effective_cores():
+    """Host cores this process may really use: the scheduler affinity mask clamped by the cgroup CPU quota (a 1-GPU lease
+    on a 128-core node owns a share of it; os.cpu_count() would oversubscribe and inflate every GPU/CPU ratio)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:  # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:  # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    eff = n if quota is None else max(1, min(n, int(quota + 0.5)))
+    return eff, {"affinity": n, "cgroup_quota": None if quota is None else round(quota, 2), "os_cpu_count": os.cpu_count()}
+
+
 def cpu_replay_worker(args):
-    """One host core: generates one 4K picture of the given type and replays it `reps` times with the CPU restatement;
-    returns (type, pictures, seconds) — generation excluded."""
+    """One host core: generates one picture of the given type and replays it `reps` times through the REFERENCE's own
+    reconstruction functions on its SIMD table (oracle/_ref/libref_replay.so, oracle/ref_replay.cc), or — only when oracle/_ref
+    was not shipped — through the scalar port.  Returns (type, pictures, seconds, kind) — generation excluded."""
     seed0, width, height, bd, reps, ptype = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib  # CPU baseline leg: the only place bench.py touches the oracle
+    import oracle_lib  # CPU baseline leg: the only place bench.py touches oracle/
     from libde265_b200 import synth
-    orc = oracle_lib.Oracle()
+    kind = "reference" if oracle_lib.ref_replay_lib() is not None else "port"
+    orc = oracle_lib.RefReplay(simd=True) if kind == "reference" else oracle_lib.Oracle()
     if ptype == "I":
         pic = synth.make_picture(width, height, "I", seed=seed0, bit_depth=bd, dst_slot=2)
     else:
         pic = synth.make_picture(width, height, ptype, seed=seed0, bit_depth=bd, ref_slots=(0, 1) if ptype == "B" else (0,), dst_slot=2)
         for s in (0, 1):
             orc.upload_slot(s, pic.params, synth.random_planes(width, height, bd, s + 1))
+    orc.reconstruct(pic)  # warm-up: page in the surfaces
     t0 = time.time()
     for _ in range(reps):
         orc.reconstruct(pic)
     dt = time.time() - t0
     orc.close()
-    return ptype, reps, dt
+    return ptype, reps, dt, kind
 
 
-def cpu_baseline_parallel(width, height, bd, cores, reps):
-    """All host cores busy at once, one independent picture per core (the CPU analogue of one stream per GPU).  Cores time
-    I, P and B pictures (every 16th / 8th core an I / P picture, the rest B); the job rate is `cores` streams of the step's own mix
-    (1 I + 3 P + 28 B per 32 pictures) at the measured per-type seconds per picture under that full load."""
+def cpu_baseline_parallel(width, height, bd, reps, mix=(1, 3, 28), cores=None):
+    """The CPU arm: every usable host core busy at once, one independent stream per core (the CPU analogue of one stream per
+    GPU, and the most CPU-friendly reading of "all host threads": no synchronisation between cores at all).  Cores replay I, P
+    or B pictures; the job rate is `cores` streams of the workload's own picture mix at the measured per-type seconds per
+    picture under that full load.  A one-core run first gives the unloaded per-core rate (scaling check of the core count)."""
     import multiprocessing as mp
-    types = ["I" if i % 16 == 1 else "P" if i % 8 == 2 else "B" for i in range(cores)] if cores >= 3 else ["B"] * cores
-    if cores >= 3 and "I" not in types:
-        types[1] = "I"
-    if cores >= 3 and "P" not in types:
-        types[2] = "P"
-    with mp.get_context("spawn").Pool(cores) as pool:
+    info = {}
+    if cores is None:
+        cores, info = effective_cores()
+    nI, nP, nB = mix
+    if nP == 0 and nB == 0:
+        types = ["I"] * cores
+    else:
+        types = ["I" if i % 16 == 1 else "P" if i % 8 == 2 else "B" for i in range(cores)] if cores >= 3 else ["B"] * cores
+        if cores >= 3 and "I" not in types:
+            types[1] = "I"
+        if cores >= 3 and "P" not in types:
+            types[2] = "P"
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1) as pool:  # unloaded single-core rate of the dominant picture type
+        solo = pool.map(cpu_replay_worker, [(1002, width, height, bd, max(2, reps // 2), types[0])])[0]
+    with ctx.Pool(cores) as pool:
         res = pool.map(cpu_replay_worker, [(1002 + i % 4, width, height, bd, reps, types[i]) for i in range(cores)])
     sec = {}
     for t in ("I", "P", "B"):
         rs = [r for r in res if r[0] == t]
         if rs:
             sec[t] = sum(r[2] for r in rs) / sum(r[1] for r in rs)  # seconds per picture on one core, all cores loaded
+    dom = types[0]
+    sec.setdefault("B", sec.get("I"))
     sec.setdefault("I", sec["B"])
     sec.setdefault("P", sec["B"])
-    step_s = sec["I"] + 3 * sec["P"] + 28 * sec["B"]
+    step_s = nI * sec["I"] + nP * sec["P"] + nB * sec["B"]
     n = sum(r[1] for r in res)
-    return {"value": round(cores * 32 / step_s, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n} replays of synthetic {width}x{height} pictures ({reps}/core on {cores} processes: {types.count('I')} I, {types.count('P')} P, {types.count('B')} B cores; "
-                      f"{sec['I']:.2f}/{sec['P']:.2f}/{sec['B']:.2f} s per I/P/B picture and core), combined in the step's mix 1 I + 3 P + 28 B, by the CPU "
-                      "restatement oracle/hevc_oracle.c (scalar C, -O3)"}
-
-
-def calibrate_port():
-    """How the scalar port relates to the REAL reference on this host: the reference's own decoder (oracle/_ref/dec265, built
-    from /root/reference; full decode incl. parsing, 1 thread, SIMD and scalar tables) and the port's replay of the same
-    stream's records (reconstruction only), on the golden stream — the only bitstream that exists offline.  Reported next
-    to cpu_baseline so the port's number can be read for what it is; never used to scale any value."""
-    import re
-    import subprocess
-    out = {"stream": "tests/golden/girlshy.h265 (416x240, 75 pictures), one core"}
-    stream = os.path.join(ROOT, "tests", "golden", "girlshy.h265")
-    dec = os.path.join(ROOT, "oracle", "_ref", "dec265")
-    try:
-        if os.path.exists(dec):
-            for key, extra in (("reference_simd_fps_incl_parsing", []), ("reference_scalar_fps_incl_parsing", ["-0"])):
-                best = 0.0
-                for _ in range(3):
-                    r = subprocess.run([dec, "-q"] + extra + ["-o", "/dev/null", stream], capture_output=True, text=True, timeout=60)
-                    m = re.search(r"@ ([0-9.]+) fps", r.stdout + r.stderr)
-                    if m:
-                        best = max(best, float(m.group(1)))
-                out[key] = best or None
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_lib
-        from libde265_b200 import capi
-        from test_cpu_oracle import load_records
-        pics, _keep = load_records(capi.load())
-        orc = oracle_lib.Oracle()
-        for p in pics:
-            orc.reconstruct(p)
-        t0 = time.time()
-        for p in pics:
-            orc.reconstruct(p)
-        out["port_replay_fps_reconstruction_only"] = round(len(pics) / (time.time() - t0), 1)
-        orc.close()
-    except Exception as e:  # calibration is informative only
-        out["error"] = str(e)[:200]
-    return out
+    kind = res[0][3]
+    value = cores * (nI + nP + nB) / step_s
+    solo_s = solo[2] / solo[1]
+    how = ("the REFERENCE's own reconstruction functions on its SIMD table (generate_inter_prediction_samples, decode_intra_prediction, "
+           "scale_coefficients, edge_filtering_*, apply_sample_adaptive_offset_sequential via oracle/_ref/libref_replay.so; "
+           "de265_acceleration_AUTO = SSE4.1+AVX2+AVX-512 where present); reconstruction only, no parsing"
+           if kind == "reference" else "the CPU restatement oracle/hevc_oracle.c (scalar C, -O3): oracle/_ref not shipped")
+    return {"value": round(value, 3), "unit": "frames/s", "cores": cores, "kind": kind, "frames_per_s_per_core": round(value / cores, 3),
+            "core_count_source": info,
+            "one_core_alone": {"picture_type": dom, "s_per_picture": round(solo_s, 4), "loaded_s_per_picture": round(sec[dom], 4),
+                               "parallel_efficiency": round(solo_s / sec[dom], 3)},
+            "sample": f"{n} replays of synthetic {width}x{height} {bd}-bit pictures ({reps}/core on {cores} processes: {types.count('I')} I, {types.count('P')} P, "
+                      f"{types.count('B')} B cores; {sec['I']:.3f}/{sec['P']:.3f}/{sec['B']:.3f} s per I/P/B picture and core), combined in the workload's mix "
+                      f"{nI} I + {nP} P + {nB} B, by {how}"}
 
 
 # real intra-only streams made with the reference's own encoder (tests/golden/make_intra_streams.py)
@@ -287,21 +296,6 @@ def real_stream_b200(eng, repeats=3):
     return out
 
 
-def cpu_baseline_inline(seq, ref0, ref_slot, n_pics):
-    """Rank 0, one core: replays the first pictures of the very workload the GPU ran."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib  # CPU baseline leg: the only place bench.py touches the oracle
-    orc = oracle_lib.Oracle()
-    orc.upload_slot(ref_slot, seq[0].params, ref0)
-    t0 = time.time()
-    for p in seq[:n_pics]:
-        orc.reconstruct(p)
-    dt = time.time() - t0
-    orc.close()
-    return {"value": round(n_pics / dt, 3), "unit": "frames/s", "cores": 1, "kind": "port",
-            "sample": f"first {n_pics} pictures of the step (decode order: P,B,B,...) replayed by the CPU restatement oracle/hevc_oracle.c (scalar C, -O3)"}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,13 +317,11 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        cores = os.cpu_count() or 1
-        reps = 8 if a.width * a.height > 1920 * 1080 else 32
+        reps = 12 if a.width * a.height > 1920 * 1080 else 48
         vals = []
         for _ in range(max(1, min(a.steps, 2))):
-            vals.append(cpu_baseline_parallel(a.width, a.height, a.bit_depth, cores, reps))
+            vals.append(cpu_baseline_parallel(a.width, a.height, a.bit_depth, reps))
         best = max(vals, key=lambda v: v["value"])
-        best["calibration"] = calibrate_port()
         try:
             real = real_stream_reference()
         except Exception as e:  # informative extra, never fatal
@@ -472,8 +464,7 @@ def main():
         except Exception as e:  # informative extra, never fatal
             line["real_streams"] = {"error": str(e)[:200]}
         if not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_inline(seq, ref0, key_slot, 16 if a.width * a.height > 1920 * 1080 else 32)
-            line["cpu_baseline"]["calibration"] = calibrate_port()
+            line["cpu_baseline"] = cpu_baseline_parallel(a.width, a.height, a.bit_depth, 4 if a.width * a.height > 1920 * 1080 else 16)
         print(json.dumps(line))
     for h in prepared:
         eng.free_prepared(h)
