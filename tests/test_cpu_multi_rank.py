@@ -75,5 +75,5 @@ def test_reference_arm_json_line():
     assert line["impl"] == "reference" and line["metric"] == base["metric"] and line["unit"] == "frames/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
-    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb and "calibration" in cb
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb and cb["frames_per_s_per_core"] > 0 and "one_core_alone" in cb
     assert "workload" in line["config"] and "model" not in line["config"]
