@@ -29,6 +29,7 @@
 #include "kernels_filter.cuh"
 #include "kernels_mc.cuh"
 #include "kernels_mc8.cuh"
+#include "kernels_mct.cuh"
 #include "kernels_recon.cuh"
 
 // ---- error reporting -----------------------------------------------------------------------------
@@ -52,19 +53,46 @@ extern "C" const char* b200_last_error(void) { return g_err; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- surfaces ------------------------------------------------------------------------------------
+// A surface keeps a replicated BORDER around every plane (B200_PAD_* samples on each side) so that the motion-compensation
+// kernel never clamps a coordinate: mc_luma / mc_chroma clamp every reference sample position to the picture
+// (motion.cc:147-153, 251-254), which is the same as reading a picture whose edge samples are replicated outwards; a window
+// that lies further out than the border is moved to the border's rim, where every sample already is the edge sample.
+// plane[c] points at sample (0, 0); the two chroma planes share one allocation (fixed plane stride) so that one 3-D TMA box
+// fetches the Cb and the Cr window of a prediction unit.
+// (B200_PAD_X / _Y / _CX / _CY: dev_common.cuh)
+
 struct Surface {
-  uint8_t* plane[3] = {nullptr, nullptr, nullptr};
+  uint8_t* plane[3] = {nullptr, nullptr, nullptr};  // sample (0,0) of each plane
+  uint8_t* alloc[2] = {nullptr, nullptr};           // luma allocation, chroma allocation (Cb then Cr)
+  size_t alloc_bytes[2] = {0, 0};
   int pitch[3] = {0, 0, 0};
   int w = 0, h = 0, cw = 0, ch = 0, chroma = 0, bd_y = 0, bd_c = 0;
   bool valid = false;  // holds a picture
+  bool has_tm = false; // tensor maps of the padded planes for the TMA-staged MC kernel (8-bit surfaces)
+  CUtensorMap tm_luma, tm_chroma;
 };
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*b200_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static b200_encode_tiled_fn encode_tiled()
+{
+  static b200_encode_tiled_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+    return (b200_encode_tiled_fn)p;
+  }();
+  return fn;
+}
 
 static void surface_free(Surface& s)
 {
-  for (int c = 0; c < 3; c++) {
-    if (s.plane[c]) cudaFree(s.plane[c]);
-    s.plane[c] = nullptr;
+  for (int i = 0; i < 2; i++) {
+    if (s.alloc[i]) cudaFree(s.alloc[i]);
+    s.alloc[i] = nullptr;
   }
+  for (int c = 0; c < 3; c++) s.plane[c] = nullptr;
   s.w = s.h = 0;
   s.valid = false;
 }
@@ -85,17 +113,101 @@ static int surface_ensure(Surface& s, const b200_pic_params& p, cudaStream_t st)
   surface_free(s);
   s.w = p.width; s.h = p.height; s.cw = cw; s.ch = ch; s.chroma = p.chroma_format_idc;
   s.bd_y = p.bit_depth_luma; s.bd_c = p.bit_depth_chroma;
-  // rows padded to 256 bytes: every CTB row segment starts 16-byte aligned and vector accesses may overshoot
-  // the picture width inside the padding
-  s.pitch[0] = (int)align_up((size_t)p.width * bytes_per_sample(p.bit_depth_luma) + 16, 256);
-  s.pitch[1] = s.pitch[2] = cw ? (int)align_up((size_t)cw * bytes_per_sample(p.bit_depth_chroma) + 16, 256) : 0;
-  CU(cudaMalloc(&s.plane[0], (size_t)s.pitch[0] * p.height));
-  CU(cudaMemsetAsync(s.plane[0], 0, (size_t)s.pitch[0] * p.height, st));
-  for (int c = 1; c < 3 && cw; c++) {
-    CU(cudaMalloc(&s.plane[c], (size_t)s.pitch[c] * ch));
-    CU(cudaMemsetAsync(s.plane[c], 0, (size_t)s.pitch[c] * ch, st));
+  const int bl = bytes_per_sample(p.bit_depth_luma), bc = bytes_per_sample(p.bit_depth_chroma);
+  // rows padded to 256 bytes: sample (0, y) is 128-byte aligned, every CTB row segment 16-byte aligned, and vector accesses may
+  // overshoot the picture width inside the border
+  s.pitch[0] = (int)align_up((size_t)(p.width + 2 * B200_PAD_X) * bl, 256);
+  s.pitch[1] = s.pitch[2] = cw ? (int)align_up((size_t)(cw + 2 * B200_PAD_CX) * bc, 256) : 0;
+  s.alloc_bytes[0] = (size_t)s.pitch[0] * (p.height + 2 * B200_PAD_Y);
+  CU(cudaMalloc(&s.alloc[0], s.alloc_bytes[0]));
+  CU(cudaMemsetAsync(s.alloc[0], 0, s.alloc_bytes[0], st));
+  s.plane[0] = s.alloc[0] + (size_t)B200_PAD_Y * s.pitch[0] + (size_t)B200_PAD_X * bl;
+  if (cw) {
+    const size_t plane_bytes = (size_t)s.pitch[1] * (ch + 2 * B200_PAD_CY);
+    s.alloc_bytes[1] = 2 * plane_bytes;
+    CU(cudaMalloc(&s.alloc[1], s.alloc_bytes[1]));
+    CU(cudaMemsetAsync(s.alloc[1], 0, s.alloc_bytes[1], st));
+    for (int c = 1; c < 3; c++) s.plane[c] = s.alloc[1] + (c - 1) * plane_bytes + (size_t)B200_PAD_CY * s.pitch[1] + (size_t)B200_PAD_CX * bc;
+  }
+  s.has_tm = false;
+  if (bl == 1 && bc == 1) {
+    // Tensor maps over the PADDED planes (coordinate = picture coordinate + border): rows of `pitch` bytes; boxes of one MC
+    // tile's reference window (kernels_mct.cuh).  Out-of-range box parts (skew rows above the surface) are zero-filled and unused.
+    b200_encode_tiled_fn enc = encode_tiled();
+    if (!enc) return set_err(B200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)s.pitch[0], (cuuint64_t)(p.height + 2 * B200_PAD_Y)}, strides[1] = {(cuuint64_t)s.pitch[0]};
+      cuuint32_t box[2] = {MCT_LW_PITCH, MCT_LW_ROWS}, es[2] = {1, 1};
+      if (enc(&s.tm_luma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.alloc[0], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return set_err(B200_ERR_CUDA, "cuTensorMapEncodeTiled (luma) failed");
+    }
+    if (cw) {
+      cuuint64_t dims[3] = {(cuuint64_t)s.pitch[1], (cuuint64_t)(ch + 2 * B200_PAD_CY), 2};
+      cuuint64_t strides[2] = {(cuuint64_t)s.pitch[1], (cuuint64_t)s.pitch[1] * (ch + 2 * B200_PAD_CY)};
+      cuuint32_t box[3] = {MCT_CW_PITCH, MCT_CW_ROWS, 2}, es[3] = {1, 1, 1};
+      if (enc(&s.tm_chroma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s.alloc[1], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return set_err(B200_ERR_CUDA, "cuTensorMapEncodeTiled (chroma) failed");
+    } else {
+      s.tm_chroma = s.tm_luma;
+    }
+    s.has_tm = true;
   }
   return B200_OK;
+}
+
+// Replicates the edge samples of a finished picture into its border (one launch for all planes).  blockIdx.y = plane.
+//   part 1 (rows 0..h-1): the pad_x samples left of column 0 and right of column w-1;
+//   part 2 (pad_y rows above row 0 and below row h-1): the whole padded row, copied from row 0 / h-1 with the column clamped.
+template <typename P>
+__global__ void k_extend_borders(uint8_t* p0, uint8_t* p1, uint8_t* p2, int pitch0, int pitch1, int w, int h, int cw, int ch)
+{
+  const int c = blockIdx.y;
+  uint8_t* base = c == 0 ? p0 : c == 1 ? p1 : p2;
+  const int pitch = c ? pitch1 : pitch0, pw = c ? cw : w, ph = c ? ch : h;
+  const int padx = c ? B200_PAD_CX : B200_PAD_X, pady = c ? B200_PAD_CY : B200_PAD_Y;
+  constexpr int V = 16 / sizeof(P);       // samples per 16-byte store
+  const int side_chunks = padx / V;       // per side and row
+  const int n1 = ph * 2 * side_chunks;
+  const int row_chunks = (pw + 2 * padx + V - 1) / V;  // the last chunk may overshoot into the row's alignment padding (pitch is a multiple of 256)
+  const int n2 = 2 * pady * row_chunks;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int y = i / (2 * side_chunks), k = i - y * 2 * side_chunks;
+      const bool right = k >= side_chunks;
+      P* row = row_ptr<P>(base, pitch, y);
+      const P v = right ? row[pw - 1] : row[0];
+      P* dst = right ? row + pw + (k - side_chunks) * V : row - padx + k * V;
+      P tmp[V];
+#pragma unroll
+      for (int j = 0; j < V; j++) tmp[j] = v;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(tmp);
+      else
+        for (int j = 0; j < V; j++) dst[j] = v;  // chroma widths that are not a multiple of 16 bytes
+    } else {
+      const int j2 = i - n1;
+      const int r = j2 / row_chunks, k = j2 - r * row_chunks;
+      const bool below = r >= pady;
+      const int y = below ? ph + (r - pady) : r - pady;
+      const P* src = row_ptr<P>(base, pitch, below ? ph - 1 : 0);
+      P* dst = row_ptr<P>(base, pitch, y) - padx + k * V;
+      const int x0 = k * V - padx;
+      P tmp[V];
+#pragma unroll
+      for (int j = 0; j < V; j++) tmp[j] = src[min(max(x0 + j, 0), pw - 1)];
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(tmp);
+    }
+  }
+}
+
+static void launch_extend_borders(const Surface& s, cudaStream_t st)
+{
+  dim3 grid(148 * 2, s.chroma ? 3 : 1);
+  if (bytes_per_sample(s.bd_y) == 2)
+    k_extend_borders<uint16_t><<<grid, 256, 0, st>>>(s.plane[0], s.plane[1], s.plane[2], s.pitch[0], s.pitch[1], s.w, s.h, s.cw, s.ch);
+  else
+    k_extend_borders<uint8_t><<<grid, 256, 0, st>>>(s.plane[0], s.plane[1], s.plane[2], s.pitch[0], s.pitch[1], s.w, s.h, s.cw, s.ch);
 }
 
 // ---- engine --------------------------------------------------------------------------------------
@@ -196,6 +308,8 @@ struct b200_engine {
   int num_sms = 148;
   int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
   int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
+  bool mc_legacy = false;  // B200_MC_LEGACY=1: the first-generation 8-bit MC kernel (k_inter_pred8) for A/B measurements
+  int mc_ctas = 3;         // k_inter_pred_tma: persistent CTAs per SM (B200_MC_CTAS)
   bool timing = false;
   std::vector<cudaEvent_t> tev;  // timing ring: TIMING_RING pictures x 7 events
   unsigned tcount = 0;           // pictures recorded since enable / reset
@@ -205,7 +319,7 @@ struct b200_engine {
   uint64_t host_n = 0;
   // host scratch reused across pictures
   std::vector<uint32_t> part_a[4][3];  // plan_tus_validate: per part, per k_residual class
-  std::vector<uint32_t> ctb_count, tiles, list_a, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
+  std::vector<uint32_t> ctb_count, tiles, tiles_sorted, list_a, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
 };
 
 #define TIMING_RING 256
@@ -261,39 +375,9 @@ static int init_tables(int device)
     }
     CU(cudaMemcpyToSymbol(c_res, &rt, sizeof(rt)));
   }
-  // ---- packed tap tables of the 8-bit MC kernel (kernels_mc8.cuh) from the HEVC interpolation taps ----
-  {
-    static const int8_t q[4][8] = {{0, 0, 0, 1, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
-    static const int8_t ep[8][4] = {{0, 1, 0, 0},     {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
-                                    {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
-    auto pack = [](int b0, int b1, int b2, int b3) { return (uint32_t)(uint8_t)b0 | ((uint32_t)(uint8_t)b1 << 8) | ((uint32_t)(uint8_t)b2 << 16) | ((uint32_t)(uint8_t)b3 << 24); };
+  {  // packed tap tables of the 8-bit MC kernels (kernels_mc8.cuh mc8_build_tables)
     static Mc8Tables tb;
-    auto& qh = tb.qh; auto& qv = tb.qv; auto& eh = tb.eh; auto& ev = tb.ev;
-    for (int f = 0; f < 5; f++) {
-      int8_t t[8];
-      for (int i = 0; i < 8; i++) t[i] = (f == 4) ? (int8_t)(i == 3 ? 64 : 0) : q[f][i];
-      for (int j = 0; j < 4; j++)
-        for (int k = 0; k < 3; k++) {
-          int b[4];
-          for (int i = 0; i < 4; i++) { const int idx = 4 * k + i - j; b[i] = (idx >= 0 && idx < 8) ? t[idx] : 0; }
-          qh[f][j][k] = pack(b[0], b[1], b[2], b[3]);
-        }
-      if (f < 4) {
-        qv[f][0] = pack(t[0], t[1], t[2], t[3]); qv[f][1] = pack(t[4], t[5], t[6], t[7]);
-        qv[f][2] = pack(0, t[0], t[1], t[2]);    qv[f][3] = pack(t[3], t[4], t[5], t[6]); qv[f][4] = pack(t[7], 0, 0, 0);
-      }
-    }
-    for (int f = 0; f < 9; f++) {
-      int8_t t[4];
-      for (int i = 0; i < 4; i++) t[i] = (f == 8) ? (int8_t)(i == 1 ? 64 : 0) : ep[f][i];
-      for (int j = 0; j < 4; j++)
-        for (int k = 0; k < 2; k++) {
-          int b[4];
-          for (int i = 0; i < 4; i++) { const int idx = 4 * k + i - j; b[i] = (idx >= 0 && idx < 4) ? t[idx] : 0; }
-          eh[f][j][k] = pack(b[0], b[1], b[2], b[3]);
-        }
-      if (f < 8) { ev[f][0] = pack(t[0], t[1], t[2], t[3]); ev[f][1] = pack(0, t[0], t[1], t[2]); ev[f][2] = pack(t[3], 0, 0, 0); }
-    }
+    mc8_build_tables(tb);
     CU(cudaMemcpyToSymbol(c_mc8, &tb, sizeof(tb)));
   }
   if (device < 64) g_tables_ready[device] = true;
@@ -323,6 +407,8 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   if (const char* e = getenv("B200_INTRA_CTAS")) en->intra_ctas = std::max(1, std::min(4, atoi(e)));
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
+  if (const char* e = getenv("B200_MC_LEGACY")) en->mc_legacy = atoi(e) != 0;
+  if (const char* e = getenv("B200_MC_CTAS")) en->mc_ctas = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("B200_STREAMS")) en->n_ctx = std::max(1, std::min(B200_MAX_CTX, atoi(e)));
   for (int k = 0; k < B200_MAX_CTX; k++) {
     PipeCtx& cx = en->ctx[k];
@@ -334,6 +420,7 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
     CU(cudaEventCreateWithFlags(&ss.written, cudaEventDisableTiming));
     for (int k = 0; k < B200_MAX_CTX; k++) CU(cudaEventCreateWithFlags(&ss.read[k], cudaEventDisableTiming));
   }
+  CU(cudaFuncSetAttribute(k_inter_pred_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MctShared)));
   CU(cudaFuncSetAttribute(k_intra<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<uint8_t>)));
   CU(cudaFuncSetAttribute(k_intra<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<uint16_t>)));
   CU(cudaDeviceGetAttribute(&en->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -502,7 +589,24 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
   const bool run_deblock = L.run_deblock, run_sao = L.run_sao;
   if (en->timing) CU(cudaEventRecord(en->ev[1], st));
   if (n_tiles > 0) {
-    if (sizeof(P) == 1)
+    if (sizeof(P) == 1 && !en->mc_legacy) {
+      // reference windows staged by TMA: the tensor maps of the slots this picture reads travel as a kernel parameter
+      MctMaps maps;
+      memset(&maps, 0, sizeof(maps));
+      int n = 0;
+      for (int i = 0; i < B200_MAX_SLOTS; i++) {
+        maps.index_of_slot[i] = -1;
+        if (!((L.ref_mask >> i) & 1) || !refs.plane[i][0] || !en->slot[i].has_tm) continue;
+        if (n == MCT_MAX_REFS) return set_err(B200_ERR_UNSUPPORTED, "picture references more than %d DPB slots", MCT_MAX_REFS);
+        maps.luma[n] = en->slot[i].tm_luma;
+        maps.chroma[n] = en->slot[i].tm_chroma;
+        maps.index_of_slot[i] = (int8_t)n++;
+        maps.valid_slots |= 1u << i;
+      }
+      const int n_batches = n_tiles / MCT_TILES;
+      k_inter_pred_tma<<<std::min(n_batches, en->num_sms * en->mc_ctas), MCT_THREADS, sizeof(MctShared), st>>>(
+          dp, maps, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]), (const uint32_t*)(dbase + off[12]), n_batches);
+    } else if (sizeof(P) == 1)
       k_inter_pred8<<<std::min((n_tiles + MC8_UNITS_PER_CTA - 1) / MC8_UNITS_PER_CTA, en->num_sms * 5), MC8_WARPS * 32, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
                                                          (const uint32_t*)(dbase + off[12]), n_tiles);
     else
@@ -641,7 +745,7 @@ static int plan_begin(b200_engine* en, const b200_picture* pic, PicLayout* L, si
   for (int i : k_raw_sections) { L->off[i] = total; total += align_up(sz[i], 256); }
   L->raw_total = total;
   // upper bound of the lists: every TU in one list, one task per TU; MC units cannot outnumber 4x8 blocks unless PUs overlap
-  L->unit_cap = (size_t)w4 * h4 / 2 + 64;
+  L->unit_cap = (size_t)w4 * h4 / 2 + 64 + 8 * MCT_TILES;  // + the padding of the class-pure batches
   *cap_total = total + 3 * align_up(sizeof(uint32_t) * ((size_t)pic->n_tu + 1), 256) + align_up(sizeof(uint32_t) * L->unit_cap, 256) + 256;
   return B200_OK;
 }
@@ -666,10 +770,28 @@ static int plan_pus(b200_engine* en, const b200_picture* pic, PicLayout* L)
     if (wide) {  // 16-bit path: <= 16x16 tiles, one warp each (kernels_mc.cuh)
       for (int ty = 0; ty * MC_TILE < pu.h; ty++)
         for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
-    } else {     // 8-bit path: <= 8x16 units, one quarter-warp each (kernels_mc8.cuh)
+    } else if (en->mc_legacy) {  // first-generation 8-bit path: <= 8x16 units, one quarter-warp each (kernels_mc8.cuh)
       for (int uy = 0; uy * MC8_UH < pu.h; uy++)
         for (int ux = 0; ux * MC8_UW < pu.w; ux++) tiles.push_back(MC8_UNIT(i, ux, uy));
+    } else {     // 8-bit path: <= 16x16 tiles with their class (kernels_mct.cuh), sorted into class-pure batches below
+      const int bi = ((pu.flags & B200_PU_PRED_L0) && (pu.flags & B200_PU_PRED_L1)) ? MCT_CLASS_BI : 0;
+      for (int ty = 0; ty * 16 < pu.h; ty++)
+        for (int tx = 0; tx * 16 < pu.w; tx++) {
+          const int tw = std::min(16, pu.w - 16 * tx), th = std::min(16, pu.h - 16 * ty);
+          tiles.push_back(MCT_TILE_WORD(i, tx, ty, bi | (tw > 8 ? MCT_CLASS_WIDE : 0) | (th > 8 ? MCT_CLASS_TALL : 0)));
+        }
     }
+  }
+  if (!wide && !en->mc_legacy && !tiles.empty()) {
+    // counting sort by class, every class padded to whole batches of MCT_TILES tiles (a batch is class-pure; padding = MCT_INVALID)
+    std::vector<uint32_t>& sorted = en->tiles_sorted;
+    size_t count[8] = {}, start[8];
+    for (uint32_t t : tiles) count[(t >> 24) & 7]++;
+    size_t total = 0;
+    for (int c = 0; c < 8; c++) { start[c] = total; total += (count[c] + MCT_TILES - 1) / MCT_TILES * MCT_TILES; }
+    sorted.assign(total, MCT_INVALID);
+    for (uint32_t t : tiles) sorted[start[(t >> 24) & 7]++] = t;
+    tiles.swap(sorted);
   }
   if (tiles.size() > L->unit_cap) return set_err(B200_ERR_INVALID, "PUs overlap (more MC units than the picture has 4x8 blocks)");
   L->n_tiles = (int)tiles.size();
@@ -997,6 +1119,9 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
   if (p.bit_depth_luma > 8) rc = launch_picture<uint16_t>(en, cx, L, dp, refs, dbase);
   else rc = launch_picture<uint8_t>(en, cx, L, dp, refs, dbase);
   if (rc) return rc;
+  launch_extend_borders(dst, st);  // the finished picture may be referenced: replicate its edges into the border
+  en->launches++;
+  CU(cudaGetLastError());
   if (en->timing) { CU(cudaEventRecord(en->ev[6], st)); en->tcount++; }
   rc = order_after(en, k, L);
   if (rc) return rc;
@@ -1111,6 +1236,8 @@ extern "C" int b200_engine_fill_slot(b200_engine* en, int slot, const b200_pic_p
     else k_fill<uint8_t><<<grid, 256, 0, st>>>(s.plane[c], s.pitch[c], w, h, c ? vc : vy);
     en->launches++;
   }
+  launch_extend_borders(s, st);
+  en->launches++;
   CU(cudaGetLastError());
   CU(cudaEventRecord(en->ssync[slot].written, st));
   en->ssync[slot].writer = 0;
@@ -1135,6 +1262,9 @@ extern "C" int b200_engine_upload_slot(b200_engine* en, int slot, const b200_pic
     if (!planes[c]) return set_err(B200_ERR_INVALID, "plane %d missing", c);
     CU(cudaMemcpy2DAsync(s.plane[c], s.pitch[c], planes[c], strides[c], (size_t)w * bps, h, cudaMemcpyHostToDevice, st));
   }
+  launch_extend_borders(s, st);
+  en->launches++;
+  CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));  // the source may be pageable / reused by the caller
   s.valid = true;
   return B200_OK;

@@ -1,0 +1,547 @@
+// kernels_mct.cuh — 8-bit inter prediction, tiled and TMA-staged (the roofline-graded kernel, second generation).
+//
+// Replaces mc_luma / mc_chroma (motion.cc:48-282), every put_hevc_qpel/epel table entry (fallback-motion.cc:262-636) and the
+// four put_*_pred functions (fallback-motion.cc:33-256) for one picture's worth of PUs in ONE launch.
+//
+// Work split.  The host cuts every PU into TILES of at most 16x16 luma samples (+ the co-located 8x8 Cb/Cr samples) and sorts
+// them into 8 classes (wide: more than 8 columns | bi-predicted | tall: more than 8 rows); a BATCH is 8 tiles of one class.
+// Persistent CTAs of 128 threads take batches; inside a batch all threads run over FLAT task lists, so lanes stay busy for
+// every PU size and nothing in a task body depends on the PU shape except two uniform loop bounds:
+//   stage   16 producer threads (one per tile and list) decode the PU records and issue one 2-D TMA box (48 bytes x 26 rows,
+//           luma) and one 3-D TMA box (32 bytes x 14 rows x {Cb, Cr}) per used reference list into shared memory, completion
+//           on an mbarrier.  TMA box origins must be 16-byte aligned in the innermost dimension (measured: an unaligned origin
+//           raises "illegal instruction", tools/tma_probe2.cu), so the box starts at the 16-byte boundary left of the window and
+//           pass 1 picks the window up at its byte offset.  Reference surfaces carry a replicated border (engine.cu), so
+//           there is no coordinate clamping here: a window further out than the border is moved to the border's rim.
+//           The next batch's boxes are issued as soon as pass 1 has consumed the current windows (they land during pass 2).
+//   pass 1  horizontal filter on bytes, as the reference orders it (fallback-motion.cc:492-560): a task = 2 window rows x 8
+//           columns of one tile and list: 4 aligned words + funnel shifts give 16 source bytes per row, output j is
+//           dp4a(b0,T[j][0]) + dp4a(b1,T[j][1]) + dp4a(b2,T[j][2]) with the 8 taps pre-shifted by j bytes (11 dp4a per 4
+//           outputs).  The two rows' results (|v| < 2^15: no shift at 8 bit) are interleaved into VERTICAL int16 pairs and
+//           stored as one "pair row" with two 16-byte stores.
+//   pass 2  vertical filter on the pair rows with dp2a (4 per even output row, 5 per odd one: taps pre-packed for both
+//           parities), >> 6 with the reference's int16 wrap (one bit-field extract), weighting (all four modes through one
+//           branch-free multiply-add-shift-offset form), saturation, and 32 outputs per lane leave as whole row segments:
+//           16 columns x 2 rows (one 128-bit store per row) in the wide classes, 8 columns x 4 rows (64-bit stores) otherwise.
+// Integer phases use identity taps, so there is one code path.  Missing references predict mid-grey (motion.cc:362).
+//
+// The task bodies are __host__ __device__ so that tests/mct_emul.cu can run the very same code on the CPU against the oracle
+// (TMA replaced by a window copy); only the staging / synchronisation below is device-only.
+#pragma once
+#include "dev_common.cuh"
+#include "kernels_mc8.cuh"  // Mc8Tables, Mc8Weight, mc8_weight
+
+#define MCT_HD __host__ __device__ __forceinline__
+
+#define MCT_TILES 8                      // tiles per batch
+#define MCT_THREADS 128
+#define MCT_NTL (2 * MCT_TILES)          // tile-list slots per batch
+#define MCT_LW_PITCH 48                  // luma window: bytes per row (16-byte aligned origin + up to 15 + 23)
+#define MCT_LW_ROWS 26                   // 23 rows + up to 3 rows of bank skew
+#define MCT_LW_BYTES (MCT_LW_PITCH * MCT_LW_ROWS)  // 1248 = the TMA box
+#define MCT_LW_SLOT 1280                 // 128-byte aligned slot
+#define MCT_CW_PITCH 32                  // chroma window: bytes per row (up to 15 + 11)
+#define MCT_CW_ROWS 14                   // 11 rows + skew
+#define MCT_CW_PLANE (MCT_CW_PITCH * MCT_CW_ROWS)  // 448
+#define MCT_CW_BYTES (2 * MCT_CW_PLANE)  // 896 = the TMA box (Cb, Cr)
+#define MCT_CW_SLOT 896
+#define MCT_LI_PITCH 20                  // luma intermediate: words per pair row (16 used; 20: conflict-free 16-byte accesses)
+#define MCT_LI_WORDS (12 * MCT_LI_PITCH) // 12 pair rows
+#define MCT_CI_PITCH 12                  // chroma intermediate: words per pair row (8 used)
+#define MCT_CI_PLANE (6 * MCT_CI_PITCH)  // 6 pair rows
+#define MCT_CI_WORDS (2 * MCT_CI_PLANE)
+
+// tile word: bits 0-19 PU index, 20-21 x offset / 16, 22-23 y offset / 16, 24-26 class; 0xFFFFFFFF = padding
+#define MCT_CLASS_WIDE 1
+#define MCT_CLASS_BI 2
+#define MCT_CLASS_TALL 4
+#define MCT_TILE_WORD(pu, tx, ty, cls) ((uint32_t)(pu) | ((uint32_t)(tx) << 20) | ((uint32_t)(ty) << 22) | ((uint32_t)(cls) << 24))
+#define MCT_INVALID 0xFFFFFFFFu
+
+struct MctTile {
+  int dst_y, dst_c;       // byte offsets of the tile's first luma / chroma sample in the destination planes
+  uint8_t tw, th, nl, valid;
+  uint8_t xo[2], hidx[2], yf[2], sh6[2];      // per list slot: window byte offset, pass-1 tap table index, vertical phase, final shift
+  uint8_t cxo[2], chidx[2], cyf[2], csh6[2];  // chroma
+  uint8_t missing[2], pad[2];
+  Mc8Weight w[3];
+};
+
+struct MctShared {
+  alignas(128) uint8_t lw[MCT_NTL][MCT_LW_SLOT];
+  alignas(128) uint8_t cw[MCT_NTL][MCT_CW_SLOT];
+  alignas(16) uint32_t li[MCT_NTL][MCT_LI_WORDS];
+  alignas(16) uint32_t ci[MCT_NTL][MCT_CI_WORDS];
+  MctTile info[2][MCT_TILES];
+  Mc8Tables tab;
+  alignas(8) unsigned long long bar;
+};
+
+// ---- portable forms of the packed-integer instructions (host emulation) ----
+MCT_HD int mct_dp4a(uint32_t a, uint32_t b, int c)  // unsigned bytes of a x signed bytes of b
+{
+#ifdef __CUDA_ARCH__
+  return dp4a_us(a, b, c);
+#else
+  for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 0xff) * (int)(int8_t)((b >> (8 * i)) & 0xff);
+  return c;
+#endif
+}
+MCT_HD int mct_dp2a_lo(uint32_t a, uint32_t b, int c)  // int16 halves of a x signed bytes 0,1 of b
+{
+#ifdef __CUDA_ARCH__
+  return dp2a_lo_ss(a, b, c);
+#else
+  return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)(b & 0xff) + (int)(int16_t)(a >> 16) * (int)(int8_t)((b >> 8) & 0xff);
+#endif
+}
+MCT_HD int mct_dp2a_hi(uint32_t a, uint32_t b, int c)  // int16 halves of a x signed bytes 2,3 of b
+{
+#ifdef __CUDA_ARCH__
+  return dp2a_hi_ss(a, b, c);
+#else
+  return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)((b >> 16) & 0xff) + (int)(int16_t)(a >> 16) * (int)(int8_t)((b >> 24) & 0xff);
+#endif
+}
+MCT_HD uint32_t mct_funnel(uint32_t lo, uint32_t hi, int sh)  // bytes of hi:lo starting at bit sh (sh in 0, 8, 16, 24)
+{
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+MCT_HD uint32_t mct_pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+MCT_HD int mct_wrap16(int v, int shift)  // (v >> shift) as int16 with wrap-around
+{
+#ifdef __CUDA_ARCH__
+  return shr_wrap16(v, shift);
+#else
+  return (int)(int16_t)(uint16_t)((uint32_t)v >> shift);
+#endif
+}
+MCT_HD int mct_clip3(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
+MCT_HD int mct_sat_u8(int v)
+{
+#ifdef __CUDA_ARCH__
+  return sat_u8(v);
+#else
+  return v < 0 ? 0 : v > 255 ? 255 : v;
+#endif
+}
+
+// ---- task-space geometry of a batch class ----
+struct MctGeom {
+  int nl, ntl;          // list slots per tile (1 | 2), tile-list items per batch
+  int nco;              // luma column octets per tile (1 | 2)
+  int nrp, nrpc;        // pair rows of the luma / chroma intermediate that pass 1 produces (8 | 12, 4 | 6)
+  int n1l, n1c;         // pass-1 task counts (luma, chroma)
+  int n2l, n2c;         // pass-2 task counts
+  bool wide, tall;
+};
+MCT_HD MctGeom mct_geom(int cls)
+{
+  MctGeom g;
+  g.wide = cls & MCT_CLASS_WIDE;
+  g.tall = cls & MCT_CLASS_TALL;
+  g.nl = (cls & MCT_CLASS_BI) ? 2 : 1;
+  g.ntl = MCT_TILES * g.nl;
+  g.nco = g.wide ? 2 : 1;
+  g.nrp = g.tall ? 12 : 8;
+  g.nrpc = g.tall ? 6 : 4;
+  g.n1l = g.nrp * g.ntl * g.nco;
+  g.n1c = g.nrpc * g.ntl * 2;
+  // pass 2: wide 16 cols x 2 rows per task, narrow 8 cols x 4 rows; chroma 8 cols x 4 rows per plane
+  g.n2l = MCT_TILES * (g.wide ? (g.tall ? 8 : 4) : (g.tall ? 4 : 2));
+  g.n2c = MCT_TILES * 2 * (g.tall ? 2 : 1);
+  return g;
+}
+
+// ---- pass 1, luma: task -> (pair row rp, tile-list item, column octet) ----
+MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const uint8_t (*lw)[MCT_LW_SLOT], uint32_t (*li)[MCT_LI_WORDS], const Mc8Tables& tab)
+{
+  const int co = g.nco == 2 ? (t & 1) : 0;
+  const int u = g.nco == 2 ? (t >> 1) : t;
+  const int tli = u % g.ntl, rp = u / g.ntl;
+  const int tile = g.nl == 2 ? (tli >> 1) : tli, s = g.nl == 2 ? (tli & 1) : 0;
+  const MctTile& ti = info[tile];
+  if (!ti.valid || ti.missing[s] || 2 * rp >= ti.th + 7 || 8 * co >= ti.tw) return;
+  const int tl = tile * 2 + s;
+  const uint32_t* tp = &tab.qh[ti.hidx[s]][0][0];
+  uint32_t T[4][3];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) T[j][k] = tp[j * 3 + k];
+  const int b = ti.xo[s] + 8 * co, sh = (b & 3) * 8;
+  const uint8_t* base = lw[tl] + (2 * rp + (tl & 3)) * MCT_LW_PITCH + (b & ~3);
+  int o[2][8];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const uint32_t* wp_ = reinterpret_cast<const uint32_t*>(base + i * MCT_LW_PITCH);
+    const uint32_t w0 = wp_[0], w1 = wp_[1], w2 = wp_[2], w3 = wp_[3], w4 = wp_[4];
+    uint32_t sb[4];
+    sb[0] = mct_funnel(w0, w1, sh); sb[1] = mct_funnel(w1, w2, sh); sb[2] = mct_funnel(w2, w3, sh); sb[3] = mct_funnel(w3, w4, sh);
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int v = mct_dp4a(sb[q], T[j][0], 0);
+        v = mct_dp4a(sb[q + 1], T[j][1], v);
+        if (j > 0) v = mct_dp4a(sb[q + 2], T[j][2], v);
+        o[i][4 * q + j] = v;
+      }
+  }
+  uint32_t* dst = li[tl] + rp * MCT_LI_PITCH + 8 * co;
+  uint4 a, c;
+  a.x = mct_pack16(o[0][0], o[1][0]); a.y = mct_pack16(o[0][1], o[1][1]); a.z = mct_pack16(o[0][2], o[1][2]); a.w = mct_pack16(o[0][3], o[1][3]);
+  c.x = mct_pack16(o[0][4], o[1][4]); c.y = mct_pack16(o[0][5], o[1][5]); c.z = mct_pack16(o[0][6], o[1][6]); c.w = mct_pack16(o[0][7], o[1][7]);
+  *reinterpret_cast<uint4*>(dst) = a;
+  *reinterpret_cast<uint4*>(dst + 4) = c;
+}
+
+// ---- pass 1, chroma: task -> (pair row, tile-list item, plane); 8 columns x 2 rows ----
+MCT_HD void mct_pass1_chroma(int t, const MctGeom& g, const MctTile* info, const uint8_t (*cw)[MCT_CW_SLOT], uint32_t (*ci)[MCT_CI_WORDS], const Mc8Tables& tab)
+{
+  const int pl = t & 1, u = t >> 1;
+  const int tli = u % g.ntl, rp = u / g.ntl;
+  const int tile = g.nl == 2 ? (tli >> 1) : tli, s = g.nl == 2 ? (tli & 1) : 0;
+  const MctTile& ti = info[tile];
+  if (!ti.valid || ti.missing[s] || 2 * rp >= (ti.th >> 1) + 3) return;
+  const int tl = tile * 2 + s;
+  const uint32_t* tp = &tab.eh[ti.chidx[s]][0][0];
+  uint32_t T[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int k = 0; k < 2; k++) T[j][k] = tp[j * 2 + k];
+  const int b = ti.cxo[s], sh = (b & 3) * 8;
+  const uint8_t* base = cw[tl] + pl * MCT_CW_PLANE + (2 * rp + (tl & 3)) * MCT_CW_PITCH + (b & ~3);
+  int o[2][8];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const uint32_t* wp_ = reinterpret_cast<const uint32_t*>(base + i * MCT_CW_PITCH);
+    const uint32_t w0 = wp_[0], w1 = wp_[1], w2 = wp_[2], w3 = wp_[3];
+    uint32_t sb[3];
+    sb[0] = mct_funnel(w0, w1, sh); sb[1] = mct_funnel(w1, w2, sh); sb[2] = mct_funnel(w2, w3, sh);
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int v = mct_dp4a(sb[q], T[j][0], 0);
+        if (j > 0) v = mct_dp4a(sb[q + 1], T[j][1], v);
+        o[i][4 * q + j] = v;
+      }
+  }
+  uint32_t* dst = ci[tl] + pl * MCT_CI_PLANE + rp * MCT_CI_PITCH;
+  uint4 a, c;
+  a.x = mct_pack16(o[0][0], o[1][0]); a.y = mct_pack16(o[0][1], o[1][1]); a.z = mct_pack16(o[0][2], o[1][2]); a.w = mct_pack16(o[0][3], o[1][3]);
+  c.x = mct_pack16(o[0][4], o[1][4]); c.y = mct_pack16(o[0][5], o[1][5]); c.z = mct_pack16(o[0][6], o[1][6]); c.w = mct_pack16(o[0][7], o[1][7]);
+  *reinterpret_cast<uint4*>(dst) = a;
+  *reinterpret_cast<uint4*>(dst + 4) = c;
+}
+
+// Vertical 8-tap filter of COLS columns x ROWS rows (ROWS even, first row even) from pair rows at `src` (pitch in words):
+// out[i][c], already shifted / wrapped to the reference's int16 intermediate.
+template <int COLS, int ROWS, int PITCH>
+MCT_HD void mct_vfilter8(const uint32_t* src, const uint32_t (&tv)[5], int sh6, int (&out)[ROWS][COLS])
+{
+  constexpr int NP = ROWS / 2 + 4;
+#pragma unroll
+  for (int c4 = 0; c4 < COLS / 4; c4++) {
+    uint32_t V[NP][4];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const uint4 q = *reinterpret_cast<const uint4*>(src + p * PITCH + 4 * c4);
+      V[p][0] = q.x; V[p][1] = q.y; V[p][2] = q.z; V[p][3] = q.w;
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS / 2; u++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        int e = mct_dp2a_lo(V[u][c], tv[0], 0);
+        e = mct_dp2a_hi(V[u + 1][c], tv[0], e);
+        e = mct_dp2a_lo(V[u + 2][c], tv[1], e);
+        e = mct_dp2a_hi(V[u + 3][c], tv[1], e);
+        int o = mct_dp2a_lo(V[u][c], tv[2], 0);
+        o = mct_dp2a_hi(V[u + 1][c], tv[2], o);
+        o = mct_dp2a_lo(V[u + 2][c], tv[3], o);
+        o = mct_dp2a_hi(V[u + 3][c], tv[3], o);
+        o = mct_dp2a_lo(V[u + 4][c], tv[4], o);
+        out[2 * u][4 * c4 + c] = mct_wrap16(e, sh6);
+        out[2 * u + 1][4 * c4 + c] = mct_wrap16(o, sh6);
+      }
+  }
+}
+
+// Vertical 4-tap filter (chroma): 8 columns x 4 rows from pair rows.
+template <int PITCH>
+MCT_HD void mct_vfilter4(const uint32_t* src, const uint32_t (&tv)[3], int sh6, int (&out)[4][8])
+{
+#pragma unroll
+  for (int c4 = 0; c4 < 2; c4++) {
+    uint32_t V[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const uint4 q = *reinterpret_cast<const uint4*>(src + p * PITCH + 4 * c4);
+      V[p][0] = q.x; V[p][1] = q.y; V[p][2] = q.z; V[p][3] = q.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        int e = mct_dp2a_lo(V[u][c], tv[0], 0);
+        e = mct_dp2a_hi(V[u + 1][c], tv[0], e);
+        int o = mct_dp2a_lo(V[u][c], tv[1], 0);
+        o = mct_dp2a_hi(V[u + 1][c], tv[1], o);
+        o = mct_dp2a_lo(V[u + 2][c], tv[2], o);
+        out[2 * u][4 * c4 + c] = mct_wrap16(e, sh6);
+        out[2 * u + 1][4 * c4 + c] = mct_wrap16(o, sh6);
+      }
+  }
+}
+
+MCT_HD uint32_t mct_weight4(const int* a, const int* b, const Mc8Weight& w)
+{
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8(((a[k] * w.w0 + b[k] * w.w1 + w.rnd) >> w.shift) + w.off) << (8 * k);
+  return r;
+}
+
+// Row segment store: nbytes (multiple of 4 for luma, of 2 for chroma) of `words` to dst, widest aligned form available.
+MCT_HD void mct_store_row(uint8_t* dst, const uint32_t* words, int full_bytes, int nbytes)
+{
+  if (nbytes == full_bytes && full_bytes == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+  } else if (nbytes >= 8 && (nbytes & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    for (int k = 0; k < nbytes / 8; k++) *reinterpret_cast<uint2*>(dst + 8 * k) = make_uint2(words[2 * k], words[2 * k + 1]);
+  } else if ((nbytes & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+    for (int k = 0; k < nbytes / 4; k++) *reinterpret_cast<uint32_t*>(dst + 4 * k) = words[k];
+  } else {
+    for (int k = 0; k < nbytes / 2; k++) *reinterpret_cast<uint16_t*>(dst + 2 * k) = (uint16_t)(words[k >> 1] >> (16 * (k & 1)));
+  }
+}
+
+// ---- pass 2, luma: task -> (tile, row group); COLS x ROWS = 32 outputs ----
+template <int COLS, int ROWS>
+MCT_HD void mct_pass2_luma(int t, int groups, const MctTile* info, const uint32_t (*li)[MCT_LI_WORDS], const Mc8Tables& tab, uint8_t* plane, int pitch)
+{
+  const int tile = t / groups, rg = t % groups;
+  const MctTile& ti = info[tile];
+  const int y0 = ROWS * rg;
+  if (!ti.valid || y0 >= ti.th) return;
+  int v[2][ROWS][COLS];
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    if (s < ti.nl && !ti.missing[s]) {
+      uint32_t tv[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) tv[k] = tab.qv[ti.yf[s]][k];
+      mct_vfilter8<COLS, ROWS, MCT_LI_PITCH>(li[tile * 2 + s] + (y0 >> 1) * MCT_LI_PITCH, tv, ti.sh6[s], v[s]);
+    } else {
+      const int fill = s < ti.nl ? (1 << 13) : 0;  // missing reference: mid-grey intermediate (motion.cc:362)
+#pragma unroll
+      for (int i = 0; i < ROWS; i++)
+#pragma unroll
+        for (int c = 0; c < COLS; c++) v[s][i][c] = fill;
+    }
+  }
+  const Mc8Weight w = ti.w[0];
+  const int nbytes = ti.tw < COLS ? ti.tw : COLS;
+#pragma unroll
+  for (int i = 0; i < ROWS; i++) {
+    if (y0 + i >= ti.th) break;
+    uint32_t words[COLS / 4];
+#pragma unroll
+    for (int k = 0; k < COLS / 4; k++) words[k] = mct_weight4(&v[0][i][4 * k], &v[1][i][4 * k], w);
+    mct_store_row(plane + ti.dst_y + (size_t)(y0 + i) * pitch, words, COLS, nbytes);
+  }
+}
+
+// ---- pass 2, chroma: task -> (tile, plane, row group of 4) ----
+MCT_HD void mct_pass2_chroma(int t, int groups, const MctTile* info, const uint32_t (*ci)[MCT_CI_WORDS], const Mc8Tables& tab, uint8_t* cb, uint8_t* cr,
+                             int pitch)
+{
+  const int pl = t & 1, u = t >> 1;
+  const int tile = u / groups, rg = u % groups;
+  const MctTile& ti = info[tile];
+  const int y0 = 4 * rg, ch = ti.th >> 1, cwd = ti.tw >> 1;
+  if (!ti.valid || y0 >= ch) return;
+  int v[2][4][8];
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    if (s < ti.nl && !ti.missing[s]) {
+      uint32_t tv[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) tv[k] = tab.ev[ti.cyf[s]][k];
+      mct_vfilter4<MCT_CI_PITCH>(ci[tile * 2 + s] + pl * MCT_CI_PLANE + (y0 >> 1) * MCT_CI_PITCH, tv, ti.csh6[s], v[s]);
+    } else {
+      const int fill = s < ti.nl ? (1 << 13) : 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[s][i][c] = fill;
+    }
+  }
+  const Mc8Weight w = ti.w[1 + pl];
+  uint8_t* plane = pl ? cr : cb;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (y0 + i >= ch) break;
+    uint32_t words[2];
+    words[0] = mct_weight4(&v[0][i][0], &v[1][i][0], w);
+    words[1] = mct_weight4(&v[0][i][4], &v[1][i][4], w);
+    mct_store_row(plane + ti.dst_c + (size_t)(y0 + i) * pitch, words, 8, cwd);
+  }
+}
+
+// ---- tile decode (producer side): fills the tile's info and returns the window geometry of list slot s ----
+struct MctBox {
+  int active;      // this (tile, slot) fetches windows
+  int slot;        // DPB slot of the reference
+  int lx, ly;      // luma box origin in picture coordinates (16-byte aligned x)
+  int cx, cy;      // chroma box origin
+};
+MCT_HD MctBox mct_decode_tile(uint32_t word, int s, const b200_pu* pus, const b200_weight_entry* wts, uint32_t valid_slots, const DevPic& pic, MctTile* ti)
+{
+  MctBox bx;
+  bx.active = 0; bx.slot = -1; bx.lx = bx.ly = bx.cx = bx.cy = 0;
+  if (word == MCT_INVALID) {
+    if (s == 0) ti->valid = 0;
+    return bx;
+  }
+  const b200_pu pu = pus[word & 0xFFFFF];
+  const int tx = (word >> 20) & 3, ty = (word >> 22) & 3;
+  const int x0 = pu.x + 16 * tx, y0 = pu.y + 16 * ty;
+  const int tw = pu.w - 16 * tx < 16 ? pu.w - 16 * tx : 16, th = pu.h - 16 * ty < 16 ? pu.h - 16 * ty : 16;
+  const bool use0 = pu.flags & B200_PU_PRED_L0, use1 = pu.flags & B200_PU_PRED_L1;
+  const int nl = (use0 && use1) ? 2 : 1;
+  const int first = use0 ? 0 : 1;
+  if (s == 0) {
+    ti->valid = (use0 || use1) ? 1 : 0;
+    ti->tw = (uint8_t)tw; ti->th = (uint8_t)th; ti->nl = (uint8_t)nl;
+    ti->dst_y = y0 * pic.pitch[0] + x0;
+    ti->dst_c = (y0 >> 1) * pic.pitch[1] + (x0 >> 1);
+    const bool wgt = pu.flags & B200_PU_WEIGHTED;
+    const b200_weight_entry* we = wts + (wgt ? pu.wt_idx : 0);
+#pragma unroll
+    for (int c = 0; c < 3; c++) ti->w[c] = mc8_weight(nl == 2, wgt, first, we, c);
+  }
+  if (s >= nl || !(use0 || use1)) return bx;
+  const int l = s == 0 ? first : 1;
+  const int slot = pu.ref_slot[l];
+  const bool missing = slot < 0 || !((valid_slots >> slot) & 1);
+  const int mvx = pu.mv[l][0], mvy = pu.mv[l][1];
+  const int xf = mvx & 3, yf = mvy & 3, cxf = mvx & 7, cyf = mvy & 7;
+  ti->missing[s] = missing;
+  ti->hidx[s] = (uint8_t)((xf == 0 && yf == 0) ? 4 : xf);  // full-sample position: gain 64 (<< 6) in pass 1, identity in pass 2
+  ti->yf[s] = (uint8_t)yf;
+  ti->sh6[s] = (uint8_t)((xf && yf) ? 6 : 0);
+  ti->chidx[s] = (uint8_t)((cxf == 0 && cyf == 0) ? 8 : cxf);
+  ti->cyf[s] = (uint8_t)cyf;
+  ti->csh6[s] = (uint8_t)((cxf && cyf) ? 6 : 0);
+  // window origin = first sample the 8-tap (4-tap) filters touch, moved to the border's rim when further out (see engine.cu)
+  const int wx = mct_clip3(-B200_PAD_X, pic.w + B200_PAD_X - 23, x0 + (mvx >> 2) - 3);
+  const int wy = mct_clip3(-B200_PAD_Y, pic.h + B200_PAD_Y - 23, y0 + (mvy >> 2) - 3);
+  const int cwx = mct_clip3(-B200_PAD_CX, pic.cw + B200_PAD_CX - 11, (x0 >> 1) + (mvx >> 3) - 1);
+  const int cwy = mct_clip3(-B200_PAD_CY, pic.ch + B200_PAD_CY - 11, (y0 >> 1) + (mvy >> 3) - 1);
+  ti->xo[s] = (uint8_t)(wx & 15);
+  ti->cxo[s] = (uint8_t)(cwx & 15);
+  bx.active = !missing;
+  bx.slot = slot;
+  bx.lx = wx & ~15; bx.ly = wy;
+  bx.cx = cwx & ~15; bx.cy = cwy;
+  return bx;
+}
+
+#ifdef __CUDACC__
+// ---- device-only part: tensor maps, mbarrier, the kernel ----
+#include <cuda.h>
+
+#define MCT_MAX_REFS 16
+struct MctMaps {
+  CUtensorMap luma[MCT_MAX_REFS];    // 2-D: {pitch bytes, padded rows}, box 48 x 26
+  CUtensorMap chroma[MCT_MAX_REFS];  // 3-D: {pitch bytes, padded rows, 2 planes}, box 32 x 14 x 2
+  int8_t index_of_slot[B200_MAX_SLOTS];
+  uint32_t valid_slots;
+};
+
+__device__ __forceinline__ uint32_t mct_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(MCT_THREADS) k_inter_pred_tma(DevPic pic, const __grid_constant__ MctMaps maps, const b200_pu* __restrict__ pus,
+                                                                const b200_weight_entry* __restrict__ wts, const uint32_t* __restrict__ tiles,
+                                                                int n_batches)
+{
+  extern __shared__ __align__(128) uint8_t mct_smem_raw[];
+  MctShared& sm = *reinterpret_cast<MctShared*>(mct_smem_raw);
+  const int tid = threadIdx.x;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_mc8);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.tab);
+    for (int i = tid; i < (int)(sizeof(Mc8Tables) / 4); i += MCT_THREADS) dst[i] = src[i];
+  }
+  const uint32_t bar = mct_smem(&sm.bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(MCT_NTL));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool has_chroma = pic.chroma != 0;
+
+  auto produce = [&](int batch, MctTile* info) {  // threads 0 .. MCT_NTL-1: one (tile, list slot) each
+    const int tile = tid >> 1, s = tid & 1;
+    const MctBox bx = mct_decode_tile(tiles[batch * MCT_TILES + tile], s, pus, wts, maps.valid_slots, pic, &info[tile]);
+    const int mi = bx.active ? maps.index_of_slot[bx.slot] : -1;
+    if (mi >= 0) {
+      const int tl = tid, skew = tl & 3;
+      const uint32_t bytes = MCT_LW_BYTES + (has_chroma ? MCT_CW_BYTES : 0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the windows were read through the generic proxy in pass 1
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(mct_smem(sm.lw[tl])),
+                   "l"(&maps.luma[mi]), "r"(bx.lx + B200_PAD_X), "r"(bx.ly + B200_PAD_Y - skew), "r"(bar)
+                   : "memory");
+      if (has_chroma)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                         mct_smem(sm.cw[tl])),
+                     "l"(&maps.chroma[mi]), "r"(bx.cx + B200_PAD_CX), "r"(bx.cy + B200_PAD_CY - skew), "r"(0), "r"(bar)
+                     : "memory");
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+  };
+
+  int batch = blockIdx.x;
+  if (batch < n_batches && tid < MCT_NTL) produce(batch, sm.info[0]);
+  for (int it = 0; batch < n_batches; batch += gridDim.x, it++) {
+    {  // wait for this batch's windows (and the producers' tile info)
+      const uint32_t parity = it & 1;
+      uint32_t done;
+      do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      } while (!done);
+    }
+    const MctTile* info = sm.info[it & 1];
+    const uint32_t w0 = tiles[batch * MCT_TILES];
+    const MctGeom g = mct_geom((w0 >> 24) & 7);  // a batch is class-pure and its first tile is never padding
+    for (int t = tid; t < g.n1l; t += MCT_THREADS) mct_pass1_luma(t, g, info, sm.lw, sm.li, sm.tab);
+    if (has_chroma)
+      for (int t = tid; t < g.n1c; t += MCT_THREADS) mct_pass1_chroma(t, g, info, sm.cw, sm.ci, sm.tab);
+    __syncthreads();
+    const int next = batch + gridDim.x;
+    if (next < n_batches && tid < MCT_NTL) produce(next, sm.info[(it + 1) & 1]);  // the windows are free: fetch ahead during pass 2
+    if (g.wide) {
+      const int groups = g.tall ? 8 : 4;
+      for (int t = tid; t < g.n2l; t += MCT_THREADS) mct_pass2_luma<16, 2>(t, groups, info, sm.li, sm.tab, pic.cur[0], pic.pitch[0]);
+    } else {
+      const int groups = g.tall ? 4 : 2;
+      for (int t = tid; t < g.n2l; t += MCT_THREADS) mct_pass2_luma<8, 4>(t, groups, info, sm.li, sm.tab, pic.cur[0], pic.pitch[0]);
+    }
+    if (has_chroma) {
+      const int groups = g.tall ? 2 : 1;
+      for (int t = tid; t < g.n2c; t += MCT_THREADS) mct_pass2_chroma(t, groups, info, sm.ci, sm.tab, pic.cur[1], pic.cur[2], pic.pitch[1]);
+    }
+    __syncthreads();
+  }
+}
+#endif  // __CUDACC__

@@ -34,16 +34,28 @@ def check_picture(lib, pic):
     flags = tus["flags"].astype(int)
     intra = (flags & capi.TU_INTRA) != 0
     work = ((flags & (capi.TU_CBF | capi.TU_PCM)) != 0) & ~intra
-    # ---- MC units: every predicted PU is tiled exactly once by <= 8x16 units ----
+    # ---- MC tiles: every predicted PU is cut exactly once into <= 16x16 tiles; the list is sorted into class-pure batches of 8
+    #      (class = wide | bi-predicted | tall, kernels_mct.cuh), padded with 0xFFFFFFFF (8-bit pictures; > 8 bit: plain 16x16 tiles) ----
     area = np.zeros(len(pus), np.int64)
-    for u in r["units"]:
-        i, ux, uy = int(u) & 0xFFFFF, (int(u) >> 20) & 7, (int(u) >> 23) & 3
+    wide_path = pic.params.bit_depth_luma > 8
+    real = [int(u) for u in r["units"] if int(u) != 0xFFFFFFFF]
+    if not wide_path:
+        assert len(r["units"]) % 8 == 0
+        for b in range(0, len(r["units"]), 8):
+            batch = [int(u) for u in r["units"][b:b + 8]]
+            assert batch[0] != 0xFFFFFFFF and len({(u >> 24) & 7 for u in batch if u != 0xFFFFFFFF}) == 1
+    for u in real:
+        i, tx, ty = u & 0xFFFFF, (u >> 20) & 3, (u >> 22) & 3
         w, h = int(pus["w"][i]), int(pus["h"][i])
-        assert ux * 8 < w and uy * 16 < h
-        area[i] += min(8, w - ux * 8) * min(16, h - uy * 16)
+        assert tx * 16 < w and ty * 16 < h
+        tw, th = min(16, w - tx * 16), min(16, h - ty * 16)
+        area[i] += tw * th
+        if not wide_path:
+            cls = (u >> 24) & 7
+            assert bool(cls & 1) == (tw > 8) and bool(cls & 4) == (th > 8) and bool(cls & 2) == ((int(pus["flags"][i]) & 3) == 3)
     pred = (pus["flags"] & 3) != 0
     assert (area[pred] == pus["w"][pred].astype(np.int64) * pus["h"][pred]).all() and (area[~pred] == 0).all()
-    assert len(set(r["units"].tolist())) == len(r["units"])
+    assert len(set(real)) == len(real)
     # ---- k_residual classes ----
     la = r["la"]
     assert sorted(la.tolist()) == np.nonzero(work)[0].tolist()
