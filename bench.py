@@ -42,8 +42,8 @@ STEP_VARIANTS = 2
 
 
 def build_workload(width, height, bd, seed0=1000):
-    """2 x 32 pictures in decode order from 6 generated base pictures (slots are patched per use).
-    Returns (pictures, slot of the key picture the very first GOP references, generation seconds)."""
+    """Random-access workload (BASELINE configs 3 and 4): 2 x 32 pictures in decode order from 6 generated base pictures (slots
+    are patched per use).  Returns (pictures, slot of the key picture the very first GOP references, generation seconds)."""
     from libde265_b200 import synth
     t0 = time.time()
     base = {
@@ -89,6 +89,35 @@ def build_workload(width, height, bd, seed0=1000):
             seq.append(synth.SynthPicture(params, pus, b.weights, b.tus, b.coeffs, b.slices, b.ctbs, b.bs_map, b.qp_map, b.nofilt_map))
     assert slot_of[32 * STEP_VARIANTS] == first_key_slot, "the slot assignment must repeat after the last variant"
     return seq, first_key_slot, time.time() - t0
+
+
+def build_intra_workload(width, height, bd, seed0=3000, n_base=4):
+    """All-intra workload (BASELINE config 2): 2 x 32 I pictures from `n_base` generated pictures, destination slots rotating
+    over 16 DPB slots.  Intra pictures depend on nothing, so the engine pipelines them over its streams."""
+    from libde265_b200 import synth
+    t0 = time.time()
+    base = [synth.make_picture(width, height, "I", seed=seed0 + i, bit_depth=bd) for i in range(n_base)]
+    seq = []
+    for i in range(32 * STEP_VARIANTS):
+        b = base[i % n_base]
+        params = type(b.params).from_buffer_copy(b.params)
+        params.dst_slot = i % 16
+        params.poc = i
+        seq.append(synth.SynthPicture(params, b.pus, b.weights, b.tus, b.coeffs, b.slices, b.ctbs, b.bs_map, b.qp_map, b.nofilt_map))
+    return seq, None, time.time() - t0
+
+
+# The bench configurations: BASELINE.json configs 3 (the headline the metric is quoted on), 2 and 4
+CONFIGS = {
+    "main_ra_4k": dict(width=3840, height=2160, bd=8, kind="ra", mix=(1, 3, 28),
+                       what="3840x2160 8-bit 4:2:0 synthetic command records, hierarchical-B GOP8, intra period 32 (1 I + 3 P + 28 B per step), "
+                            "deblock+SAO on, one independent stream per GPU"),
+    "main10_4k": dict(width=3840, height=2160, bd=10, kind="ra", mix=(1, 3, 28),
+                      what="3840x2160 10-bit 4:2:0 (Main10: 16-bit sample path) synthetic command records, hierarchical-B GOP8, intra period 32 "
+                           "(1 I + 3 P + 28 B per step), deblock+SAO on"),
+    "intra1080": dict(width=1920, height=1080, bd=8, kind="intra", mix=(32, 0, 0),
+                      what="1920x1080 8-bit 4:2:0 synthetic command records, intra-only CTBs (32 I pictures per step, IDCT + intra path), deblock+SAO on"),
+}
 
 
 def algorithmic_bytes(seq, bd):
@@ -296,79 +325,40 @@ def real_stream_b200(eng, repeats=3):
     return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--width", type=int, default=W)
-    ap.add_argument("--height", type=int, default=H)
-    ap.add_argument("--bit-depth", type=int, default=BD)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    a = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": f"{a.width}x{a.height} {a.bit_depth}-bit 4:2:0 synthetic command records, hierarchical-B GOP8, intra period 32 "
-                          "(1 I + 3 P + 28 B per step), deblock+SAO on, one independent stream per GPU",
-              "pictures_per_step": 32, "l2_policy": "per-step working set (32 DPB surfaces x 12.4 MB + 2 x 32 record sets) exceeds the 126 MB L2"}
-
-    if a.impl == "reference":
-        if rank != 0:
-            return 0
-        reps = 12 if a.width * a.height > 1920 * 1080 else 48
-        vals = []
-        for _ in range(max(1, min(a.steps, 2))):
-            vals.append(cpu_baseline_parallel(a.width, a.height, a.bit_depth, reps))
-        best = max(vals, key=lambda v: v["value"])
-        try:
-            real = real_stream_reference()
-        except Exception as e:  # informative extra, never fatal
-            real = {"error": str(e)[:200]}
-        line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": "frames/s",
-                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1000.0 * 32 / best["value"], 3),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if a.bit_depth == 8 else "u16", "data": "synthetic",
-                "config": config, "cpu_baseline": best,
-                "e2e": {"value": best["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "real_streams": real}
-        print(json.dumps(line))
-        return 0
-
-    import torch
-    import torch.distributed as dist
+def run_config(name, eng, torch, dist, stream, a, rank, local_rank, world, headline):
+    """Runs one bench configuration on this rank's engine: `value` (records resident in HBM, pictures pipelined over the engine's
+    streams), the per-stage one-stream pass behind `roofline`, and `e2e` (host records in, pictures out).  Returns the
+    config's result dict on rank 0 (None elsewhere)."""
     from libde265_b200 import capi, shard, synth
-    from libde265_b200.engine import Engine
-
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    eng = Engine(local_rank)
-    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
-
-    seq, key_slot, gen_s = build_workload(a.width, a.height, a.bit_depth, seed0=shard.stream_seed(rank))
-    params = seq[0].params
-    ref0 = synth.random_planes(a.width, a.height, a.bit_depth, shard.reference_seed(rank))
-    eng.upload_slot(key_slot, params, ref0)  # POC 0 reference
+    cfg = CONFIGS[name]
+    width, height, bd = (a.width, a.height, a.bit_depth) if (headline and (a.width, a.height, a.bit_depth) != (W, H, BD)) else (cfg["width"], cfg["height"], cfg["bd"])
+    steps = a.steps if headline else max(2, min(a.steps, 4))
+    if cfg["kind"] == "ra":
+        seq, key_slot, gen_s = build_workload(width, height, bd, seed0=shard.stream_seed(rank) + (0 if headline else 7000))
+        ref0 = synth.random_planes(width, height, bd, shard.reference_seed(rank))
+        eng.upload_slot(key_slot, seq[0].params, ref0)  # POC 0 reference
+    else:
+        seq, key_slot, gen_s = build_intra_workload(width, height, bd, seed0=shard.stream_seed(rank) + 3000)
     prepared = [eng.prepare(p) for p in seq]
     h2d_bytes = sum(int(p.pus.nbytes + p.weights.nbytes + p.tus.nbytes + p.coeffs.nbytes + p.slices.nbytes + p.ctbs.nbytes + p.bs_map.nbytes +
                         p.qp_map.nbytes + p.nofilt_map.nbytes) for p in seq) // STEP_VARIANTS
-    bps = 2 if a.bit_depth > 8 else 1
-    pic_bytes = a.width * a.height * 3 // 2 * bps
+    bps = 2 if bd > 8 else 1
+    pic_bytes = width * height * 3 // 2 * bps
     # pinned host output buffers for the e2e leg (a ring of 8: more than the engine keeps pictures in flight)
-    outs = [[torch.empty((a.height, a.width), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory(),
-             torch.empty((a.height // 2, a.width // 2), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory(),
-             torch.empty((a.height // 2, a.width // 2), dtype=torch.uint8 if bps == 1 else torch.int16).pin_memory()] for _ in range(8)]
+    dt = torch.uint8 if bps == 1 else torch.int16
+    outs = [[torch.empty((height, width), dtype=dt).pin_memory(), torch.empty((height // 2, width // 2), dtype=dt).pin_memory(),
+             torch.empty((height // 2, width // 2), dtype=dt).pin_memory()] for _ in range(8)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         eng.join()  # stream 0 waits for the other pipeline streams: e1 marks the completion of every picture
         e1.record(stream)
@@ -378,7 +368,7 @@ def main():
 
     counter = {"step": 0}  # shared: the DPB state continues from one step to the next whatever leg runs it
 
-    def step_resident():  # one intra period; consecutive steps alternate between the workload's variants
+    def step_resident():  # one step; consecutive steps alternate between the workload's variants
         v = counter["step"] % STEP_VARIANTS
         counter["step"] += 1
         for h in prepared[32 * v:32 * (v + 1)]:
@@ -393,20 +383,20 @@ def main():
             capi.check(eng.lib.b200_engine_read_slot_async(eng.handle, p.params.dst_slot, capi.PlaneArray(*[t.data_ptr() for t in o]),
                                                            capi.StrideArray(*[t.stride(0) * bps for t in o])), "read_slot_async")
 
-    for _ in range(max(3, a.warmup)):
+    for _ in range(max(3, a.warmup) if headline else 3):
         step_resident()
     eng.sync()
     # ---- value: records resident in HBM, kernels only, pictures pipelined over the engine's streams ----
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = eng.launch_count()
-    ms_res = timed(step_resident, a.steps)
+    ms_res = timed(step_resident, steps)
     launches = eng.launch_count() - l0
     clk = clocks.stop()
     # ---- per-stage kernel times: CUDA events around every stage of every picture on the launching stream.  Stages of
     #      different pictures must not overlap for that, so this pass runs the same steps on ONE stream ----
     eng.enable_timing(True)
-    stage_steps = min(a.steps, 4)
+    stage_steps = min(steps, 4)
     ms_serial = timed(step_resident, stage_steps)
     stage_ms, n_timed = eng.timing_sum(reset=True)
     eng.enable_timing(False)
@@ -414,60 +404,148 @@ def main():
     for _ in range(2):
         step_e2e()
     eng.sync()
-    ms_e2e = timed(step_e2e, a.steps)
+    ms_e2e = timed(step_e2e, steps)
+    eng.sync()
+    for h in prepared:
+        eng.free_prepared(h)
+    if rank != 0:
+        return None
 
-    if rank == 0:
-        frames = 32 * a.steps * world
-        fps = frames / (ms_res / 1000.0)
-        fps_e2e = frames / (ms_e2e / 1000.0)
-        peaks = {}
+    frames = 32 * steps * world
+    fps = frames / (ms_res / 1000.0)
+    fps_e2e = frames / (ms_e2e / 1000.0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    alg = algorithmic_bytes(seq[:32], bd)
+    n_inter = sum(1 for p in seq[:32] if len(p.pus))
+    per_stage = {}
+    for k in ("inter_pred", "recon", "deblock", "sao"):
+        ms = stage_ms[k] / max(1, n_timed) * 32  # per step
+        gbs = (alg[k] / 1e9) / (ms / 1000.0) if ms > 0 else 0.0
+        per_stage[k] = {"ms_per_step": round(ms, 4), "algorithmic_MB_per_step": round(alg[k] / 1e6, 2), "achieved_gbs": round(gbs, 1),
+                        "frac": round(gbs / peak, 4)}
+    dominant = max(per_stage, key=lambda k: per_stage[k]["ms_per_step"])
+    traffic = {}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic_per_launch.json")))
+    except (OSError, ValueError):
+        pass
+    mc_kernel = "k_inter_pred_tma" if bd == 8 and not os.environ.get("B200_MC_LEGACY") else ("k_inter_pred8" if bd == 8 else "k_inter_pred<u16>")
+
+    def roof(k):
+        launches_per_step = max(1, {"inter_pred": n_inter, "recon": 32, "deblock": 64, "sao": 32}[k])
+        return {"kernel": {"inter_pred": mc_kernel, "recon": "k_residual+k_mark_pending+k_intra", "deblock": "k_deblock<V>+<H>", "sao": "k_sao_prep+k_sao"}[k],
+                "bound": "hbm", "achieved": per_stage[k]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_stage[k]["frac"],
+                "traffic": traffic.get(k) if name == "main_ra_4k" else None, "peak_source": peak_src,
+                "avg_launch_ms": round(per_stage[k]["ms_per_step"] / launches_per_step, 5),
+                "algorithmic_bytes_per_launch": int(alg[k] / launches_per_step),
+                "timing": "CUDA events per stage on the launching stream, one-stream pass of %d steps right after the timed region" % stage_steps}
+
+    res = {"value": round(fps, 2), "unit": "frames/s", "steps": steps, "ms_per_step": round(ms_res / steps, 4),
+           "dtype": "u8" if bd == 8 else "u16",
+           "config": {"workload": cfg["what"] if (width, height, bd) == (cfg["width"], cfg["height"], cfg["bd"]) else
+                      f"{width}x{height} {bd}-bit 4:2:0 synthetic command records ({cfg['kind']} structure of {name})",
+                      "name": name, "pictures_per_step": 32,
+                      "l2_policy": f"per-step working set ({len({p.params.dst_slot for p in seq})} DPB surfaces x {pic_bytes / 1e6:.1f} MB + {STEP_VARIANTS} x 32 record sets) "
+                                   "exceeds the 126 MB L2"},
+           "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 * pic_bytes,
+                   "ms_per_step": round(ms_e2e / steps, 4)},
+           "gpu_launches": int(launches), "clocks": clk, "roofline": roof(dominant), "stages": per_stage,
+           "one_stream": {"value": round(32 * stage_steps * world / (ms_serial / 1000.0), 2), "unit": "frames/s",
+                          "note": "same steps with picture pipelining off (per-stage timing pass)"},
+           "workload_gen_s": round(gen_s, 1)}
+    if n_inter:
+        res["roofline_mc"] = roof("inter_pred")
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="main_ra_4k", choices=sorted(CONFIGS), help="headline workload (default: BASELINE config 3, the one the metric is quoted on)")
+    ap.add_argument("--legs", default=None, help="comma-separated extra configs reported under 'legs' (default at 1 GPU: the other two BASELINE configs; 'none' to skip)")
+    ap.add_argument("--width", type=int, default=W)
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--bit-depth", type=int, default=BD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = CONFIGS[a.config]
+    custom = (a.width, a.height, a.bit_depth) != (W, H, BD)
+    width, height, bd = (a.width, a.height, a.bit_depth) if custom else (cfg["width"], cfg["height"], cfg["bd"])
+    legs = [x for x in (a.legs.split(",") if a.legs else ([] if (world > 1 or custom) else [c for c in ("intra1080", "main10_4k", "main_ra_4k") if c != a.config])) if x and x != "none"]
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+
+        def cpu_arm(w_, h_, bd_, mix):
+            reps = 12 if w_ * h_ > 1920 * 1080 else 48
+            vals = [cpu_baseline_parallel(w_, h_, bd_, reps, mix=mix) for _ in range(max(1, min(a.steps, 2)))]
+            return max(vals, key=lambda v: v["value"])
+
+        best = cpu_arm(width, height, bd, cfg["mix"])
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        alg = algorithmic_bytes(seq[:32], a.bit_depth)
-        per_stage = {}
-        for k in ("inter_pred", "recon", "deblock", "sao"):
-            ms = stage_ms[k] / max(1, n_timed) * 32  # per step
-            gbs = (alg[k] / 1e9) / (ms / 1000.0) if ms > 0 else 0.0
-            per_stage[k] = {"ms_per_step": round(ms, 4), "algorithmic_MB_per_step": round(alg[k] / 1e6, 2), "achieved_gbs": round(gbs, 1),
-                            "frac": round(gbs / peak, 4)}
-        dominant = max(per_stage, key=lambda k: per_stage[k]["ms_per_step"])
-        traffic = {}
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic_per_launch.json")))
-        except (OSError, ValueError):
-            pass
+            real = real_stream_reference()
+        except Exception as e:  # informative extra, never fatal
+            real = {"error": str(e)[:200]}
+        line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": "frames/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1000.0 * 32 / best["value"], 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if bd == 8 else "u16", "data": "synthetic",
+                "config": {"workload": cfg["what"], "name": a.config, "pictures_per_step": 32}, "cpu_baseline": best,
+                "e2e": {"value": best["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "real_streams": real}
+        if legs:
+            line["legs"] = {}
+            for leg in legs:
+                lc = CONFIGS[leg]
+                r = cpu_baseline_parallel(lc["width"], lc["height"], lc["bd"], 6 if lc["width"] > 1920 else 24, mix=lc["mix"])
+                line["legs"][leg] = {"value": r["value"], "unit": "frames/s", "config": {"workload": lc["what"], "name": leg}, "cpu_baseline": r}
+        print(json.dumps(line))
+        return 0
 
-        def roof(k):
-            launches_per_step = {"inter_pred": 31, "recon": 32, "deblock": 64, "sao": 32}[k]
-            return {"kernel": {"inter_pred": "k_inter_pred8", "recon": "k_residual+k_mark_pending+k_intra", "deblock": "k_deblock<V>+<H>",
-                               "sao": "k_sao_prep+k_sao"}[k],
-                    "bound": "hbm", "achieved": per_stage[k]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_stage[k]["frac"],
-                    "traffic": traffic.get(k), "peak_source": peak_src, "avg_launch_ms": round(per_stage[k]["ms_per_step"] / launches_per_step, 5),
-                    "algorithmic_bytes_per_launch": int(alg[k] / launches_per_step),
-                    "timing": "CUDA events per stage on the launching stream, one-stream pass of %d steps right after the timed region" % stage_steps}
+    import torch
+    import torch.distributed as dist
+    from libde265_b200.engine import Engine
 
-        line = {"metric": METRIC, "value": round(fps, 2), "unit": "frames/s",
-                "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": round(ms_res / a.steps, 4), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8" if a.bit_depth == 8 else "u16", "data": "synthetic", "config": config,
-                "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 * pic_bytes,
-                        "ms_per_step": round(ms_e2e / a.steps, 4)},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roof(dominant), "roofline_mc": roof("inter_pred"),
-                "stages": per_stage, "one_stream": {"value": round(32 * stage_steps * world / (ms_serial / 1000.0), 2), "unit": "frames/s",
-                                                    "note": "same steps with picture pipelining off (per-stage timing pass)"},
-                "workload_gen_s": round(gen_s, 1)}
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    eng = Engine(local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+
+    head = run_config(a.config, eng, torch, dist, stream, a, rank, local_rank, world, True)
+    leg_res = {}
+    for leg in legs:
+        try:
+            leg_res[leg] = run_config(leg, eng, torch, dist, stream, a, rank, local_rank, world, False)
+        except Exception as e:  # a leg never takes the headline down
+            leg_res[leg] = {"error": str(e)[:300]}
+    if rank == 0:
+        line = {"metric": METRIC, "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"],
+                "data": "synthetic", "config": head["config"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+                "roofline": head["roofline"], "stages": head["stages"], "one_stream": head["one_stream"], "workload_gen_s": head["workload_gen_s"]}
+        if "roofline_mc" in head:
+            line["roofline_mc"] = head["roofline_mc"]
+        if leg_res:
+            line["legs"] = leg_res
         try:
             line["real_streams"] = real_stream_b200(eng)
         except Exception as e:  # informative extra, never fatal
             line["real_streams"] = {"error": str(e)[:200]}
         if not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_parallel(a.width, a.height, a.bit_depth, 4 if a.width * a.height > 1920 * 1080 else 16)
+            line["cpu_baseline"] = cpu_baseline_parallel(width, height, bd, 4 if width * height > 1920 * 1080 else 16, mix=cfg["mix"])
         print(json.dumps(line))
-    for h in prepared:
-        eng.free_prepared(h)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

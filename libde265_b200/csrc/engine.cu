@@ -69,7 +69,7 @@ struct Surface {
   int w = 0, h = 0, cw = 0, ch = 0, chroma = 0, bd_y = 0, bd_c = 0;
   bool valid = false;  // holds a picture
   bool has_tm = false; // tensor maps of the padded planes for the TMA-staged MC kernel (8-bit surfaces)
-  CUtensorMap tm_luma, tm_chroma;
+  CUtensorMap tm_luma[2], tm_chroma[2];  // [0] big boxes, [1] small boxes (kernels_mct.cuh)
 };
 
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
@@ -135,22 +135,22 @@ static int surface_ensure(Surface& s, const b200_pic_params& p, cudaStream_t st)
     // tile's reference window (kernels_mct.cuh).  Out-of-range box parts (skew rows above the surface) are zero-filled and unused.
     b200_encode_tiled_fn enc = encode_tiled();
     if (!enc) return set_err(B200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-    {
+    for (int k = 0; k < 2; k++) {
       cuuint64_t dims[2] = {(cuuint64_t)s.pitch[0], (cuuint64_t)(p.height + 2 * B200_PAD_Y)}, strides[1] = {(cuuint64_t)s.pitch[0]};
-      cuuint32_t box[2] = {MCT_LW_PITCH, MCT_LW_ROWS}, es[2] = {1, 1};
-      if (enc(&s.tm_luma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.alloc[0], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+      cuuint32_t box[2] = {(cuuint32_t)(k ? MCT_LWS_PITCH : MCT_LWB_PITCH), (cuuint32_t)(k ? MCT_LWS_ROWS : MCT_LWB_ROWS)}, es[2] = {1, 1};
+      if (enc(&s.tm_luma[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.alloc[0], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return set_err(B200_ERR_CUDA, "cuTensorMapEncodeTiled (luma) failed");
-    }
-    if (cw) {
-      cuuint64_t dims[3] = {(cuuint64_t)s.pitch[1], (cuuint64_t)(ch + 2 * B200_PAD_CY), 2};
-      cuuint64_t strides[2] = {(cuuint64_t)s.pitch[1], (cuuint64_t)s.pitch[1] * (ch + 2 * B200_PAD_CY)};
-      cuuint32_t box[3] = {MCT_CW_PITCH, MCT_CW_ROWS, 2}, es[3] = {1, 1, 1};
-      if (enc(&s.tm_chroma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s.alloc[1], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return set_err(B200_ERR_CUDA, "cuTensorMapEncodeTiled (chroma) failed");
-    } else {
-      s.tm_chroma = s.tm_luma;
+      if (cw) {
+        cuuint64_t cdims[3] = {(cuuint64_t)s.pitch[1], (cuuint64_t)(ch + 2 * B200_PAD_CY), 2};
+        cuuint64_t cstrides[2] = {(cuuint64_t)s.pitch[1], (cuuint64_t)s.pitch[1] * (ch + 2 * B200_PAD_CY)};
+        cuuint32_t cbox[3] = {(cuuint32_t)(k ? MCT_CWS_PITCH : MCT_CWB_PITCH), (cuuint32_t)(k ? MCT_CWS_ROWS : MCT_CWB_ROWS), 2}, ces[3] = {1, 1, 1};
+        if (enc(&s.tm_chroma[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s.alloc[1], cdims, cstrides, cbox, ces, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return set_err(B200_ERR_CUDA, "cuTensorMapEncodeTiled (chroma) failed");
+      } else {
+        s.tm_chroma[k] = s.tm_luma[k];
+      }
     }
     s.has_tm = true;
   }
@@ -308,6 +308,12 @@ struct b200_engine {
   int num_sms = 148;
   int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
   int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
+  // B200_TIMELINE=<file>: a CUDA event before and after every launch; the intervals of all streams (ms since the first launch)
+  // are appended to the file at b200_engine_sync / destroy: which kernels of which pictures really overlap (tools/timeline.py)
+  struct TlEntry { cudaEvent_t e0, e1; const char* name; int poc, ctx; };
+  std::vector<TlEntry> tl;
+  const char* tl_path = nullptr;
+  cudaEvent_t tl_base = nullptr;
   bool mc_legacy = false;  // B200_MC_LEGACY=1: the first-generation 8-bit MC kernel (k_inter_pred8) for A/B measurements
   int mc_ctas = 3;         // k_inter_pred_tma: persistent CTAs per SM (B200_MC_CTAS)
   bool timing = false;
@@ -324,10 +330,42 @@ struct b200_engine {
 
 #define TIMING_RING 256
 
+static void tl_begin(b200_engine* en, cudaStream_t st, const char* name, int poc, int ctx)
+{
+  b200_engine::TlEntry e{nullptr, nullptr, name, poc, ctx};
+  cudaEventCreate(&e.e0);
+  cudaEventCreate(&e.e1);
+  if (!en->tl_base) { cudaEventCreate(&en->tl_base); cudaEventRecord(en->tl_base, st); }
+  cudaEventRecord(e.e0, st);
+  en->tl.push_back(e);
+}
+static void tl_end(b200_engine* en, cudaStream_t st) { cudaEventRecord(en->tl.back().e1, st); }
+static void tl_flush(b200_engine* en)  // after all streams were synchronised
+{
+  if (!en->tl_path || en->tl.empty()) return;
+  if (FILE* f = fopen(en->tl_path, "a")) {
+    for (auto& e : en->tl) {
+      float t0 = 0, t1 = 0;
+      cudaEventElapsedTime(&t0, en->tl_base, e.e0);
+      cudaEventElapsedTime(&t1, en->tl_base, e.e1);
+      fprintf(f, "%d %s %d %.4f %.4f\n", e.ctx, e.name, e.poc, t0, t1);
+    }
+    fclose(f);
+  }
+  for (auto& e : en->tl) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+  en->tl.clear();
+}
+#define TL(name, launch)                                                              \
+  do {                                                                                \
+    if (en->tl_path) tl_begin(en, st, name, L.params.poc, (int)(&cx - en->ctx));      \
+    launch;                                                                           \
+    if (en->tl_path) tl_end(en, st);                                                  \
+  } while (0)
+
 struct PicLayout {
   size_t off[14] = {}, total = 0, raw_total = 0, unit_cap = 0;
   uint32_t ref_mask = 0;  // slots the picture's PUs read
-  int n_tiles = 0, n_a = 0, n_aw = 0, n_a8 = 0, n_b = 0, n_task = 0;
+  int n_tiles = 0, n_batches = 0, n_a = 0, n_aw = 0, n_a8 = 0, n_b = 0, n_task = 0;
   bool run_deblock = false, run_sao = false, has_scaling = false;
   b200_pic_params params{};
   uint32_t n_tu = 0;
@@ -407,6 +445,7 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   if (const char* e = getenv("B200_INTRA_CTAS")) en->intra_ctas = std::max(1, std::min(4, atoi(e)));
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
+  en->tl_path = getenv("B200_TIMELINE");
   if (const char* e = getenv("B200_MC_LEGACY")) en->mc_legacy = atoi(e) != 0;
   if (const char* e = getenv("B200_MC_CTAS")) en->mc_ctas = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("B200_STREAMS")) en->n_ctx = std::max(1, std::min(B200_MAX_CTX, atoi(e)));
@@ -433,6 +472,8 @@ extern "C" void b200_engine_destroy(b200_engine* en)
   if (!en) return;
   cudaSetDevice(en->device);
   cudaDeviceSynchronize();
+  tl_flush(en);
+  if (en->tl_base) cudaEventDestroy(en->tl_base);
   if (getenv("B200_HOST_PROF") && en->host_n)
     fprintf(stderr, "[b200] submit_picture host ms/picture over %llu pictures: validate+staging-wait %.3f  plan+pack (threaded) %.3f  launch %.3f\n",
             (unsigned long long)en->host_n, 1e3 * en->host_s[0] / en->host_n, 1e3 * en->host_s[1] / en->host_n, 1e3 * en->host_s[3] / en->host_n);
@@ -463,6 +504,7 @@ extern "C" void* b200_engine_stream(b200_engine* en) { return en ? (void*)en->ct
 static int sync_all(b200_engine* en)
 {
   for (int k = 0; k < B200_MAX_CTX; k++) CU(cudaStreamSynchronize(en->ctx[k].stream));
+  tl_flush(en);
   for (auto& ss : en->ssync) {
     ss.writer = -1;
     for (auto& r : ss.read_pending) r = false;
@@ -598,14 +640,13 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
         maps.index_of_slot[i] = -1;
         if (!((L.ref_mask >> i) & 1) || !refs.plane[i][0] || !en->slot[i].has_tm) continue;
         if (n == MCT_MAX_REFS) return set_err(B200_ERR_UNSUPPORTED, "picture references more than %d DPB slots", MCT_MAX_REFS);
-        maps.luma[n] = en->slot[i].tm_luma;
-        maps.chroma[n] = en->slot[i].tm_chroma;
+        for (int k = 0; k < 2; k++) { maps.luma[k][n] = en->slot[i].tm_luma[k]; maps.chroma[k][n] = en->slot[i].tm_chroma[k]; }
         maps.index_of_slot[i] = (int8_t)n++;
         maps.valid_slots |= 1u << i;
       }
-      const int n_batches = n_tiles / MCT_TILES;
-      k_inter_pred_tma<<<std::min(n_batches, en->num_sms * en->mc_ctas), MCT_THREADS, sizeof(MctShared), st>>>(
-          dp, maps, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]), (const uint32_t*)(dbase + off[12]), n_batches);
+      const uint32_t* tw = (const uint32_t*)(dbase + off[12]);  // tile words, then the batch table
+      TL("mc", (k_inter_pred_tma<<<std::min(L.n_batches, en->num_sms * en->mc_ctas), MCT_THREADS, sizeof(MctShared), st>>>(
+                   dp, maps, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]), tw, tw + n_tiles, L.n_batches)));
     } else if (sizeof(P) == 1)
       k_inter_pred8<<<std::min((n_tiles + MC8_UNITS_PER_CTA - 1) / MC8_UNITS_PER_CTA, en->num_sms * 5), MC8_WARPS * 32, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
                                                          (const uint32_t*)(dbase + off[12]), n_tiles);
@@ -635,7 +676,7 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
       ra.n_listw = L.n_aw;
       ra.n_list8 = L.n_a8;
       const int items = L.n_aw + (L.n_a8 + 3) / 4 + (L.n_a - L.n_aw - L.n_a8 + 31) / 32;
-      k_residual<P><<<std::min((items + RC_WARPS - 1) / RC_WARPS, en->num_sms * 4), RC_THREADS, 0, st>>>(dp, ra);
+      TL("residual", (k_residual<P><<<std::min((items + RC_WARPS - 1) / RC_WARPS, en->num_sms * 4), RC_THREADS, 0, st>>>(dp, ra)));
       en->launches++;
     }
     ra.trace = nullptr;
@@ -650,14 +691,14 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
       ra.list = (const uint32_t*)(dbase + off[4]);
       ra.n_list = L.n_b;
       CU(cudaMemsetAsync(cx.sync_buf, 0, 256 + (size_t)dp.w4 * dp.h4 + 2 * cw4 * ch4, st));
-      k_mark_pending<<<(L.n_b + 255) / 256, 256, 0, st>>>(ra);
+      TL("mark", (k_mark_pending<<<(L.n_b + 255) / 256, 256, 0, st>>>(ra)));
       ra.task_start = (const uint32_t*)(dbase + off[13]);
       ra.n_task = L.n_task;
       int grid = (L.n_task + RC_WARPS - 1) / RC_WARPS;
       // an intra picture's DAG is latency-bound (one CTA per SM is as fast) and should leave room for the pictures it overlaps with
       const int cap = en->num_sms * (L.ref_mask == 0 && en->n_ctx > 1 ? 1 : en->intra_ctas);
       if (grid > cap) grid = cap;
-      k_intra<P><<<grid, RC_THREADS, sizeof(IntraSmem<P>), st>>>(dp, ra);
+      TL("intra", (k_intra<P><<<grid, RC_THREADS, sizeof(IntraSmem<P>), st>>>(dp, ra)));
       en->launches += 2;
       if (trace_dev) {
         std::vector<unsigned long long> h(4 * (size_t)L.n_task);
@@ -683,17 +724,17 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
   if (run_deblock) {
     const int nseg = ((dp.w4 + 1) / 2) * dp.h4 > dp.w4 * ((dp.h4 + 1) / 2) ? ((dp.w4 + 1) / 2) * dp.h4 : dp.w4 * ((dp.h4 + 1) / 2);
     dim3 grid((nseg + 127) / 128, dp.chroma ? 2 : 1);
-    k_deblock<P, true><<<grid, 128, 0, st>>>(dp, fa);
-    k_deblock<P, false><<<grid, 128, 0, st>>>(dp, fa);
+    TL("deblock_v", (k_deblock<P, true><<<grid, 128, 0, st>>>(dp, fa)));
+    TL("deblock_h", (k_deblock<P, false><<<grid, 128, 0, st>>>(dp, fa)));
     en->launches += 2;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[4], st));
   if (run_sao) {
     uint16_t* avail = (uint16_t*)(cx.sync_buf + sync_sao_offset(L.params));
     fa.sao_avail = avail;
-    k_sao_prep<<<(2 * dp.wctb * dp.hctb + 127) / 128, 128, 0, st>>>(dp, fa, avail);
+    TL("sao_prep", (k_sao_prep<<<(2 * dp.wctb * dp.hctb + 127) / 128, 128, 0, st>>>(dp, fa, avail)));
     dim3 grid((dp.w / 8 + 127) / 128, dp.h, dp.chroma ? 3 : 1);
-    k_sao<P><<<grid, 128, 0, st>>>(dp, fa);
+    TL("sao", (k_sao<P><<<grid, 128, 0, st>>>(dp, fa)));
     en->launches += 2;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[5], st));
@@ -745,7 +786,7 @@ static int plan_begin(b200_engine* en, const b200_picture* pic, PicLayout* L, si
   for (int i : k_raw_sections) { L->off[i] = total; total += align_up(sz[i], 256); }
   L->raw_total = total;
   // upper bound of the lists: every TU in one list, one task per TU; MC units cannot outnumber 4x8 blocks unless PUs overlap
-  L->unit_cap = (size_t)w4 * h4 / 2 + 64 + 8 * MCT_TILES;  // + the padding of the class-pure batches
+  L->unit_cap = ((size_t)w4 * h4 / 2 + 64 + 8 * MCT_MAX_TILES) * 9 / 8 + 64;  // + the padding of the class-pure batches + the batch table
   *cap_total = total + 3 * align_up(sizeof(uint32_t) * ((size_t)pic->n_tu + 1), 256) + align_up(sizeof(uint32_t) * L->unit_cap, 256) + 256;
   return B200_OK;
 }
@@ -782,19 +823,33 @@ static int plan_pus(b200_engine* en, const b200_picture* pic, PicLayout* L)
         }
     }
   }
+  L->n_batches = 0;
+  size_t n_words = tiles.size();
   if (!wide && !en->mc_legacy && !tiles.empty()) {
-    // counting sort by class, every class padded to whole batches of MCT_TILES tiles (a batch is class-pure; padding = MCT_INVALID)
+    // counting sort by class; every class padded to whole batches (MCT_CLASS_TILES tiles of one class, padding = MCT_INVALID);
+    // the batch table (first tile index | class) follows the tile words in the same section
     std::vector<uint32_t>& sorted = en->tiles_sorted;
     size_t count[8] = {}, start[8];
     for (uint32_t t : tiles) count[(t >> 24) & 7]++;
-    size_t total = 0;
-    for (int c = 0; c < 8; c++) { start[c] = total; total += (count[c] + MCT_TILES - 1) / MCT_TILES * MCT_TILES; }
-    sorted.assign(total, MCT_INVALID);
+    size_t total = 0, nb = 0;
+    for (int c = 0; c < 8; c++) {
+      const size_t per = MCT_CLASS_TILES(c), batches = (count[c] + per - 1) / per;
+      start[c] = total;
+      total += batches * per;
+      nb += batches;
+    }
+    sorted.assign(total + nb, MCT_INVALID);
+    size_t bi = total;
+    for (int c = 0; c < 8; c++)
+      for (size_t f = start[c]; f < start[c] + (count[c] + MCT_CLASS_TILES(c) - 1) / MCT_CLASS_TILES(c) * MCT_CLASS_TILES(c); f += MCT_CLASS_TILES(c))
+        sorted[bi++] = MCT_BATCH_WORD(f, c);
     for (uint32_t t : tiles) sorted[start[(t >> 24) & 7]++] = t;
     tiles.swap(sorted);
+    n_words = total;
+    L->n_batches = (int)nb;
   }
   if (tiles.size() > L->unit_cap) return set_err(B200_ERR_INVALID, "PUs overlap (more MC units than the picture has 4x8 blocks)");
-  L->n_tiles = (int)tiles.size();
+  L->n_tiles = (int)n_words;  // tile words; en->tiles also holds the n_batches batch words behind them
   return B200_OK;
 }
 
@@ -902,7 +957,7 @@ static void plan_finish(PicLayout* L)
   size_t sz[14] = {};
   sz[3] = sizeof(uint32_t) * (size_t)L->n_a;
   sz[4] = sizeof(uint32_t) * (size_t)L->n_b;
-  sz[12] = sizeof(uint32_t) * (size_t)L->n_tiles;
+  sz[12] = sizeof(uint32_t) * (size_t)(L->n_tiles + L->n_batches);
   sz[13] = L->n_task ? sizeof(uint32_t) * (size_t)(L->n_task + 1) : 0;
   size_t total = L->raw_total;
   for (int i : k_list_sections) { L->off[i] = total; total += align_up(sz[i], 256); }
@@ -939,7 +994,7 @@ static void pack_lists(b200_engine* en, const PicLayout& L, uint8_t* hb)
   if (L.n_a) memcpy(hb + off[3], en->list_a.data(), sizeof(uint32_t) * (size_t)L.n_a);
   if (L.n_b) memcpy(hb + off[4], en->list_b.data(), sizeof(uint32_t) * (size_t)L.n_b);
   if (L.n_task) memcpy(hb + off[13], en->task_start.data(), sizeof(uint32_t) * (size_t)(L.n_task + 1));
-  if (L.n_tiles) memcpy(hb + off[12], en->tiles.data(), sizeof(uint32_t) * (size_t)L.n_tiles);
+  if (L.n_tiles) memcpy(hb + off[12], en->tiles.data(), sizeof(uint32_t) * (size_t)(L.n_tiles + L.n_batches));
 }
 
 static int ensure_staging(StagingSet& ss, size_t total)
@@ -1119,7 +1174,9 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
   if (p.bit_depth_luma > 8) rc = launch_picture<uint16_t>(en, cx, L, dp, refs, dbase);
   else rc = launch_picture<uint8_t>(en, cx, L, dp, refs, dbase);
   if (rc) return rc;
+  if (en->tl_path) tl_begin(en, st, "extend", L.params.poc, k);
   launch_extend_borders(dst, st);  // the finished picture may be referenced: replicate its edges into the border
+  if (en->tl_path) tl_end(en, st);
   en->launches++;
   CU(cudaGetLastError());
   if (en->timing) { CU(cudaEventRecord(en->ev[6], st)); en->tcount++; }

@@ -33,23 +33,26 @@
 
 #define MCT_HD __host__ __device__ __forceinline__
 
-#define MCT_TILES 8                      // tiles per batch
 #define MCT_THREADS 128
-#define MCT_NTL (2 * MCT_TILES)          // tile-list slots per batch
-#define MCT_LW_PITCH 48                  // luma window: bytes per row (16-byte aligned origin + up to 15 + 23)
-#define MCT_LW_ROWS 26                   // 23 rows + up to 3 rows of bank skew
-#define MCT_LW_BYTES (MCT_LW_PITCH * MCT_LW_ROWS)  // 1248 = the TMA box
-#define MCT_LW_SLOT 1280                 // 128-byte aligned slot
-#define MCT_CW_PITCH 32                  // chroma window: bytes per row (up to 15 + 11)
-#define MCT_CW_ROWS 14                   // 11 rows + skew
-#define MCT_CW_PLANE (MCT_CW_PITCH * MCT_CW_ROWS)  // 448
-#define MCT_CW_BYTES (2 * MCT_CW_PLANE)  // 896 = the TMA box (Cb, Cr)
-#define MCT_CW_SLOT 896
-#define MCT_LI_PITCH 20                  // luma intermediate: words per pair row (16 used; 20: conflict-free 16-byte accesses)
-#define MCT_LI_WORDS (12 * MCT_LI_PITCH) // 12 pair rows
-#define MCT_CI_PITCH 12                  // chroma intermediate: words per pair row (8 used)
-#define MCT_CI_PLANE (6 * MCT_CI_PITCH)  // 6 pair rows
-#define MCT_CI_WORDS (2 * MCT_CI_PLANE)
+#define MCT_MAX_TL 32                    // tile-list items per batch: 32 with the small boxes, 16 with the big ones
+#define MCT_MAX_TILES 32                 // tiles per batch (small, uni-predicted)
+#define MCT_WIN_BYTES 40960              // window region: 16 x (1280 + 896) big  |  32 x (640 + 640) small
+#define MCT_INT_WORDS 6400               // intermediate region: 16 x (240 + 144) big  |  32 x (100 + 100) small
+// big boxes (tiles wider or taller than 8): luma 48 bytes x 26 rows (16-byte aligned origin + up to 15 + 23 columns; 23 rows + up
+// to 3 rows of bank skew), chroma 32 bytes x 14 rows x {Cb, Cr}
+#define MCT_LWB_PITCH 48
+#define MCT_LWB_ROWS 26
+#define MCT_LWB_SLOT 1280
+#define MCT_CWB_PITCH 32
+#define MCT_CWB_ROWS 14
+#define MCT_CWB_SLOT 896
+// small boxes (tiles of at most 8x8): luma 32 bytes x 18 rows (up to 15 + 15 columns, 15 rows + skew), chroma 32 x 10 x 2
+#define MCT_LWS_PITCH 32
+#define MCT_LWS_ROWS 18
+#define MCT_LWS_SLOT 640
+#define MCT_CWS_PITCH 32
+#define MCT_CWS_ROWS 10
+#define MCT_CWS_SLOT 640
 
 // tile word: bits 0-19 PU index, 20-21 x offset / 16, 22-23 y offset / 16, 24-26 class; 0xFFFFFFFF = padding
 #define MCT_CLASS_WIDE 1
@@ -57,22 +60,66 @@
 #define MCT_CLASS_TALL 4
 #define MCT_TILE_WORD(pu, tx, ty, cls) ((uint32_t)(pu) | ((uint32_t)(tx) << 20) | ((uint32_t)(ty) << 22) | ((uint32_t)(cls) << 24))
 #define MCT_INVALID 0xFFFFFFFFu
+// tiles per batch of a class: 32 tile-list items with the small boxes (narrow and short), 16 otherwise
+#define MCT_CLASS_TILES(cls) ((((cls) & (MCT_CLASS_WIDE | MCT_CLASS_TALL)) ? 16 : 32) >> (((cls) & MCT_CLASS_BI) ? 1 : 0))
+// batch word (host planner -> kernel): bits 0-27 index of the batch's first tile word, 28-30 class
+#define MCT_BATCH_WORD(first, cls) ((uint32_t)(first) | ((uint32_t)(cls) << 28))
 
 struct MctTile {
   int dst_y, dst_c;       // byte offsets of the tile's first luma / chroma sample in the destination planes
   uint8_t tw, th, nl, valid;
   uint8_t xo[2], hidx[2], yf[2], sh6[2];      // per list slot: window byte offset, pass-1 tap table index, vertical phase, final shift
   uint8_t cxo[2], chidx[2], cyf[2], csh6[2];  // chroma
-  uint8_t missing[2], pad[2];
+  uint8_t missing[2], plain, pad;             // plain: no explicit weights (fallback-motion.cc:33-62)
   Mc8Weight w[3];
 };
 
+// ---- task-space and shared-memory geometry of a batch class ----
+struct MctGeom {
+  int small;            // small boxes
+  int nl, ntl, ntiles;  // list slots per tile (1 | 2), tile-list items and tiles per batch
+  int nco;              // luma column octets per tile (1 | 2)
+  int nrp, nrpc;        // pair rows of the luma / chroma intermediate that pass 1 produces
+  int nu, nuc;          // output row pairs per tile in pass 2 (luma, chroma)
+  int n1l, n1c;         // pass-1 task counts (luma, chroma)
+  int n2l, n2c;         // pass-2 task counts
+  int lw_pitch, lw_slot, cw_off, cw_pitch, cw_plane, cw_slot;        // window region (bytes)
+  int li_pitch, li_words, ci_off, ci_pitch, ci_plane, ci_words;      // intermediate region (words)
+};
+MCT_HD MctGeom mct_geom(int cls)
+{
+  MctGeom g;
+  const bool wide = cls & MCT_CLASS_WIDE, tall = cls & MCT_CLASS_TALL;
+  g.small = !wide && !tall;
+  g.nl = (cls & MCT_CLASS_BI) ? 2 : 1;
+  g.ntl = g.small ? 32 : 16;
+  g.ntiles = g.ntl / g.nl;
+  g.nco = wide ? 2 : 1;
+  g.nrp = tall ? 12 : 8;
+  g.nrpc = tall ? 6 : 4;
+  g.nu = tall ? 8 : 4;
+  g.nuc = tall ? 4 : 2;
+  g.n1l = g.nrp * g.ntl * g.nco;
+  g.n1c = g.nrpc * g.ntl * 2;
+  g.n2l = g.ntiles * g.nco * g.nu;   // 8 columns x 2 rows per task
+  g.n2c = g.ntiles * 2 * g.nuc;
+  if (g.small) {
+    g.lw_pitch = MCT_LWS_PITCH; g.lw_slot = MCT_LWS_SLOT; g.cw_off = 32 * MCT_LWS_SLOT; g.cw_pitch = MCT_CWS_PITCH;
+    g.cw_plane = MCT_CWS_PITCH * MCT_CWS_ROWS; g.cw_slot = MCT_CWS_SLOT;
+    g.li_pitch = 12; g.li_words = 100; g.ci_off = 32 * 100; g.ci_pitch = 12; g.ci_plane = 48; g.ci_words = 100;
+  } else {
+    g.lw_pitch = MCT_LWB_PITCH; g.lw_slot = MCT_LWB_SLOT; g.cw_off = 16 * MCT_LWB_SLOT; g.cw_pitch = MCT_CWB_PITCH;
+    g.cw_plane = MCT_CWB_PITCH * MCT_CWB_ROWS; g.cw_slot = MCT_CWB_SLOT;
+    g.li_pitch = 20; g.li_words = 240; g.ci_off = 16 * 240; g.ci_pitch = 12; g.ci_plane = 72; g.ci_words = 144;
+  }
+  return g;
+}
+
 struct MctShared {
-  alignas(128) uint8_t lw[MCT_NTL][MCT_LW_SLOT];
-  alignas(128) uint8_t cw[MCT_NTL][MCT_CW_SLOT];
-  alignas(16) uint32_t li[MCT_NTL][MCT_LI_WORDS];
-  alignas(16) uint32_t ci[MCT_NTL][MCT_CI_WORDS];
-  MctTile info[2][MCT_TILES];
+  alignas(128) uint8_t win[MCT_WIN_BYTES];
+  alignas(16) uint32_t interm[MCT_INT_WORDS];
+  MctTile info[2][MCT_MAX_TILES];
+  MctGeom geom[2];
   Mc8Tables tab;
   alignas(8) unsigned long long bar;
 };
@@ -130,35 +177,8 @@ MCT_HD int mct_sat_u8(int v)
 #endif
 }
 
-// ---- task-space geometry of a batch class ----
-struct MctGeom {
-  int nl, ntl;          // list slots per tile (1 | 2), tile-list items per batch
-  int nco;              // luma column octets per tile (1 | 2)
-  int nrp, nrpc;        // pair rows of the luma / chroma intermediate that pass 1 produces (8 | 12, 4 | 6)
-  int n1l, n1c;         // pass-1 task counts (luma, chroma)
-  int n2l, n2c;         // pass-2 task counts
-  bool wide, tall;
-};
-MCT_HD MctGeom mct_geom(int cls)
-{
-  MctGeom g;
-  g.wide = cls & MCT_CLASS_WIDE;
-  g.tall = cls & MCT_CLASS_TALL;
-  g.nl = (cls & MCT_CLASS_BI) ? 2 : 1;
-  g.ntl = MCT_TILES * g.nl;
-  g.nco = g.wide ? 2 : 1;
-  g.nrp = g.tall ? 12 : 8;
-  g.nrpc = g.tall ? 6 : 4;
-  g.n1l = g.nrp * g.ntl * g.nco;
-  g.n1c = g.nrpc * g.ntl * 2;
-  // pass 2: wide 16 cols x 2 rows per task, narrow 8 cols x 4 rows; chroma 8 cols x 4 rows per plane
-  g.n2l = MCT_TILES * (g.wide ? (g.tall ? 8 : 4) : (g.tall ? 4 : 2));
-  g.n2c = MCT_TILES * 2 * (g.tall ? 2 : 1);
-  return g;
-}
-
 // ---- pass 1, luma: task -> (pair row rp, tile-list item, column octet) ----
-MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const uint8_t (*lw)[MCT_LW_SLOT], uint32_t (*li)[MCT_LI_WORDS], const Mc8Tables& tab)
+MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const uint8_t* win, uint32_t* interm, const Mc8Tables& tab)
 {
   const int co = g.nco == 2 ? (t & 1) : 0;
   const int u = g.nco == 2 ? (t >> 1) : t;
@@ -166,7 +186,6 @@ MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const u
   const int tile = g.nl == 2 ? (tli >> 1) : tli, s = g.nl == 2 ? (tli & 1) : 0;
   const MctTile& ti = info[tile];
   if (!ti.valid || ti.missing[s] || 2 * rp >= ti.th + 7 || 8 * co >= ti.tw) return;
-  const int tl = tile * 2 + s;
   const uint32_t* tp = &tab.qh[ti.hidx[s]][0][0];
   uint32_t T[4][3];
 #pragma unroll
@@ -174,11 +193,11 @@ MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const u
 #pragma unroll
     for (int k = 0; k < 3; k++) T[j][k] = tp[j * 3 + k];
   const int b = ti.xo[s] + 8 * co, sh = (b & 3) * 8;
-  const uint8_t* base = lw[tl] + (2 * rp + (tl & 3)) * MCT_LW_PITCH + (b & ~3);
+  const uint8_t* base = win + tli * g.lw_slot + (2 * rp + (tli & 3)) * g.lw_pitch + (b & ~3);
   int o[2][8];
 #pragma unroll
   for (int i = 0; i < 2; i++) {
-    const uint32_t* wp_ = reinterpret_cast<const uint32_t*>(base + i * MCT_LW_PITCH);
+    const uint32_t* wp_ = reinterpret_cast<const uint32_t*>(base + i * g.lw_pitch);
     const uint32_t w0 = wp_[0], w1 = wp_[1], w2 = wp_[2], w3 = wp_[3], w4 = wp_[4];
     uint32_t sb[4];
     sb[0] = mct_funnel(w0, w1, sh); sb[1] = mct_funnel(w1, w2, sh); sb[2] = mct_funnel(w2, w3, sh); sb[3] = mct_funnel(w3, w4, sh);
@@ -192,7 +211,7 @@ MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const u
         o[i][4 * q + j] = v;
       }
   }
-  uint32_t* dst = li[tl] + rp * MCT_LI_PITCH + 8 * co;
+  uint32_t* dst = interm + tli * g.li_words + rp * g.li_pitch + 8 * co;
   uint4 a, c;
   a.x = mct_pack16(o[0][0], o[1][0]); a.y = mct_pack16(o[0][1], o[1][1]); a.z = mct_pack16(o[0][2], o[1][2]); a.w = mct_pack16(o[0][3], o[1][3]);
   c.x = mct_pack16(o[0][4], o[1][4]); c.y = mct_pack16(o[0][5], o[1][5]); c.z = mct_pack16(o[0][6], o[1][6]); c.w = mct_pack16(o[0][7], o[1][7]);
@@ -201,14 +220,13 @@ MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const u
 }
 
 // ---- pass 1, chroma: task -> (pair row, tile-list item, plane); 8 columns x 2 rows ----
-MCT_HD void mct_pass1_chroma(int t, const MctGeom& g, const MctTile* info, const uint8_t (*cw)[MCT_CW_SLOT], uint32_t (*ci)[MCT_CI_WORDS], const Mc8Tables& tab)
+MCT_HD void mct_pass1_chroma(int t, const MctGeom& g, const MctTile* info, const uint8_t* win, uint32_t* interm, const Mc8Tables& tab)
 {
   const int pl = t & 1, u = t >> 1;
   const int tli = u % g.ntl, rp = u / g.ntl;
   const int tile = g.nl == 2 ? (tli >> 1) : tli, s = g.nl == 2 ? (tli & 1) : 0;
   const MctTile& ti = info[tile];
   if (!ti.valid || ti.missing[s] || 2 * rp >= (ti.th >> 1) + 3) return;
-  const int tl = tile * 2 + s;
   const uint32_t* tp = &tab.eh[ti.chidx[s]][0][0];
   uint32_t T[4][2];
 #pragma unroll
@@ -216,11 +234,11 @@ MCT_HD void mct_pass1_chroma(int t, const MctGeom& g, const MctTile* info, const
 #pragma unroll
     for (int k = 0; k < 2; k++) T[j][k] = tp[j * 2 + k];
   const int b = ti.cxo[s], sh = (b & 3) * 8;
-  const uint8_t* base = cw[tl] + pl * MCT_CW_PLANE + (2 * rp + (tl & 3)) * MCT_CW_PITCH + (b & ~3);
+  const uint8_t* base = win + g.cw_off + tli * g.cw_slot + pl * g.cw_plane + (2 * rp + (tli & 3)) * g.cw_pitch + (b & ~3);
   int o[2][8];
 #pragma unroll
   for (int i = 0; i < 2; i++) {
-    const uint32_t* wp_ = reinterpret_cast<const uint32_t*>(base + i * MCT_CW_PITCH);
+    const uint32_t* wp_ = reinterpret_cast<const uint32_t*>(base + i * g.cw_pitch);
     const uint32_t w0 = wp_[0], w1 = wp_[1], w2 = wp_[2], w3 = wp_[3];
     uint32_t sb[3];
     sb[0] = mct_funnel(w0, w1, sh); sb[1] = mct_funnel(w1, w2, sh); sb[2] = mct_funnel(w2, w3, sh);
@@ -233,7 +251,7 @@ MCT_HD void mct_pass1_chroma(int t, const MctGeom& g, const MctTile* info, const
         o[i][4 * q + j] = v;
       }
   }
-  uint32_t* dst = ci[tl] + pl * MCT_CI_PLANE + rp * MCT_CI_PITCH;
+  uint32_t* dst = interm + g.ci_off + tli * g.ci_words + pl * g.ci_plane + rp * g.ci_pitch;
   uint4 a, c;
   a.x = mct_pack16(o[0][0], o[1][0]); a.y = mct_pack16(o[0][1], o[1][1]); a.z = mct_pack16(o[0][2], o[1][2]); a.w = mct_pack16(o[0][3], o[1][3]);
   c.x = mct_pack16(o[0][4], o[1][4]); c.y = mct_pack16(o[0][5], o[1][5]); c.z = mct_pack16(o[0][6], o[1][6]); c.w = mct_pack16(o[0][7], o[1][7]);
@@ -241,145 +259,139 @@ MCT_HD void mct_pass1_chroma(int t, const MctGeom& g, const MctTile* info, const
   *reinterpret_cast<uint4*>(dst + 4) = c;
 }
 
-// Vertical 8-tap filter of COLS columns x ROWS rows (ROWS even, first row even) from pair rows at `src` (pitch in words):
+// Vertical 8-tap filter of 8 columns x 2 rows (an even row and the next) from the 5 pair rows at `src`:
 // out[i][c], already shifted / wrapped to the reference's int16 intermediate.
-template <int COLS, int ROWS, int PITCH>
-MCT_HD void mct_vfilter8(const uint32_t* src, const uint32_t (&tv)[5], int sh6, int (&out)[ROWS][COLS])
-{
-  constexpr int NP = ROWS / 2 + 4;
-#pragma unroll
-  for (int c4 = 0; c4 < COLS / 4; c4++) {
-    uint32_t V[NP][4];
-#pragma unroll
-    for (int p = 0; p < NP; p++) {
-      const uint4 q = *reinterpret_cast<const uint4*>(src + p * PITCH + 4 * c4);
-      V[p][0] = q.x; V[p][1] = q.y; V[p][2] = q.z; V[p][3] = q.w;
-    }
-#pragma unroll
-    for (int u = 0; u < ROWS / 2; u++)
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        int e = mct_dp2a_lo(V[u][c], tv[0], 0);
-        e = mct_dp2a_hi(V[u + 1][c], tv[0], e);
-        e = mct_dp2a_lo(V[u + 2][c], tv[1], e);
-        e = mct_dp2a_hi(V[u + 3][c], tv[1], e);
-        int o = mct_dp2a_lo(V[u][c], tv[2], 0);
-        o = mct_dp2a_hi(V[u + 1][c], tv[2], o);
-        o = mct_dp2a_lo(V[u + 2][c], tv[3], o);
-        o = mct_dp2a_hi(V[u + 3][c], tv[3], o);
-        o = mct_dp2a_lo(V[u + 4][c], tv[4], o);
-        out[2 * u][4 * c4 + c] = mct_wrap16(e, sh6);
-        out[2 * u + 1][4 * c4 + c] = mct_wrap16(o, sh6);
-      }
-  }
-}
-
-// Vertical 4-tap filter (chroma): 8 columns x 4 rows from pair rows.
-template <int PITCH>
-MCT_HD void mct_vfilter4(const uint32_t* src, const uint32_t (&tv)[3], int sh6, int (&out)[4][8])
+MCT_HD void mct_vpair8(const uint32_t* src, int pitch, const uint32_t (&tv)[5], int sh6, int (&out)[2][8])
 {
 #pragma unroll
   for (int c4 = 0; c4 < 2; c4++) {
-    uint32_t V[4][4];
+    uint32_t V[5][4];
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-      const uint4 q = *reinterpret_cast<const uint4*>(src + p * PITCH + 4 * c4);
+    for (int p = 0; p < 5; p++) {
+      const uint4 q = *reinterpret_cast<const uint4*>(src + p * pitch + 4 * c4);
       V[p][0] = q.x; V[p][1] = q.y; V[p][2] = q.z; V[p][3] = q.w;
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++)
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        int e = mct_dp2a_lo(V[u][c], tv[0], 0);
-        e = mct_dp2a_hi(V[u + 1][c], tv[0], e);
-        int o = mct_dp2a_lo(V[u][c], tv[1], 0);
-        o = mct_dp2a_hi(V[u + 1][c], tv[1], o);
-        o = mct_dp2a_lo(V[u + 2][c], tv[2], o);
-        out[2 * u][4 * c4 + c] = mct_wrap16(e, sh6);
-        out[2 * u + 1][4 * c4 + c] = mct_wrap16(o, sh6);
-      }
+    for (int c = 0; c < 4; c++) {
+      int e = mct_dp2a_lo(V[0][c], tv[0], 0);
+      e = mct_dp2a_hi(V[1][c], tv[0], e);
+      e = mct_dp2a_lo(V[2][c], tv[1], e);
+      e = mct_dp2a_hi(V[3][c], tv[1], e);
+      int o = mct_dp2a_lo(V[0][c], tv[2], 0);
+      o = mct_dp2a_hi(V[1][c], tv[2], o);
+      o = mct_dp2a_lo(V[2][c], tv[3], o);
+      o = mct_dp2a_hi(V[3][c], tv[3], o);
+      o = mct_dp2a_lo(V[4][c], tv[4], o);
+      out[0][4 * c4 + c] = mct_wrap16(e, sh6);
+      out[1][4 * c4 + c] = mct_wrap16(o, sh6);
+    }
   }
 }
 
-MCT_HD uint32_t mct_weight4(const int* a, const int* b, const Mc8Weight& w)
+// Vertical 4-tap filter (chroma): 8 columns x 2 rows from 3 pair rows.
+MCT_HD void mct_vpair4(const uint32_t* src, int pitch, const uint32_t (&tv)[3], int sh6, int (&out)[2][8])
+{
+#pragma unroll
+  for (int c4 = 0; c4 < 2; c4++) {
+    uint32_t V[3][4];
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      const uint4 q = *reinterpret_cast<const uint4*>(src + p * pitch + 4 * c4);
+      V[p][0] = q.x; V[p][1] = q.y; V[p][2] = q.z; V[p][3] = q.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      int e = mct_dp2a_lo(V[0][c], tv[0], 0);
+      e = mct_dp2a_hi(V[1][c], tv[0], e);
+      int o = mct_dp2a_lo(V[0][c], tv[1], 0);
+      o = mct_dp2a_hi(V[1][c], tv[1], o);
+      o = mct_dp2a_lo(V[2][c], tv[2], o);
+      out[0][4 * c4 + c] = mct_wrap16(e, sh6);
+      out[1][4 * c4 + c] = mct_wrap16(o, sh6);
+    }
+  }
+}
+
+MCT_HD uint32_t mct_weight4(const int* a, const int* b, const Mc8Weight& w, bool plain)
 {
   uint32_t r = 0;
+  if (plain) {  // (a + 32) >> 6 resp. (a + b + 64) >> 7 (fallback-motion.cc:33-62): b is 0 for uni-prediction
 #pragma unroll
-  for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8(((a[k] * w.w0 + b[k] * w.w1 + w.rnd) >> w.shift) + w.off) << (8 * k);
+    for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8((a[k] + b[k] + w.rnd) >> w.shift) << (8 * k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8(((a[k] * w.w0 + b[k] * w.w1 + w.rnd) >> w.shift) + w.off) << (8 * k);
+  }
   return r;
 }
 
-// Row segment store: nbytes (multiple of 4 for luma, of 2 for chroma) of `words` to dst, widest aligned form available.
-MCT_HD void mct_store_row(uint8_t* dst, const uint32_t* words, int full_bytes, int nbytes)
+// Row segment store: nbytes (<= 8; multiple of 4 for luma, of 2 for chroma) of the two words to dst, widest aligned form available.
+MCT_HD void mct_store_row(uint8_t* dst, uint32_t w0, uint32_t w1, int nbytes)
 {
-  if (nbytes == full_bytes && full_bytes == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
-  } else if (nbytes >= 8 && (nbytes & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-    for (int k = 0; k < nbytes / 8; k++) *reinterpret_cast<uint2*>(dst + 8 * k) = make_uint2(words[2 * k], words[2 * k + 1]);
+  if (nbytes == 8 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(w0, w1);
   } else if ((nbytes & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
-    for (int k = 0; k < nbytes / 4; k++) *reinterpret_cast<uint32_t*>(dst + 4 * k) = words[k];
+    *reinterpret_cast<uint32_t*>(dst) = w0;
+    if (nbytes == 8) *reinterpret_cast<uint32_t*>(dst + 4) = w1;
   } else {
-    for (int k = 0; k < nbytes / 2; k++) *reinterpret_cast<uint16_t*>(dst + 2 * k) = (uint16_t)(words[k >> 1] >> (16 * (k & 1)));
+    for (int k = 0; k < nbytes / 2; k++) *reinterpret_cast<uint16_t*>(dst + 2 * k) = (uint16_t)((k < 2 ? w0 : w1) >> (16 * (k & 1)));
   }
 }
 
-// ---- pass 2, luma: task -> (tile, row group); COLS x ROWS = 32 outputs ----
-template <int COLS, int ROWS>
-MCT_HD void mct_pass2_luma(int t, int groups, const MctTile* info, const uint32_t (*li)[MCT_LI_WORDS], const Mc8Tables& tab, uint8_t* plane, int pitch)
+// ---- pass 2, luma: task -> (tile, column octet, output row pair); 8 columns x 2 rows ----
+MCT_HD void mct_pass2_luma(int t, const MctGeom& g, const MctTile* info, const uint32_t* interm, const Mc8Tables& tab, uint8_t* plane, int pitch)
 {
-  const int tile = t / groups, rg = t % groups;
+  const int u = t % g.nu, tc = t / g.nu;
+  const int co = g.nco == 2 ? (tc & 1) : 0, tile = g.nco == 2 ? (tc >> 1) : tc;
   const MctTile& ti = info[tile];
-  const int y0 = ROWS * rg;
-  if (!ti.valid || y0 >= ti.th) return;
-  int v[2][ROWS][COLS];
+  const int y0 = 2 * u;
+  if (!ti.valid || y0 >= ti.th || 8 * co >= ti.tw) return;
+  int v[2][2][8];
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     if (s < ti.nl && !ti.missing[s]) {
       uint32_t tv[5];
 #pragma unroll
       for (int k = 0; k < 5; k++) tv[k] = tab.qv[ti.yf[s]][k];
-      mct_vfilter8<COLS, ROWS, MCT_LI_PITCH>(li[tile * 2 + s] + (y0 >> 1) * MCT_LI_PITCH, tv, ti.sh6[s], v[s]);
+      mct_vpair8(interm + (tile * g.nl + s) * g.li_words + u * g.li_pitch + 8 * co, g.li_pitch, tv, ti.sh6[s], v[s]);
     } else {
       const int fill = s < ti.nl ? (1 << 13) : 0;  // missing reference: mid-grey intermediate (motion.cc:362)
 #pragma unroll
-      for (int i = 0; i < ROWS; i++)
+      for (int i = 0; i < 2; i++)
 #pragma unroll
-        for (int c = 0; c < COLS; c++) v[s][i][c] = fill;
+        for (int c = 0; c < 8; c++) v[s][i][c] = fill;
     }
   }
   const Mc8Weight w = ti.w[0];
-  const int nbytes = ti.tw < COLS ? ti.tw : COLS;
+  const int nbytes = ti.tw - 8 * co < 8 ? ti.tw - 8 * co : 8;
 #pragma unroll
-  for (int i = 0; i < ROWS; i++) {
+  for (int i = 0; i < 2; i++) {
     if (y0 + i >= ti.th) break;
-    uint32_t words[COLS / 4];
-#pragma unroll
-    for (int k = 0; k < COLS / 4; k++) words[k] = mct_weight4(&v[0][i][4 * k], &v[1][i][4 * k], w);
-    mct_store_row(plane + ti.dst_y + (size_t)(y0 + i) * pitch, words, COLS, nbytes);
+    const uint32_t w0 = mct_weight4(&v[0][i][0], &v[1][i][0], w, ti.plain), w1 = mct_weight4(&v[0][i][4], &v[1][i][4], w, ti.plain);
+    mct_store_row(plane + ti.dst_y + (size_t)(y0 + i) * pitch + 8 * co, w0, w1, nbytes);
   }
 }
 
-// ---- pass 2, chroma: task -> (tile, plane, row group of 4) ----
-MCT_HD void mct_pass2_chroma(int t, int groups, const MctTile* info, const uint32_t (*ci)[MCT_CI_WORDS], const Mc8Tables& tab, uint8_t* cb, uint8_t* cr,
-                             int pitch)
+// ---- pass 2, chroma: task -> (tile, plane, output row pair); 8 columns x 2 rows ----
+MCT_HD void mct_pass2_chroma(int t, const MctGeom& g, const MctTile* info, const uint32_t* interm, const Mc8Tables& tab, uint8_t* cb, uint8_t* cr, int pitch)
 {
-  const int pl = t & 1, u = t >> 1;
-  const int tile = u / groups, rg = u % groups;
+  const int u = t % g.nuc, tp_ = t / g.nuc;
+  const int pl = tp_ & 1, tile = tp_ >> 1;
   const MctTile& ti = info[tile];
-  const int y0 = 4 * rg, ch = ti.th >> 1, cwd = ti.tw >> 1;
+  const int y0 = 2 * u, ch = ti.th >> 1, cwd = ti.tw >> 1;
   if (!ti.valid || y0 >= ch) return;
-  int v[2][4][8];
+  int v[2][2][8];
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     if (s < ti.nl && !ti.missing[s]) {
       uint32_t tv[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) tv[k] = tab.ev[ti.cyf[s]][k];
-      mct_vfilter4<MCT_CI_PITCH>(ci[tile * 2 + s] + pl * MCT_CI_PLANE + (y0 >> 1) * MCT_CI_PITCH, tv, ti.csh6[s], v[s]);
+      mct_vpair4(interm + g.ci_off + (tile * g.nl + s) * g.ci_words + pl * g.ci_plane + u * g.ci_pitch, g.ci_pitch, tv, ti.csh6[s], v[s]);
     } else {
       const int fill = s < ti.nl ? (1 << 13) : 0;
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int c = 0; c < 8; c++) v[s][i][c] = fill;
     }
@@ -387,12 +399,10 @@ MCT_HD void mct_pass2_chroma(int t, int groups, const MctTile* info, const uint3
   const Mc8Weight w = ti.w[1 + pl];
   uint8_t* plane = pl ? cr : cb;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 2; i++) {
     if (y0 + i >= ch) break;
-    uint32_t words[2];
-    words[0] = mct_weight4(&v[0][i][0], &v[1][i][0], w);
-    words[1] = mct_weight4(&v[0][i][4], &v[1][i][4], w);
-    mct_store_row(plane + ti.dst_c + (size_t)(y0 + i) * pitch, words, 8, cwd);
+    const uint32_t w0 = mct_weight4(&v[0][i][0], &v[1][i][0], w, ti.plain), w1 = mct_weight4(&v[0][i][4], &v[1][i][4], w, ti.plain);
+    mct_store_row(plane + ti.dst_c + (size_t)(y0 + i) * pitch, w0, w1, cwd);
   }
 }
 
@@ -424,6 +434,7 @@ MCT_HD MctBox mct_decode_tile(uint32_t word, int s, const b200_pu* pus, const b2
     ti->dst_y = y0 * pic.pitch[0] + x0;
     ti->dst_c = (y0 >> 1) * pic.pitch[1] + (x0 >> 1);
     const bool wgt = pu.flags & B200_PU_WEIGHTED;
+    ti->plain = wgt ? 0 : 1;
     const b200_weight_entry* we = wts + (wgt ? pu.wt_idx : 0);
 #pragma unroll
     for (int c = 0; c < 3; c++) ti->w[c] = mc8_weight(nl == 2, wgt, first, we, c);
@@ -461,8 +472,8 @@ MCT_HD MctBox mct_decode_tile(uint32_t word, int s, const b200_pu* pus, const b2
 
 #define MCT_MAX_REFS 16
 struct MctMaps {
-  CUtensorMap luma[MCT_MAX_REFS];    // 2-D: {pitch bytes, padded rows}, box 48 x 26
-  CUtensorMap chroma[MCT_MAX_REFS];  // 3-D: {pitch bytes, padded rows, 2 planes}, box 32 x 14 x 2
+  CUtensorMap luma[2][MCT_MAX_REFS];    // [0] big box 48 x 26, [1] small box 32 x 18; 2-D tensor {pitch bytes, padded rows}
+  CUtensorMap chroma[2][MCT_MAX_REFS];  // [0] 32 x 14 x 2, [1] 32 x 10 x 2; 3-D tensor {pitch bytes, padded rows, 2 planes}
   int8_t index_of_slot[B200_MAX_SLOTS];
   uint32_t valid_slots;
 };
@@ -471,7 +482,7 @@ __device__ __forceinline__ uint32_t mct_smem(const void* p) { return (uint32_t)_
 
 __global__ void __launch_bounds__(MCT_THREADS) k_inter_pred_tma(DevPic pic, const __grid_constant__ MctMaps maps, const b200_pu* __restrict__ pus,
                                                                 const b200_weight_entry* __restrict__ wts, const uint32_t* __restrict__ tiles,
-                                                                int n_batches)
+                                                                const uint32_t* __restrict__ batches, int n_batches)
 {
   extern __shared__ __align__(128) uint8_t mct_smem_raw[];
   MctShared& sm = *reinterpret_cast<MctShared*>(mct_smem_raw);
@@ -483,28 +494,38 @@ __global__ void __launch_bounds__(MCT_THREADS) k_inter_pred_tma(DevPic pic, cons
   }
   const uint32_t bar = mct_smem(&sm.bar);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(MCT_NTL));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(MCT_MAX_TL));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const bool has_chroma = pic.chroma != 0;
 
-  auto produce = [&](int batch, MctTile* info) {  // threads 0 .. MCT_NTL-1: one (tile, list slot) each
-    const int tile = tid >> 1, s = tid & 1;
-    const MctBox bx = mct_decode_tile(tiles[batch * MCT_TILES + tile], s, pus, wts, maps.valid_slots, pic, &info[tile]);
-    const int mi = bx.active ? maps.index_of_slot[bx.slot] : -1;
+  // threads 0 .. 31: one tile-list item each (all 32 arrive on the barrier, whatever the class uses)
+  auto produce = [&](int batch, int buf) {
+    const uint32_t bw = batches[batch];
+    const MctGeom g = mct_geom((bw >> 28) & 7);
+    if (tid == 0) sm.geom[buf] = g;
+    int mi = -1;
+    MctBox bx;
+    if (tid < g.ntl) {
+      const int tile = g.nl == 2 ? (tid >> 1) : tid, s = g.nl == 2 ? (tid & 1) : 0;
+      bx = mct_decode_tile(tiles[(bw & 0x0FFFFFFF) + tile], s, pus, wts, maps.valid_slots, pic, &sm.info[buf][tile]);
+      mi = bx.active ? maps.index_of_slot[bx.slot] : -1;
+    }
     if (mi >= 0) {
-      const int tl = tid, skew = tl & 3;
-      const uint32_t bytes = MCT_LW_BYTES + (has_chroma ? MCT_CW_BYTES : 0);
+      const int skew = tid & 3, k = g.small;
+      const uint32_t bytes = (k ? MCT_LWS_PITCH * MCT_LWS_ROWS : MCT_LWB_PITCH * MCT_LWB_ROWS) +
+                             (has_chroma ? (k ? 2 * MCT_CWS_PITCH * MCT_CWS_ROWS : 2 * MCT_CWB_PITCH * MCT_CWB_ROWS) : 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the windows were read through the generic proxy in pass 1
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(mct_smem(sm.lw[tl])),
-                   "l"(&maps.luma[mi]), "r"(bx.lx + B200_PAD_X), "r"(bx.ly + B200_PAD_Y - skew), "r"(bar)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                       mct_smem(sm.win + tid * g.lw_slot)),
+                   "l"(&maps.luma[k][mi]), "r"(bx.lx + B200_PAD_X), "r"(bx.ly + B200_PAD_Y - skew), "r"(bar)
                    : "memory");
       if (has_chroma)
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                         mct_smem(sm.cw[tl])),
-                     "l"(&maps.chroma[mi]), "r"(bx.cx + B200_PAD_CX), "r"(bx.cy + B200_PAD_CY - skew), "r"(0), "r"(bar)
+                         mct_smem(sm.win + g.cw_off + tid * g.cw_slot)),
+                     "l"(&maps.chroma[k][mi]), "r"(bx.cx + B200_PAD_CX), "r"(bx.cy + B200_PAD_CY - skew), "r"(0), "r"(bar)
                      : "memory");
     } else {
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -512,7 +533,7 @@ __global__ void __launch_bounds__(MCT_THREADS) k_inter_pred_tma(DevPic pic, cons
   };
 
   int batch = blockIdx.x;
-  if (batch < n_batches && tid < MCT_NTL) produce(batch, sm.info[0]);
+  if (batch < n_batches && tid < MCT_MAX_TL) produce(batch, 0);
   for (int it = 0; batch < n_batches; batch += gridDim.x, it++) {
     {  // wait for this batch's windows (and the producers' tile info)
       const uint32_t parity = it & 1;
@@ -522,25 +543,16 @@ __global__ void __launch_bounds__(MCT_THREADS) k_inter_pred_tma(DevPic pic, cons
       } while (!done);
     }
     const MctTile* info = sm.info[it & 1];
-    const uint32_t w0 = tiles[batch * MCT_TILES];
-    const MctGeom g = mct_geom((w0 >> 24) & 7);  // a batch is class-pure and its first tile is never padding
-    for (int t = tid; t < g.n1l; t += MCT_THREADS) mct_pass1_luma(t, g, info, sm.lw, sm.li, sm.tab);
+    const MctGeom g = sm.geom[it & 1];
+    for (int t = tid; t < g.n1l; t += MCT_THREADS) mct_pass1_luma(t, g, info, sm.win, sm.interm, sm.tab);
     if (has_chroma)
-      for (int t = tid; t < g.n1c; t += MCT_THREADS) mct_pass1_chroma(t, g, info, sm.cw, sm.ci, sm.tab);
+      for (int t = tid; t < g.n1c; t += MCT_THREADS) mct_pass1_chroma(t, g, info, sm.win, sm.interm, sm.tab);
     __syncthreads();
     const int next = batch + gridDim.x;
-    if (next < n_batches && tid < MCT_NTL) produce(next, sm.info[(it + 1) & 1]);  // the windows are free: fetch ahead during pass 2
-    if (g.wide) {
-      const int groups = g.tall ? 8 : 4;
-      for (int t = tid; t < g.n2l; t += MCT_THREADS) mct_pass2_luma<16, 2>(t, groups, info, sm.li, sm.tab, pic.cur[0], pic.pitch[0]);
-    } else {
-      const int groups = g.tall ? 4 : 2;
-      for (int t = tid; t < g.n2l; t += MCT_THREADS) mct_pass2_luma<8, 4>(t, groups, info, sm.li, sm.tab, pic.cur[0], pic.pitch[0]);
-    }
-    if (has_chroma) {
-      const int groups = g.tall ? 2 : 1;
-      for (int t = tid; t < g.n2c; t += MCT_THREADS) mct_pass2_chroma(t, groups, info, sm.ci, sm.tab, pic.cur[1], pic.cur[2], pic.pitch[1]);
-    }
+    if (next < n_batches && tid < MCT_MAX_TL) produce(next, (it + 1) & 1);  // the windows are free: fetch ahead during pass 2
+    for (int t = tid; t < g.n2l; t += MCT_THREADS) mct_pass2_luma(t, g, info, sm.interm, sm.tab, pic.cur[0], pic.pitch[0]);
+    if (has_chroma)
+      for (int t = tid; t < g.n2c; t += MCT_THREADS) mct_pass2_chroma(t, g, info, sm.interm, sm.tab, pic.cur[1], pic.cur[2], pic.pitch[1]);
     __syncthreads();
   }
 }

@@ -57,36 +57,34 @@ extern "C" __attribute__((visibility("default"))) int mct_emulate(const b200_pic
   }
   static MctShared sm;
   mc8_build_tables(sm.tab);
-  if (n_tiles % MCT_TILES) return -1;
-  for (int batch = 0; batch < n_tiles / MCT_TILES; batch++) {
-    MctTile* info = sm.info[batch & 1];
-    memset(sm.lw, 0xAB, sizeof(sm.lw));  // poison: stale data must never matter
-    memset(sm.cw, 0xAB, sizeof(sm.cw));
-    memset(sm.li, 0xCD, sizeof(sm.li));
-    memset(sm.ci, 0xCD, sizeof(sm.ci));
-    for (int tid = 0; tid < MCT_NTL; tid++) {  // the producer threads
-      const int tile = tid >> 1, s = tid & 1;
-      const MctBox bx = mct_decode_tile(tiles[batch * MCT_TILES + tile], s, pic->pus, pic->weights, valid, dp, &info[tile]);
+  int it = 0;
+  for (int first = 0; first < n_tiles; it++) {
+    const uint32_t w0 = tiles[first];
+    if (w0 == MCT_INVALID) return -2;  // a batch starts with a real tile
+    const int cls = (w0 >> 24) & 7;
+    const MctGeom g = mct_geom(cls);
+    if (g.ntiles != MCT_CLASS_TILES(cls) || first + g.ntiles > n_tiles) return -1;
+    MctTile* info = sm.info[it & 1];
+    memset(sm.win, 0xAB, sizeof(sm.win));  // poison: stale data must never matter
+    memset(sm.interm, 0xCD, sizeof(sm.interm));
+    for (int tid = 0; tid < g.ntl; tid++) {  // the producer threads
+      const int tile = g.nl == 2 ? (tid >> 1) : tid, s = g.nl == 2 ? (tid & 1) : 0;
+      const MctBox bx = mct_decode_tile(tiles[first + tile], s, pic->pus, pic->weights, valid, dp, &info[tile]);
       if (!bx.active) continue;
       const int skew = tid & 3;
-      pad[bx.slot][0].box(sm.lw[tid], bx.lx + B200_PAD_X, bx.ly + B200_PAD_Y - skew, MCT_LW_PITCH, MCT_LW_ROWS);
+      pad[bx.slot][0].box(sm.win + tid * g.lw_slot, bx.lx + B200_PAD_X, bx.ly + B200_PAD_Y - skew, g.lw_pitch, g.small ? MCT_LWS_ROWS : MCT_LWB_ROWS);
       if (CW)
         for (int c = 0; c < 2; c++)
-          pad[bx.slot][1 + c].box(sm.cw[tid] + c * MCT_CW_PLANE, bx.cx + B200_PAD_CX, bx.cy + B200_PAD_CY - skew, MCT_CW_PITCH, MCT_CW_ROWS);
+          pad[bx.slot][1 + c].box(sm.win + g.cw_off + tid * g.cw_slot + c * g.cw_plane, bx.cx + B200_PAD_CX, bx.cy + B200_PAD_CY - skew, g.cw_pitch,
+                                  g.small ? MCT_CWS_ROWS : MCT_CWB_ROWS);
     }
-    const uint32_t w0 = tiles[batch * MCT_TILES];
-    if (w0 == MCT_INVALID) return -2;  // a batch starts with a real tile
-    const MctGeom g = mct_geom((w0 >> 24) & 7);
-    for (int t = 0; t < g.n1l; t++) mct_pass1_luma(t, g, info, sm.lw, sm.li, sm.tab);
+    for (int t = 0; t < g.n1l; t++) mct_pass1_luma(t, g, info, sm.win, sm.interm, sm.tab);
     if (CW)
-      for (int t = 0; t < g.n1c; t++) mct_pass1_chroma(t, g, info, sm.cw, sm.ci, sm.tab);
-    if (g.wide) {
-      for (int t = 0; t < g.n2l; t++) mct_pass2_luma<16, 2>(t, g.tall ? 8 : 4, info, sm.li, sm.tab, dp.cur[0], dp.pitch[0]);
-    } else {
-      for (int t = 0; t < g.n2l; t++) mct_pass2_luma<8, 4>(t, g.tall ? 4 : 2, info, sm.li, sm.tab, dp.cur[0], dp.pitch[0]);
-    }
+      for (int t = 0; t < g.n1c; t++) mct_pass1_chroma(t, g, info, sm.win, sm.interm, sm.tab);
+    for (int t = 0; t < g.n2l; t++) mct_pass2_luma(t, g, info, sm.interm, sm.tab, dp.cur[0], dp.pitch[0]);
     if (CW)
-      for (int t = 0; t < g.n2c; t++) mct_pass2_chroma(t, g.tall ? 2 : 1, info, sm.ci, sm.tab, dp.cur[1], dp.cur[2], dp.pitch[1]);
+      for (int t = 0; t < g.n2c; t++) mct_pass2_chroma(t, g, info, sm.interm, sm.tab, dp.cur[1], dp.cur[2], dp.pitch[1]);
+    first += g.ntiles;
   }
   return 0;
 }

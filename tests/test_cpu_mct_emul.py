@@ -57,7 +57,6 @@ def run_case(b200lib, emul, W, H, ptype, seed, refs_present=(0, 1), **kw):
     want = orc.read_slot(2, pic.params)
     orc.close()
     units, n = plan_tiles(b200lib, pic)
-    assert n % 8 == 0
     refp = (C.c_void_p * 96)()
     for s, p in planes.items():
         for c in range(3):
@@ -75,9 +74,16 @@ def run_case(b200lib, emul, W, H, ptype, seed, refs_present=(0, 1), **kw):
 def test_planner_emits_class_pure_batches(b200lib):
     pic = synth.make_picture(416, 240, "B", seed=3, dst_slot=2, ref_slots=(0, 1))
     units, n = plan_tiles(b200lib, pic)
-    u = np.frombuffer(units, np.uint32)[:n].reshape(-1, 8)
+    u = np.frombuffer(units, np.uint32)[:n]
     covered = np.zeros((240, 416), np.int32)
-    for batch in u:
+    batches, first = [], 0
+    while first < n:  # batches are self-describing: the first tile's class gives the batch size (32 tile-list items with small boxes, else 16)
+        cls = (int(u[first]) >> 24) & 7
+        size = (16 if cls & 5 else 32) >> (1 if cls & 2 else 0)
+        batches.append(u[first:first + size])
+        first += size
+    assert first == n
+    for batch in batches:
         assert batch[0] != 0xFFFFFFFF
         cls = (batch[0] >> 24) & 7
         for w in batch:

@@ -40,10 +40,13 @@ def check_picture(lib, pic):
     wide_path = pic.params.bit_depth_luma > 8
     real = [int(u) for u in r["units"] if int(u) != 0xFFFFFFFF]
     if not wide_path:
-        assert len(r["units"]) % 8 == 0
-        for b in range(0, len(r["units"]), 8):
-            batch = [int(u) for u in r["units"][b:b + 8]]
-            assert batch[0] != 0xFFFFFFFF and len({(u >> 24) & 7 for u in batch if u != 0xFFFFFFFF}) == 1
+        b = 0
+        while b < len(r["units"]):  # batch size by the class of its first tile: 32 tile-list items with the small boxes, else 16
+            cls = (int(r["units"][b]) >> 24) & 7
+            size = (16 if cls & 5 else 32) >> (1 if cls & 2 else 0)
+            batch = [int(u) for u in r["units"][b:b + size]]
+            assert len(batch) == size and batch[0] != 0xFFFFFFFF and len({(u >> 24) & 7 for u in batch if u != 0xFFFFFFFF}) == 1
+            b += size
     for u in real:
         i, tx, ty = u & 0xFFFFF, (u >> 20) & 3, (u >> 22) & 3
         w, h = int(pus["w"][i]), int(pus["h"][i])

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_probe(const CUtensorMap* gmap, c
   unsigned acc = 0;
   auto coords = [&](int i, int& x, int& y) {
     const uint32_t h = hash32(wid + i);
-    x = (int)(h % (uint32_t)(W - bw));
+    x = (int)(h % (uint32_t)(W - bw)) & ~15;  // TMA box origins must be 16-byte aligned in the innermost dimension (tools/tma_probe2.cu)
     y = (int)((h >> 12) % (uint32_t)(H - bh));
   };
   if (MODE < 2) {
