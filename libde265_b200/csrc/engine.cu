@@ -280,7 +280,7 @@ struct HostPool {
 // writers of its reference slots and for every earlier reader / writer of its destination slot.  So pictures that do
 // not depend on each other (the B pictures of one hierarchy level, the next intra period's I picture) overlap, and a
 // latency-bound kernel (the intra DAG) of one picture leaves the SMs to the others.
-#define B200_MAX_CTX 8
+#define B200_MAX_CTX 12
 struct PipeCtx {
   cudaStream_t stream = nullptr;
   Surface scratch;              // pre-SAO picture
@@ -306,6 +306,8 @@ struct b200_engine {
   SlotSync ssync[B200_MAX_SLOTS];
   HostPool pool;
   int num_sms = 148;
+  int n_ind = 2, next_ind = 0;  // streams for pictures that read no reference (intra pictures), used round-robin (B200_IND_STREAMS)
+  int intra_i_grid = 0;         // grid cap of k_intra for such pictures (0: one CTA per SM; B200_INTRA_I_GRID)
   int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
   int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
   // B200_TIMELINE=<file>: a CUDA event before and after every launch; the intervals of all streams (ms since the first launch)
@@ -443,6 +445,8 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
     en->pool.start(nt);
   }
   if (const char* e = getenv("B200_INTRA_CTAS")) en->intra_ctas = std::max(1, std::min(4, atoi(e)));
+  if (const char* e = getenv("B200_IND_STREAMS")) en->n_ind = std::max(1, std::min(3, atoi(e)));
+  if (const char* e = getenv("B200_INTRA_I_GRID")) en->intra_i_grid = std::max(0, atoi(e));
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
   en->tl_path = getenv("B200_TIMELINE");
@@ -520,6 +524,7 @@ extern "C" int b200_engine_set_streams(b200_engine* en, int n)
   if (rc) return rc;
   en->n_ctx = n;
   en->next_ctx = 0;
+  en->next_ind = 0;
   return B200_OK;
 }
 
@@ -645,7 +650,7 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
         maps.valid_slots |= 1u << i;
       }
       const uint32_t* tw = (const uint32_t*)(dbase + off[12]);  // tile words, then the batch table
-      TL("mc", (k_inter_pred_tma<<<std::min(L.n_batches, en->num_sms * en->mc_ctas), MCT_THREADS, sizeof(MctShared), st>>>(
+      TL("mc", (k_inter_pred_tma<<<std::min(L.n_batches, en->num_sms * en->mc_ctas), MCT_CTA_THREADS, sizeof(MctShared), st>>>(
                    dp, maps, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]), tw, tw + n_tiles, L.n_batches)));
     } else if (sizeof(P) == 1)
       k_inter_pred8<<<std::min((n_tiles + MC8_UNITS_PER_CTA - 1) / MC8_UNITS_PER_CTA, en->num_sms * 5), MC8_WARPS * 32, 0, st>>>(dp, refs, (const b200_pu*)(dbase + off[0]), (const b200_weight_entry*)(dbase + off[1]),
@@ -696,7 +701,8 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
       ra.n_task = L.n_task;
       int grid = (L.n_task + RC_WARPS - 1) / RC_WARPS;
       // an intra picture's DAG is latency-bound (one CTA per SM is as fast) and should leave room for the pictures it overlaps with
-      const int cap = en->num_sms * (L.ref_mask == 0 && en->n_ctx > 1 ? 1 : en->intra_ctas);
+      const bool background = L.ref_mask == 0 && en->n_ctx > 1;
+      const int cap = background ? (en->intra_i_grid ? en->intra_i_grid : en->num_sms) : en->num_sms * en->intra_ctas;
       if (grid > cap) grid = cap;
       TL("intra", (k_intra<P><<<grid, RC_THREADS, sizeof(IntraSmem<P>), st>>>(dp, ra)));
       en->launches += 2;
@@ -1192,7 +1198,11 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
 static int pick_ctx(b200_engine* en, bool independent)
 {
   if (en->timing || en->n_ctx <= 1) return 0;
-  if (independent && en->n_ctx < B200_MAX_CTX) return en->n_ctx;
+  if (independent && en->n_ctx + en->n_ind <= B200_MAX_CTX) {  // the long intra DAGs of consecutive intra pictures overlap each other too
+    const int k = en->n_ctx + en->next_ind;
+    en->next_ind = (en->next_ind + 1) % en->n_ind;
+    return k;
+  }
   const int k = en->next_ctx;
   en->next_ctx = (en->next_ctx + 1) % en->n_ctx;
   return k;

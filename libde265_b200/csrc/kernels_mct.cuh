@@ -81,6 +81,7 @@ struct MctGeom {
   int nco;              // luma column octets per tile (1 | 2)
   int nrp, nrpc;        // pair rows of the luma / chroma intermediate that pass 1 produces
   int nu, nuc;          // output row pairs per tile in pass 2 (luma, chroma)
+  int l2ntl, l2nu, l2nuc;  // log2 of ntl / nu / nuc (task decode by shifts)
   int n1l, n1c;         // pass-1 task counts (luma, chroma)
   int n2l, n2c;         // pass-2 task counts
   int lw_pitch, lw_slot, cw_off, cw_pitch, cw_plane, cw_slot;        // window region (bytes)
@@ -99,6 +100,7 @@ MCT_HD MctGeom mct_geom(int cls)
   g.nrpc = tall ? 6 : 4;
   g.nu = tall ? 8 : 4;
   g.nuc = tall ? 4 : 2;
+  g.l2ntl = g.small ? 5 : 4; g.l2nu = tall ? 3 : 2; g.l2nuc = tall ? 2 : 1;
   g.n1l = g.nrp * g.ntl * g.nco;
   g.n1c = g.nrpc * g.ntl * 2;
   g.n2l = g.ntiles * g.nco * g.nu;   // 8 columns x 2 rows per task
@@ -121,7 +123,7 @@ struct MctShared {
   MctTile info[2][MCT_MAX_TILES];
   MctGeom geom[2];
   Mc8Tables tab;
-  alignas(8) unsigned long long bar;
+  alignas(8) unsigned long long bar, bar_empty;
 };
 
 // ---- portable forms of the packed-integer instructions (host emulation) ----
@@ -182,7 +184,7 @@ MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const u
 {
   const int co = g.nco == 2 ? (t & 1) : 0;
   const int u = g.nco == 2 ? (t >> 1) : t;
-  const int tli = u % g.ntl, rp = u / g.ntl;
+  const int tli = u & (g.ntl - 1), rp = u >> g.l2ntl;
   const int tile = g.nl == 2 ? (tli >> 1) : tli, s = g.nl == 2 ? (tli & 1) : 0;
   const MctTile& ti = info[tile];
   if (!ti.valid || ti.missing[s] || 2 * rp >= ti.th + 7 || 8 * co >= ti.tw) return;
@@ -223,7 +225,7 @@ MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const u
 MCT_HD void mct_pass1_chroma(int t, const MctGeom& g, const MctTile* info, const uint8_t* win, uint32_t* interm, const Mc8Tables& tab)
 {
   const int pl = t & 1, u = t >> 1;
-  const int tli = u % g.ntl, rp = u / g.ntl;
+  const int tli = u & (g.ntl - 1), rp = u >> g.l2ntl;
   const int tile = g.nl == 2 ? (tli >> 1) : tli, s = g.nl == 2 ? (tli & 1) : 0;
   const MctTile& ti = info[tile];
   if (!ti.valid || ti.missing[s] || 2 * rp >= (ti.th >> 1) + 3) return;
@@ -312,16 +314,18 @@ MCT_HD void mct_vpair4(const uint32_t* src, int pitch, const uint32_t (&tv)[3], 
   }
 }
 
-MCT_HD uint32_t mct_weight4(const int* a, const int* b, const Mc8Weight& w, bool plain)
+MCT_HD uint32_t mct_weight4(const int* a, const int* b, const Mc8Weight& w)
 {
   uint32_t r = 0;
-  if (plain) {  // (a + 32) >> 6 resp. (a + b + 64) >> 7 (fallback-motion.cc:33-62): b is 0 for uni-prediction
 #pragma unroll
-    for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8((a[k] + b[k] + w.rnd) >> w.shift) << (8 * k);
-  } else {
+  for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8(((a[k] * w.w0 + b[k] * w.w1 + w.rnd) >> w.shift) + w.off) << (8 * k);
+  return r;
+}
+MCT_HD uint32_t mct_plain4(const int* a, const int* b, int rnd, int shift)  // (a + 32) >> 6 resp. (a + b + 64) >> 7 (fallback-motion.cc:33-62); b = 0 for uni
+{
+  uint32_t r = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8(((a[k] * w.w0 + b[k] * w.w1 + w.rnd) >> w.shift) + w.off) << (8 * k);
-  }
+  for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8((a[k] + b[k] + rnd) >> shift) << (8 * k);
   return r;
 }
 
@@ -341,7 +345,7 @@ MCT_HD void mct_store_row(uint8_t* dst, uint32_t w0, uint32_t w1, int nbytes)
 // ---- pass 2, luma: task -> (tile, column octet, output row pair); 8 columns x 2 rows ----
 MCT_HD void mct_pass2_luma(int t, const MctGeom& g, const MctTile* info, const uint32_t* interm, const Mc8Tables& tab, uint8_t* plane, int pitch)
 {
-  const int u = t % g.nu, tc = t / g.nu;
+  const int u = t & (g.nu - 1), tc = t >> g.l2nu;
   const int co = g.nco == 2 ? (tc & 1) : 0, tile = g.nco == 2 ? (tc >> 1) : tc;
   const MctTile& ti = info[tile];
   const int y0 = 2 * u;
@@ -364,18 +368,23 @@ MCT_HD void mct_pass2_luma(int t, const MctGeom& g, const MctTile* info, const u
   }
   const Mc8Weight w = ti.w[0];
   const int nbytes = ti.tw - 8 * co < 8 ? ti.tw - 8 * co : 8;
+  uint8_t* dst = plane + ti.dst_y + (size_t)y0 * pitch + 8 * co;
+  const int nr = ti.th - y0 < 2 ? 1 : 2;
+  if (ti.plain) {
 #pragma unroll
-  for (int i = 0; i < 2; i++) {
-    if (y0 + i >= ti.th) break;
-    const uint32_t w0 = mct_weight4(&v[0][i][0], &v[1][i][0], w, ti.plain), w1 = mct_weight4(&v[0][i][4], &v[1][i][4], w, ti.plain);
-    mct_store_row(plane + ti.dst_y + (size_t)(y0 + i) * pitch + 8 * co, w0, w1, nbytes);
+    for (int i = 0; i < 2; i++)
+      if (i < nr) mct_store_row(dst + (size_t)i * pitch, mct_plain4(&v[0][i][0], &v[1][i][0], w.rnd, w.shift), mct_plain4(&v[0][i][4], &v[1][i][4], w.rnd, w.shift), nbytes);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+      if (i < nr) mct_store_row(dst + (size_t)i * pitch, mct_weight4(&v[0][i][0], &v[1][i][0], w), mct_weight4(&v[0][i][4], &v[1][i][4], w), nbytes);
   }
 }
 
 // ---- pass 2, chroma: task -> (tile, plane, output row pair); 8 columns x 2 rows ----
 MCT_HD void mct_pass2_chroma(int t, const MctGeom& g, const MctTile* info, const uint32_t* interm, const Mc8Tables& tab, uint8_t* cb, uint8_t* cr, int pitch)
 {
-  const int u = t % g.nuc, tp_ = t / g.nuc;
+  const int u = t & (g.nuc - 1), tp_ = t >> g.l2nuc;
   const int pl = tp_ & 1, tile = tp_ >> 1;
   const MctTile& ti = info[tile];
   const int y0 = 2 * u, ch = ti.th >> 1, cwd = ti.tw >> 1;
@@ -397,12 +406,16 @@ MCT_HD void mct_pass2_chroma(int t, const MctGeom& g, const MctTile* info, const
     }
   }
   const Mc8Weight w = ti.w[1 + pl];
-  uint8_t* plane = pl ? cr : cb;
+  uint8_t* dst = (pl ? cr : cb) + ti.dst_c + (size_t)y0 * pitch;
+  const int nr = ch - y0 < 2 ? 1 : 2;
+  if (ti.plain) {
 #pragma unroll
-  for (int i = 0; i < 2; i++) {
-    if (y0 + i >= ch) break;
-    const uint32_t w0 = mct_weight4(&v[0][i][0], &v[1][i][0], w, ti.plain), w1 = mct_weight4(&v[0][i][4], &v[1][i][4], w, ti.plain);
-    mct_store_row(plane + ti.dst_c + (size_t)(y0 + i) * pitch, w0, w1, cwd);
+    for (int i = 0; i < 2; i++)
+      if (i < nr) mct_store_row(dst + (size_t)i * pitch, mct_plain4(&v[0][i][0], &v[1][i][0], w.rnd, w.shift), mct_plain4(&v[0][i][4], &v[1][i][4], w.rnd, w.shift), cwd);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+      if (i < nr) mct_store_row(dst + (size_t)i * pitch, mct_weight4(&v[0][i][0], &v[1][i][0], w), mct_weight4(&v[0][i][4], &v[1][i][4], w), cwd);
   }
 }
 
@@ -480,9 +493,21 @@ struct MctMaps {
 
 __device__ __forceinline__ uint32_t mct_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(MCT_THREADS) k_inter_pred_tma(DevPic pic, const __grid_constant__ MctMaps maps, const b200_pu* __restrict__ pus,
-                                                                const b200_weight_entry* __restrict__ wts, const uint32_t* __restrict__ tiles,
-                                                                const uint32_t* __restrict__ batches, int n_batches)
+// Warp roles: warps 0-3 (MCT_THREADS threads) compute; warp 4 is the PRODUCER: it decodes the next batch's tiles (two dependent
+// global loads per tile: tile word -> PU record) while the compute warps work, waits until pass 1 has consumed the current windows
+// (`empty` mbarrier), publishes the tile info and issues the TMA boxes (`full` mbarrier: 32 arrivals + the boxes' bytes).
+#define MCT_CTA_THREADS (MCT_THREADS + 32)
+__device__ __forceinline__ void mct_mbar_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+
+__global__ void __launch_bounds__(MCT_CTA_THREADS) k_inter_pred_tma(DevPic pic, const __grid_constant__ MctMaps maps, const b200_pu* __restrict__ pus,
+                                                                    const b200_weight_entry* __restrict__ wts, const uint32_t* __restrict__ tiles,
+                                                                    const uint32_t* __restrict__ batches, int n_batches)
 {
   extern __shared__ __align__(128) uint8_t mct_smem_raw[];
   MctShared& sm = *reinterpret_cast<MctShared*>(mct_smem_raw);
@@ -490,70 +515,82 @@ __global__ void __launch_bounds__(MCT_THREADS) k_inter_pred_tma(DevPic pic, cons
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_mc8);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.tab);
-    for (int i = tid; i < (int)(sizeof(Mc8Tables) / 4); i += MCT_THREADS) dst[i] = src[i];
+    for (int i = tid; i < (int)(sizeof(Mc8Tables) / 4); i += MCT_CTA_THREADS) dst[i] = src[i];
   }
-  const uint32_t bar = mct_smem(&sm.bar);
+  const uint32_t full = mct_smem(&sm.bar), empty = mct_smem(&sm.bar_empty);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(MCT_MAX_TL));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(MCT_MAX_TL));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const bool has_chroma = pic.chroma != 0;
 
-  // threads 0 .. 31: one tile-list item each (all 32 arrive on the barrier, whatever the class uses)
-  auto produce = [&](int batch, int buf) {
-    const uint32_t bw = batches[batch];
-    const MctGeom g = mct_geom((bw >> 28) & 7);
-    if (tid == 0) sm.geom[buf] = g;
-    int mi = -1;
-    MctBox bx;
-    if (tid < g.ntl) {
-      const int tile = g.nl == 2 ? (tid >> 1) : tid, s = g.nl == 2 ? (tid & 1) : 0;
-      bx = mct_decode_tile(tiles[(bw & 0x0FFFFFFF) + tile], s, pus, wts, maps.valid_slots, pic, &sm.info[buf][tile]);
-      mi = bx.active ? maps.index_of_slot[bx.slot] : -1;
-    }
-    if (mi >= 0) {
-      const int skew = tid & 3, k = g.small;
-      const uint32_t bytes = (k ? MCT_LWS_PITCH * MCT_LWS_ROWS : MCT_LWB_PITCH * MCT_LWB_ROWS) +
-                             (has_chroma ? (k ? 2 * MCT_CWS_PITCH * MCT_CWS_ROWS : 2 * MCT_CWB_PITCH * MCT_CWB_ROWS) : 0);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the windows were read through the generic proxy in pass 1
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                       mct_smem(sm.win + tid * g.lw_slot)),
-                   "l"(&maps.luma[k][mi]), "r"(bx.lx + B200_PAD_X), "r"(bx.ly + B200_PAD_Y - skew), "r"(bar)
-                   : "memory");
-      if (has_chroma)
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                         mct_smem(sm.win + g.cw_off + tid * g.cw_slot)),
-                     "l"(&maps.chroma[k][mi]), "r"(bx.cx + B200_PAD_CX), "r"(bx.cy + B200_PAD_CY - skew), "r"(0), "r"(bar)
+  if (tid >= MCT_THREADS) {
+    // ================= producer warp: lane = tile-list item =================
+    const int lane = tid - MCT_THREADS;
+    int it = 0;
+    for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x, it++) {
+      const uint32_t bw = batches[batch];
+      const MctGeom g = mct_geom((bw >> 28) & 7);
+      MctTile mine;  // decoded into registers / local memory first: the shared buffers may still be in use
+      MctBox bx;
+      bx.active = 0;
+      const int tile = g.nl == 2 ? (lane >> 1) : lane, s = g.nl == 2 ? (lane & 1) : 0;
+      if (lane < g.ntl) bx = mct_decode_tile(tiles[(bw & 0x0FFFFFFF) + tile], s, pus, wts, maps.valid_slots, pic, &mine);
+      const int mi = bx.active ? maps.index_of_slot[bx.slot] : -1;
+      // the windows (and info[it & 1], last read in pass 2 of batch it-2) are free once pass 1 of the previous batch is done
+      if (it > 0) mct_mbar_wait(empty, (it - 1) & 1);
+      MctTile* dst = &sm.info[it & 1][tile];
+      if (lane < g.ntl) {
+        if (s == 0) {  // slot-0 lane owns the common fields; with two lists the slot-1 lane adds its own
+          dst->dst_y = mine.dst_y; dst->dst_c = mine.dst_c; dst->tw = mine.tw; dst->th = mine.th; dst->nl = mine.nl; dst->valid = mine.valid;
+          dst->plain = mine.plain;
+#pragma unroll
+          for (int c = 0; c < 3; c++) dst->w[c] = mine.w[c];
+        }
+        dst->xo[s] = mine.xo[s]; dst->hidx[s] = mine.hidx[s]; dst->yf[s] = mine.yf[s]; dst->sh6[s] = mine.sh6[s];
+        dst->cxo[s] = mine.cxo[s]; dst->chidx[s] = mine.chidx[s]; dst->cyf[s] = mine.cyf[s]; dst->csh6[s] = mine.csh6[s];
+        dst->missing[s] = mine.missing[s];
+      }
+      if (lane == 0) sm.geom[it & 1] = g;
+      if (mi >= 0) {
+        const int skew = lane & 3, k = g.small;
+        const uint32_t bytes = (k ? MCT_LWS_PITCH * MCT_LWS_ROWS : MCT_LWB_PITCH * MCT_LWB_ROWS) +
+                               (has_chroma ? (k ? 2 * MCT_CWS_PITCH * MCT_CWS_ROWS : 2 * MCT_CWB_PITCH * MCT_CWB_ROWS) : 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the windows were read through the generic proxy in pass 1
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                         mct_smem(sm.win + lane * g.lw_slot)),
+                     "l"(&maps.luma[k][mi]), "r"(bx.lx + B200_PAD_X), "r"(bx.ly + B200_PAD_Y - skew), "r"(full)
                      : "memory");
-    } else {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        if (has_chroma)
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                           mct_smem(sm.win + g.cw_off + lane * g.cw_slot)),
+                       "l"(&maps.chroma[k][mi]), "r"(bx.cx + B200_PAD_CX), "r"(bx.cy + B200_PAD_CY - skew), "r"(0), "r"(full)
+                       : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+      }
     }
-  };
+    return;
+  }
 
-  int batch = blockIdx.x;
-  if (batch < n_batches && tid < MCT_MAX_TL) produce(batch, 0);
-  for (int it = 0; batch < n_batches; batch += gridDim.x, it++) {
-    {  // wait for this batch's windows (and the producers' tile info)
-      const uint32_t parity = it & 1;
-      uint32_t done;
-      do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-      } while (!done);
-    }
+  // ================= compute warps =================
+  int it = 0;
+  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x, it++) {
+    mct_mbar_wait(full, it & 1);  // this batch's windows and tile info
     const MctTile* info = sm.info[it & 1];
     const MctGeom g = sm.geom[it & 1];
     for (int t = tid; t < g.n1l; t += MCT_THREADS) mct_pass1_luma(t, g, info, sm.win, sm.interm, sm.tab);
     if (has_chroma)
       for (int t = tid; t < g.n1c; t += MCT_THREADS) mct_pass1_chroma(t, g, info, sm.win, sm.interm, sm.tab);
-    __syncthreads();
-    const int next = batch + gridDim.x;
-    if (next < n_batches && tid < MCT_MAX_TL) produce(next, (it + 1) & 1);  // the windows are free: fetch ahead during pass 2
+    asm volatile("bar.sync 1, %0;" ::"n"(MCT_THREADS) : "memory");
+    if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty) : "memory");  // the windows are free: the producer fetches ahead
     for (int t = tid; t < g.n2l; t += MCT_THREADS) mct_pass2_luma(t, g, info, sm.interm, sm.tab, pic.cur[0], pic.pitch[0]);
     if (has_chroma)
       for (int t = tid; t < g.n2c; t += MCT_THREADS) mct_pass2_chroma(t, g, info, sm.interm, sm.tab, pic.cur[1], pic.cur[2], pic.pitch[1]);
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(MCT_THREADS) : "memory");
   }
 }
 #endif  // __CUDACC__

@@ -30,7 +30,12 @@ def main():
     for k, (n, t) in sorted(per.items(), key=lambda kv: -kv[1][1]):
         print(f"{k:12s} {n:8d} {1e3 * t / n:9.1f} {t:8.3f} {t / span:10.2f}")
     # concurrency profile (launch intervals and picture intervals)
-    for what, key in (("launches", lambda r: (r[0], r[1], r[2], r[3])), ("pictures", lambda r: (r[0], r[2]))):
+    inst, last = {}, {}
+    for i, r in enumerate(sorted(rows, key=lambda r: r[3])):  # picture instance = consecutive launches of one poc on one stream
+        if last.get(r[0], (None, None))[0] != r[2]:
+            last[r[0]] = (r[2], i)
+        inst[(r[0], r[1], r[2], r[3])] = (r[0], last[r[0]][1])
+    for what, key in (("launches", lambda r: (r[0], r[1], r[2], r[3])), ("pictures", lambda r: inst[(r[0], r[1], r[2], r[3])])):
         iv = {}
         for r in rows:
             k = key(r)
@@ -42,7 +47,7 @@ def main():
             hist[cur] += t - last
             cur, last = cur + d, t
         tot = sum(hist.values())
-        print(f"{what} in flight: " + "  ".join(f"{n}: {100 * hist[n] / tot:.0f}%" for n in sorted(hist) if hist[n] > 0))
+        print(f"{what} in flight: " + "  ".join(f"{n}: {100 * hist[n] / tot:.0f}%" for n in sorted(hist) if hist[n] / tot >= 0.005))
     # ASCII timeline
     cols = 160
     glyph = {"mc": "M", "residual": "r", "mark": ".", "intra": "I", "deblock_v": "d", "deblock_h": "d", "sao_prep": ".", "sao": "s", "extend": "x"}
