@@ -248,6 +248,14 @@ B200_API int  b200_engine_read_slot(b200_engine*, int slot, void* const planes[3
 /* Async variant + explicit wait (lets the host parse picture N+1 meanwhile). */
 B200_API int  b200_engine_read_slot_async(b200_engine*, int slot, void* const planes[3], const size_t strides[3]);
 B200_API int  b200_engine_sync(b200_engine*);
+/* Blocks until everything issued so far that writes or reads `slot` has finished (the picture in it is complete and every
+ * b200_engine_read_slot_async of it has landed), without waiting for later pictures in other slots: what a decoder calls when it
+ * hands a picture to the application (push_picture_to_output_queue / de265_get_next_picture, decctx.cc:1842-1881). */
+B200_API int  b200_engine_wait_slot(b200_engine*, int slot);
+/* Page-locked host memory for picture planes that b200_engine_read_slot_async fills without staging (the reference-side binding
+ * installs them through libde265's de265_image_allocation plug-in, de265.h:350-365). */
+B200_API void* b200_host_alloc(size_t bytes);
+B200_API void  b200_host_free(void* p);
 
 /* Device pointers of a slot (zero-copy consumers, bench). */
 B200_API int  b200_engine_slot_device_planes(b200_engine*, int slot, void* planes[3], size_t strides[3]);
@@ -263,7 +271,7 @@ B200_API int  b200_engine_timing_sum(b200_engine*, float ms[6], int* n_pictures,
 /* Number of kernels this engine has launched so far (bench.py "gpu_launches"). */
 B200_API uint64_t b200_engine_launch_count(const b200_engine*);
 
-/* Picture-level pipelining.  The engine issues pictures round-robin onto `n` CUDA streams (default 4, 1..8;
+/* Picture-level pipelining.  The engine issues pictures round-robin onto `n` CUDA streams (default 8, 1..12;
  * environment B200_STREAMS overrides the default) and orders them with per-slot events: a picture waits for the
  * writers of the slots it references and for all earlier readers / writers of its destination slot, so pictures
  * that do not depend on each other overlap on the GPU, in the spirit of libde265 decoding several images at once

@@ -4,8 +4,14 @@
 // This file is compiled INTO libde265 (it includes libde265's internal headers).  It contains no
 // reconstruction arithmetic: it only reads the parser's state (thread_context, slice header, image
 // metadata) at the moment the reference would have reconstructed, and forwards it through the C ABI
-// in include/b200hevc.h.  Single decode thread only (de265_start_worker_threads must not be used
-// while attached) — WPP-parallel recording is a "next" item.
+// in include/b200hevc.h.  Single decode thread only: attaching fails while worker threads run, and a picture decoded with
+// worker threads started later is flagged as damaged instead of being recorded concurrently.
+//
+// Two ways to use it: (a) de265_b200_attach with an application-provided sink (tests, bench.py), or (b) the BUILT-IN backend
+// (de265_b200_enable, selected by DE265_DECODER_PARAM_ACCELERATION_CODE = de265_acceleration_B200): it owns a B200 engine,
+// submits every picture asynchronously at picture end, reads it back into page-locked picture planes (installed through
+// libde265's image allocation plug-in) and waits for that transfer only when the picture is handed to the application, so the
+// host parses picture N+1 while the GPU reconstructs picture N.
 
 #include "libde265_hooks.h"
 
@@ -29,15 +35,28 @@ void derive_boundaryStrength(de265_image* img, bool vertical, int yStart, int yE
 
 namespace {
 
+struct builtin_backend;
 struct hook_state {
   de265_b200_sink sink = nullptr;
+  de265_b200_wait wait = nullptr;
+  de265_b200_fill fill = nullptr;
   void* user = nullptr;
   b200_recorder* rec = nullptr;
   const de265_image* cur_img = nullptr;
   uint32_t cur_id = 0;
   bool open = false;
+  bool failed = false;  // a recorder call failed or the picture uses something the backend does not implement
   std::map<std::tuple<const void*, int, int, int>, int> weight_cache;
+  std::map<const de265_image*, int> pending;  // pictures whose read-back is in flight -> DPB slot
+  builtin_backend* builtin = nullptr;
 };
+
+void fail_picture(hook_state* st, const char* why)
+{
+  if (!st->failed) fprintf(stderr, "b200 hook: picture not reconstructed: %s\n", why);
+  st->failed = true;
+}
+#define REC(call) do { if ((call) < 0) fail_picture(st, #call); } while (0)
 
 inline hook_state* state_of(base_context* ctx) { return static_cast<hook_state*>(ctx->b200_state); }
 
@@ -69,10 +88,16 @@ void begin_picture_if_needed(hook_state* st, base_context* ctx, de265_image* img
   if (sps.scaling_list_enable_flag) p.flags |= B200_PIC_SCALING_LIST;
   p.pps_cb_qp_offset = (int8_t)pps.pic_cb_qp_offset;
   p.pps_cr_qp_offset = (int8_t)pps.pic_cr_qp_offset;
-  int slot = dpb_slot_of(ctx, img);
+  st->failed = false;
+  const int slot = dpb_slot_of(ctx, img);
+  if (slot < 0) fail_picture(st, "the picture is not in the DPB (or beyond B200_MAX_SLOTS)");
   p.dst_slot = (uint8_t)(slot < 0 ? 0 : slot);
   p.poc = img->PicOrderCntVal;
-  b200_rec_begin_picture(st->rec, &p);
+  if (pps.range_extension.cross_component_prediction_enabled_flag) fail_picture(st, "RExt cross-component prediction is not implemented");
+  if (sps.chroma_format_idc > 1) fail_picture(st, "4:2:2 / 4:4:4 are not implemented on the device");
+  if (decoder_context* dc = dynamic_cast<decoder_context*>(ctx))
+    if (dc->get_num_worker_threads() > 0) fail_picture(st, "worker threads are running (the recorder is single-threaded)");
+  REC(b200_rec_begin_picture(st->rec, &p));
   if (sps.scaling_list_enable_flag) {
     // pps.scaling_list holds the active factors (transform.cc:502-506)
     std::vector<uint8_t> f(B200_SCALING_FACTOR_BYTES);
@@ -81,7 +106,7 @@ void begin_picture_if_needed(hook_state* st, base_context* ctx, de265_image* img
     memcpy(d, pps.scaling_list.ScalingFactor_Size1, 6 * 64); d += 6 * 64;
     memcpy(d, pps.scaling_list.ScalingFactor_Size2, 6 * 256); d += 6 * 256;
     memcpy(d, pps.scaling_list.ScalingFactor_Size3, 6 * 1024);
-    b200_rec_set_scaling_factors(st->rec, f.data());
+    REC(b200_rec_set_scaling_factors(st->rec, f.data()));
   }
   st->cur_img = img;
   st->cur_id = img->get_ID();
@@ -156,7 +181,7 @@ uint64_t intra_avail_mask(const de265_image* img, int xB, int yB, int nT, int cI
 
 }  // namespace
 
-extern "C" void de265_b200_attach(void* de265_decoder_ctx, de265_b200_sink sink, void* user)
+extern "C" int de265_b200_attach(void* de265_decoder_ctx, de265_b200_sink sink, void* user)
 {
   decoder_context* ctx = static_cast<decoder_context*>(de265_decoder_ctx);
   hook_state* st = state_of(ctx);
@@ -166,15 +191,25 @@ extern "C" void de265_b200_attach(void* de265_decoder_ctx, de265_b200_sink sink,
       delete st;
       ctx->b200_state = nullptr;
     }
-    return;
+    return B200_OK;
   }
+  if (ctx->get_num_worker_threads() > 0) return B200_ERR_UNSUPPORTED;  // recording is single-threaded (slice.cc hook sites run under WPP tasks)
   if (!st) {
     st = new hook_state();
-    b200_rec_create(&st->rec);
+    if (b200_rec_create(&st->rec) < 0) { delete st; return B200_ERR_NOMEM; }
     ctx->b200_state = st;
   }
   st->sink = sink;
   st->user = user;
+  return B200_OK;
+}
+
+extern "C" void de265_b200_set_callbacks(void* de265_decoder_ctx, de265_b200_wait wait, de265_b200_fill fill)
+{
+  hook_state* st = state_of(static_cast<decoder_context*>(de265_decoder_ctx));
+  if (!st) return;
+  st->wait = wait;
+  st->fill = fill;
 }
 
 bool b200_hook_decode_TU(thread_context* tctx, int x0, int y0, int nT, int cIdx, int cuPredMode, bool cbf)
@@ -236,7 +271,7 @@ bool b200_hook_decode_TU(thread_context* tctx, int x0, int y0, int nT, int cIdx,
     }
     n = tctx->nCoeff[cIdx];
   }
-  b200_rec_add_tu(st->rec, &tu, tctx->coeffList[cIdx], tctx->coeffPos[cIdx], n);
+  REC(b200_rec_add_tu(st->rec, &tu, tctx->coeffList[cIdx], tctx->coeffPos[cIdx], n));
   return true;
 }
 
@@ -263,7 +298,7 @@ void b200_hook_pcm(thread_context* tctx, int x0, int y0, int w, int h, int cIdx)
   tu.log2_size = (uint8_t)Log2(w);
   tu.cidx = (uint8_t)cIdx;
   tu.flags = B200_TU_PCM;
-  b200_rec_add_tu(st->rec, &tu, lv.data(), ps.data(), w * h);
+  REC(b200_rec_add_tu(st->rec, &tu, lv.data(), ps.data(), w * h));
 }
 
 bool b200_hook_inter_pred(base_context* ctx, const slice_segment_header* shdr, de265_image* img, int xP, int yP, int nPbW, int nPbH,
@@ -334,12 +369,13 @@ bool b200_hook_inter_pred(base_context* ctx, const slice_segment_header* shdr, d
         }
       }
       wi = b200_rec_add_weights(st->rec, &we);
+      if (wi < 0) { fail_picture(st, "b200_rec_add_weights"); wi = 0; }
       st->weight_cache[key] = wi;
     }
     pu.flags |= B200_PU_WEIGHTED;
     pu.wt_idx = (uint16_t)wi;
   }
-  b200_rec_add_pu(st->rec, &pu);
+  REC(b200_rec_add_pu(st->rec, &pu));
   return true;
 }
 
@@ -364,7 +400,7 @@ bool b200_hook_picture_done(decoder_context* ctx, de265_image* img)
     if (sh->slice_loop_filter_across_slices_enabled_flag) s.flags |= B200_SLICE_LF_ACROSS_SLICES;
     if (sh->slice_sao_luma_flag) s.flags |= B200_SLICE_SAO_LUMA;
     if (sh->slice_sao_chroma_flag) s.flags |= B200_SLICE_SAO_CHROMA;
-    b200_rec_add_slice(st->rec, &s);
+    REC(b200_rec_add_slice(st->rec, &s));
   }
   for (int cy = 0; cy < sps.PicHeightInCtbsY; cy++)
     for (int cx = 0; cx < sps.PicWidthInCtbsY; cx++) {
@@ -378,7 +414,7 @@ bool b200_hook_picture_done(decoder_context* ctx, de265_image* img)
         c.sao_band_pos[k] = si->sao_band_position[k];
         for (int j = 0; j < 4; j++) c.sao_offset[k][j] = si->saoOffsetVal[k][j];
       }
-      b200_rec_set_ctb(st->rec, cx, cy, &c);
+      REC(b200_rec_set_ctb(st->rec, cx, cy, &c));
     }
 
   // QP / no-filter maps at 8x8 granularity (deblock.cc:513-515,576-592; sao.cc:112-117)
@@ -391,7 +427,7 @@ bool b200_hook_picture_done(decoder_context* ctx, de265_image* img)
     }
 
   // edge flags + boundary strength on the host (deblock.cc:132-383), both directions
-  b200_picture pic;
+  b200_picture pic{};
   bool deblock = !ctx->param_disable_deblocking && derive_edgeFlags(img);
   if (deblock) {
     uint8_t* bs = b200_rec_bs_map(st->rec);
@@ -402,8 +438,12 @@ bool b200_hook_picture_done(decoder_context* ctx, de265_image* img)
     for (int y = 0; y < h4; y += 2)
       for (int x = 0; x < w4; x++) bs[x + y * w4] |= (img->get_deblk_bS(x * 4, y * 4) & 3) << 2;
   }
-  b200_rec_end_picture(st->rec, &pic);
+  REC(b200_rec_end_picture(st->rec, &pic));
   st->open = false;
+  if (st->failed) {  // nothing trustworthy to hand to the backend: the picture stays as it is and is flagged (decctx.cc:615)
+    img->integrity = INTEGRITY_DECODING_ERRORS;
+    return true;
+  }
   if (!deblock) pic.params.flags |= B200_PIC_SKIP_DEBLOCK;
   if (ctx->param_disable_sao) pic.params.flags |= B200_PIC_SKIP_SAO;
 
@@ -411,6 +451,148 @@ bool b200_hook_picture_done(decoder_context* ctx, de265_image* img)
   size_t strides[3];
   for (int c = 0; c < 3; c++) strides[c] = (size_t)img->get_image_stride(c) * ((img->get_bit_depth(c) + 7) / 8);
   if (img->get_chroma_format() == de265_chroma_mono) planes[1] = planes[2] = nullptr;
-  st->sink(st->user, &pic, planes, strides);
+  const int rc = st->sink(st->user, &pic, planes, strides);
+  if (rc < 0) img->integrity = INTEGRITY_DECODING_ERRORS;
+  else if (rc == DE265_B200_SINK_PENDING) {
+    st->pending[img] = pic.params.dst_slot;
+    if (ctx->param_sei_check_hash) b200_hook_wait_image(ctx, img);  // the decoded-picture-hash check reads the host planes right away
+  }
   return true;
+}
+
+void b200_hook_wait_image(decoder_context* ctx, const de265_image* img)
+{
+  hook_state* st = state_of(ctx);
+  if (!st || !img) return;
+  auto it = st->pending.find(img);
+  if (it == st->pending.end()) return;
+  if (st->wait && st->wait(st->user, it->second) < 0) const_cast<de265_image*>(img)->integrity = INTEGRITY_DECODING_ERRORS;
+  st->pending.erase(it);
+}
+
+// libde265 fills a synthesised reference picture on the host (decctx.cc:1294-1318): mirror it into the backend's DPB slot,
+// otherwise pictures predicted from it would read whatever the slot held before.
+void b200_hook_unavailable_reference(decoder_context* ctx, de265_image* img)
+{
+  hook_state* st = state_of(ctx);
+  if (!st || !st->fill || !img) return;
+  const int slot = dpb_slot_of(ctx, img);
+  if (slot < 0) return;
+  const seq_parameter_set& sps = img->get_sps();
+  b200_pic_params p{};
+  p.width = (uint16_t)sps.pic_width_in_luma_samples;
+  p.height = (uint16_t)sps.pic_height_in_luma_samples;
+  p.chroma_format_idc = (uint8_t)sps.chroma_format_idc;
+  p.bit_depth_luma = (uint8_t)sps.BitDepth_Y;
+  p.bit_depth_chroma = (uint8_t)sps.BitDepth_C;
+  p.log2_ctb_size = sps.Log2CtbSizeY;
+  p.dst_slot = (uint8_t)slot;
+  st->fill(st->user, slot, &p, 1 << (sps.BitDepth_Y - 1), 1 << (sps.BitDepth_C - 1));
+}
+
+// ---- the built-in backend -------------------------------------------------------------------------------------
+namespace {
+struct builtin_backend {
+  b200_engine* eng = nullptr;
+  std::multimap<size_t, void*> pool;  // free page-locked planes by size: libde265 allocates the planes of every new picture
+  std::map<void*, size_t> live;
+};
+
+int builtin_sink(void* user, const b200_picture* pic, void* const planes[3], const size_t strides[3])
+{
+  builtin_backend* be = static_cast<builtin_backend*>(user);
+  int rc = b200_engine_submit_picture(be->eng, pic);
+  if (rc < 0) { fprintf(stderr, "b200 backend: %s\n", b200_last_error()); return rc; }
+  rc = b200_engine_read_slot_async(be->eng, pic->params.dst_slot, planes, strides);
+  if (rc < 0) { fprintf(stderr, "b200 backend: %s\n", b200_last_error()); return rc; }
+  return DE265_B200_SINK_PENDING;
+}
+int builtin_wait(void* user, int slot) { return b200_engine_wait_slot(static_cast<builtin_backend*>(user)->eng, slot); }
+int builtin_fill(void* user, int slot, const b200_pic_params* p, int vy, int vc)
+{
+  return b200_engine_fill_slot(static_cast<builtin_backend*>(user)->eng, slot, p, vy, vc);
+}
+
+// de265_image_allocation plug-in (de265.h:350-365): page-locked planes with the reference's own layout rules (image.cc:110-160)
+int builtin_get_buffer(de265_decoder_context*, de265_image_spec* spec, de265_image* img, void* userdata)
+{
+  builtin_backend* be = static_cast<builtin_backend*>(userdata);
+  const int bpp_y = (img->BitDepth_Y + 7) / 8, bpp_c = (img->BitDepth_C + 7) / 8;
+  const int align = spec->alignment > 0 ? spec->alignment : 16;
+  const bool mono = img->get_chroma_format() == de265_chroma_mono;
+  const int cw = mono ? 0 : spec->width / img->SubWidthC, chh = mono ? 0 : spec->height / img->SubHeightC;
+  const int ls = (spec->width + align - 1) / align * align, cs = mono ? 0 : (cw + align - 1) / align * align;
+  const size_t sizes[3] = {(size_t)ls * bpp_y * spec->height + 64, (size_t)cs * bpp_c * chh + 64, (size_t)cs * bpp_c * chh + 64};
+  void* p[3] = {nullptr, nullptr, nullptr};
+  for (int c = 0; c < (mono ? 1 : 3); c++) {
+    auto it = be->pool.find(sizes[c]);
+    if (it != be->pool.end()) { p[c] = it->second; be->pool.erase(it); }
+    else p[c] = b200_host_alloc(sizes[c]);
+    if (!p[c]) {
+      for (int k = 0; k < c; k++) { be->live.erase(p[k]); be->pool.emplace(sizes[k], p[k]); }
+      return 0;
+    }
+    be->live[p[c]] = sizes[c];
+  }
+  img->set_image_plane(0, (uint8_t*)p[0], ls, nullptr);
+  img->set_image_plane(1, (uint8_t*)p[1], cs, nullptr);
+  img->set_image_plane(2, (uint8_t*)p[2], cs, nullptr);
+  return 1;
+}
+void builtin_release_buffer(de265_decoder_context*, de265_image* img, void* userdata)
+{
+  builtin_backend* be = static_cast<builtin_backend*>(userdata);
+  for (int c = 0; c < 3; c++) {
+    void* p = img->get_image_plane(c);
+    auto it = be->live.find(p);
+    if (it == be->live.end()) continue;
+    be->pool.emplace(it->second, p);  // kept for the next picture: page-locking is expensive
+    be->live.erase(it);
+  }
+}
+}  // namespace
+
+extern "C" int de265_b200_enable(void* de265_decoder_ctx, int device)
+{
+  decoder_context* ctx = static_cast<decoder_context*>(de265_decoder_ctx);
+  if (hook_state* st = state_of(ctx))
+    if (st->builtin) return B200_OK;
+  builtin_backend* be = new builtin_backend();
+  int rc = b200_engine_create(&be->eng, device);
+  if (rc < 0) { delete be; return rc; }
+  rc = de265_b200_attach(ctx, builtin_sink, be);
+  if (rc < 0) { b200_engine_destroy(be->eng); delete be; return rc; }
+  de265_b200_set_callbacks(ctx, builtin_wait, builtin_fill);
+  state_of(ctx)->builtin = be;
+  de265_image_allocation alloc = {builtin_get_buffer, builtin_release_buffer};
+  ctx->set_image_allocation_functions(&alloc, be);
+  return B200_OK;
+}
+
+extern "C" void de265_b200_disable(void* de265_decoder_ctx)
+{
+  decoder_context* ctx = static_cast<decoder_context*>(de265_decoder_ctx);
+  hook_state* st = state_of(ctx);
+  if (!st || !st->builtin) return;
+  builtin_backend* be = st->builtin;
+  b200_engine_sync(be->eng);
+  de265_b200_attach(ctx, nullptr, nullptr);
+  b200_engine_destroy(be->eng);
+  be->eng = nullptr;
+  // The allocation plug-in and `be` stay: pictures still alive were allocated through it and are released through it
+  // (image.cc release() passes the context's CURRENT userdata); their page-locked planes return to the pool.
+}
+
+// DE265_DECODER_PARAM_ACCELERATION_CODE = de265_acceleration_B200 (de265.cc:576-578 -> base_context::set_acceleration_functions)
+void b200_hook_set_acceleration(base_context* bctx, int level)
+{
+  decoder_context* ctx = dynamic_cast<decoder_context*>(bctx);
+  if (!ctx) return;
+  if (level == DE265_ACCELERATION_B200) {
+    const char* dev = getenv("B200_DEVICE");
+    const int rc = de265_b200_enable(ctx, dev ? atoi(dev) : 0);
+    if (rc < 0) fprintf(stderr, "libde265: de265_acceleration_B200 unavailable (%s); the host tables stay in place\n", b200_last_error());
+  } else if (hook_state* st = state_of(ctx)) {
+    if (st->builtin) de265_b200_disable(ctx);
+  }
 }

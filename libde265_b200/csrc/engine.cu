@@ -306,6 +306,8 @@ struct b200_engine {
   SlotSync ssync[B200_MAX_SLOTS];
   HostPool pool;
   int num_sms = 148;
+  long long slot_depth[B200_MAX_SLOTS] = {}, tail_depth[B200_MAX_CTX] = {}, key_depth = 0;  // pick_ctx: dependency depths
+  bool sched_rr = false;        // B200_SCHED=rr: plain round-robin placement (A/B measurements)
   int n_ind = 2, next_ind = 0;  // streams for pictures that read no reference (intra pictures), used round-robin (B200_IND_STREAMS)
   int intra_i_grid = 0;         // grid cap of k_intra for such pictures (0: one CTA per SM; B200_INTRA_I_GRID)
   int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
@@ -438,13 +440,14 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   en->device = device;
   int rc = init_tables(device);
   if (rc) { delete en; return rc; }
-  en->n_ctx = 4;
+  en->n_ctx = 8;
   {
     int nt = 8;
     if (const char* e = getenv("B200_HOST_THREADS")) nt = std::max(0, std::min(16, atoi(e)));
     en->pool.start(nt);
   }
   if (const char* e = getenv("B200_INTRA_CTAS")) en->intra_ctas = std::max(1, std::min(4, atoi(e)));
+  if (const char* e = getenv("B200_SCHED")) en->sched_rr = !strcmp(e, "rr");
   if (const char* e = getenv("B200_IND_STREAMS")) en->n_ind = std::max(1, std::min(3, atoi(e)));
   if (const char* e = getenv("B200_INTRA_I_GRID")) en->intra_i_grid = std::max(0, atoi(e));
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
@@ -1195,16 +1198,48 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
 // Per-stage timing needs the stages of consecutive pictures not to overlap: one stream while it is on.
 // Pictures that read no reference (intra pictures) go to a stream of their own: nothing queued in front of them, so the
 // long intra DAG of the next intra period's I picture runs in the background of the current period's P/B pictures.
-static int pick_ctx(b200_engine* en, bool independent)
+//
+// The other pictures are placed by DEPENDENCY DEPTH (depth = 1 + the largest depth among the pictures in the slots it reads): a
+// stream is a FIFO, so a picture queued behind an unrelated picture that still waits for ITS references is held up for nothing
+// (round-robin puts the next GOP's key picture behind the current GOP's leaf B pictures: 16 picture times per 4 GOPs instead
+// of 7).  A picture goes to the stream whose last picture has the largest depth still below its own (that picture finishes
+// before this one could start anyway); if there is none, to the stream whose last picture is the shallowest.
+static uint32_t ref_mask_of(const b200_picture* pic)
+{
+  uint32_t m = 0;
+  for (uint32_t i = 0; i < pic->n_pu; i++) {
+    const b200_pu& pu = pic->pus[i];
+    if ((pu.flags & B200_PU_PRED_L0) && pu.ref_slot[0] >= 0 && pu.ref_slot[0] < B200_MAX_SLOTS) m |= 1u << pu.ref_slot[0];
+    if ((pu.flags & B200_PU_PRED_L1) && pu.ref_slot[1] >= 0 && pu.ref_slot[1] < B200_MAX_SLOTS) m |= 1u << pu.ref_slot[1];
+  }
+  return m;
+}
+
+static int pick_ctx(b200_engine* en, uint32_t ref_mask, int dst_slot)
 {
   if (en->timing || en->n_ctx <= 1) return 0;
-  if (independent && en->n_ctx + en->n_ind <= B200_MAX_CTX) {  // the long intra DAGs of consecutive intra pictures overlap each other too
-    const int k = en->n_ctx + en->next_ind;
+  long long depth = 1;
+  for (int r = 0; r < B200_MAX_SLOTS; r++)
+    if ((ref_mask >> r) & 1) depth = std::max(depth, en->slot_depth[r] + 1);
+  int k;
+  if (ref_mask == 0 && en->n_ctx + en->n_ind <= B200_MAX_CTX) {  // the long intra DAGs of consecutive intra pictures overlap each other too
+    k = en->n_ctx + en->next_ind;
     en->next_ind = (en->next_ind + 1) % en->n_ind;
-    return k;
+    depth = en->key_depth + 1;  // what references it comes after the pictures already queued
+  } else if (en->sched_rr) {
+    k = en->next_ctx;
+    en->next_ctx = (en->next_ctx + 1) % en->n_ctx;
+  } else {
+    int best = -1, shallow = 0;
+    for (int c = 0; c < en->n_ctx; c++) {
+      if (en->tail_depth[c] < depth && (best < 0 || en->tail_depth[c] > en->tail_depth[best])) best = c;
+      if (en->tail_depth[c] < en->tail_depth[shallow]) shallow = c;
+    }
+    k = best >= 0 ? best : shallow;
   }
-  const int k = en->next_ctx;
-  en->next_ctx = (en->next_ctx + 1) % en->n_ctx;
+  en->tail_depth[k] = depth;
+  if (dst_slot >= 0 && dst_slot < B200_MAX_SLOTS) en->slot_depth[dst_slot] = depth;
+  en->key_depth = std::max(en->key_depth, depth);
   return k;
 }
 
@@ -1214,7 +1249,7 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
   CU(cudaSetDevice(en->device));
   PicLayout L;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const int k = pick_ctx(en, pic->n_pu == 0);
+  const int k = pick_ctx(en, ref_mask_of(pic), pic->params.dst_slot);
   PipeCtx& cx = en->ctx[k];
   StagingSet& ss = cx.stage[cx.cur_stage];
   cx.cur_stage ^= 1;
@@ -1258,7 +1293,7 @@ extern "C" int b200_engine_run_prepared(b200_engine* en, b200_prepared* pp)
 {
   if (!en || !pp) return set_err(B200_ERR_INVALID, "null argument");
   CU(cudaSetDevice(en->device));
-  return run_layout(en, pick_ctx(en, pp->L.ref_mask == 0), pp->L, pp->dev, nullptr);
+  return run_layout(en, pick_ctx(en, pp->L.ref_mask, pp->L.params.dst_slot), pp->L, pp->dev, nullptr);
 }
 
 extern "C" void b200_engine_free_prepared(b200_engine* en, b200_prepared* pp)
@@ -1364,6 +1399,28 @@ extern "C" int b200_engine_read_slot(b200_engine* en, int slot, void* const plan
   const int k = en->ssync[slot].writer >= 0 ? en->ssync[slot].writer : 0;
   CU(cudaStreamSynchronize(en->ctx[k].stream));
   return B200_OK;
+}
+
+extern "C" int b200_engine_wait_slot(b200_engine* en, int slot)
+{
+  if (!en || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(en->device));
+  SlotSync& ss = en->ssync[slot];
+  if (ss.writer >= 0) CU(cudaEventSynchronize(ss.written));
+  for (int c = 0; c < B200_MAX_CTX; c++)
+    if (ss.read_pending[c]) CU(cudaEventSynchronize(ss.read[c]));
+  return B200_OK;
+}
+
+extern "C" void* b200_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void b200_host_free(void* p)
+{
+  if (p) cudaFreeHost(p);
 }
 
 extern "C" int b200_engine_slot_device_planes(b200_engine* en, int slot, void* planes[3], size_t strides[3])

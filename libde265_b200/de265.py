@@ -18,6 +18,7 @@ DE265_DECODER_PARAM_ACCELERATION_CODE = 5
 DE265_DECODER_PARAM_DISABLE_DEBLOCKING = 7
 DE265_DECODER_PARAM_DISABLE_SAO = 8
 de265_acceleration_SCALAR = 0
+de265_acceleration_B200 = 200  # added by the reference-side binding (integration/libde265_hooks.h)
 de265_acceleration_AUTO = 10000
 
 SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(capi.Picture), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
@@ -87,7 +88,7 @@ class Decoder:
         if not hasattr(self.lib, "de265_b200_attach"):
             raise RuntimeError("this libde265 build has no B2 hook sites (see INTEGRATION.md)")
         self.lib.de265_b200_attach.argtypes = [C.c_void_p, SINK, C.c_void_p]
-        self.lib.de265_b200_attach.restype = None
+        self.lib.de265_b200_attach.restype = C.c_int
         if sink is None:
             self.lib.de265_b200_attach(self.ctx, SINK(), None)
             self._sink_ref = None
@@ -97,7 +98,16 @@ class Decoder:
             return sink(pic.contents, planes, strides)
 
         self._sink_ref = SINK(tramp)
-        self.lib.de265_b200_attach(self.ctx, self._sink_ref, None)
+        rc = self.lib.de265_b200_attach(self.ctx, self._sink_ref, None)
+        if rc:
+            raise RuntimeError(f"de265_b200_attach failed: {rc}")
+
+    def select_b200(self):
+        """The drop-in switch: DE265_DECODER_PARAM_ACCELERATION_CODE = de265_acceleration_B200 (de265.h:416-427) — the decoder then
+        owns a B200 engine, reconstructs every picture on the GPU and hands out pictures exactly as before."""
+        if not hasattr(self.lib, "de265_b200_enable"):
+            raise RuntimeError("this libde265 build has no B200 backend (see INTEGRATION.md)")
+        self.set_parameter_int(DE265_DECODER_PARAM_ACCELERATION_CODE, de265_acceleration_B200)
 
     # -- de265.h ---------------------------------------------------------------------------------
     def set_parameter_int(self, param, value):
@@ -131,8 +141,12 @@ class Decoder:
             self.lib.de265_free_decoder(self.ctx)
             self.ctx = None
 
-    def decode_stream(self, data, on_picture, chunk=40960):
-        """The dec265 main loop (dec265.cc:745-881): push 40 KiB chunks, decode, drain pictures."""
+    def decode_stream(self, data, on_picture, chunk=40960, lag=0):
+        """The dec265 main loop (dec265.cc:745-881): push 40 KiB chunks, decode, drain pictures.  lag=1: pictures are fetched one
+        de265_decode call late (what a player with an output thread does): with the asynchronous B200 backend the host then
+        parses picture N+1 while the GPU reconstructs picture N."""
+        if lag:
+            return self._decode_stream_lagged(data, on_picture, chunk)
         pos, n = 0, 0
         stop = False
         while not stop:
@@ -156,4 +170,37 @@ class Decoder:
                     more = True
                 while self.get_warning() != DE265_OK:
                     pass
+        return n
+
+    def _decode_stream_lagged(self, data, on_picture, chunk):
+        pos, n, owed = 0, 0, 0  # owed: pictures decoded but not fetched yet
+        stop = False
+        while not stop:
+            buf = data[pos:pos + chunk]
+            if buf and self.push_data(buf) != DE265_OK:
+                break
+            pos += len(buf)
+            if pos >= len(data):
+                self.flush_data()
+                stop = True
+            more = True
+            while more:
+                err, more = self.decode()
+                if err != DE265_OK:
+                    break
+                while self.get_warning() != DE265_OK:
+                    pass
+                if owed:  # the picture of the previous call: its read-back ran while this call parsed
+                    img = self.get_next_picture()
+                    if img is not None:
+                        on_picture(img)
+                        n += 1
+                        continue
+                owed = 1
+        while True:  # drain
+            img = self.get_next_picture()
+            if img is None:
+                break
+            on_picture(img)
+            n += 1
         return n

@@ -29,7 +29,7 @@ def main():
     inc = '#include "libde265_hooks.h"\n'
     # Every other file is a symlink into the reference tree, so that `#include "decctx.h"` from any
     # translation unit resolves to the patched header (quote-includes search the includer's directory).
-    patched = {"slice.cc", "motion.cc", "decctx.cc", "decctx.h"}
+    patched = {"slice.cc", "motion.cc", "decctx.cc", "decctx.h", "de265.cc", "de265.h"}
     for name in os.listdir(src):
         if name in patched:
             continue
@@ -76,7 +76,37 @@ def main():
         r"\1if (b200_hook_picture_done(this, imgunit->img)) { } else\1\2",
         "decode_some post-processing",
     )
+    # set_acceleration_functions: the B200 level (DE265_DECODER_PARAM_ACCELERATION_CODE = de265_acceleration_B200)
+    t = sub_once(
+        t,
+        r"(void base_context::set_acceleration_functions\(enum de265_acceleration l\)\n\{\n)",
+        r"\1  b200_hook_set_acceleration(this, (int)l);\n",
+        "set_acceleration_functions",
+    )
+    # synthesised reference pictures are mirrored into the backend
+    t = sub_once(
+        t,
+        r"(img->integrity = INTEGRITY_UNAVAILABLE_REFERENCE;\n)(\n\s*return idx;)",
+        r"\1  b200_hook_unavailable_reference(this, img);\n\2",
+        "generate_unavailable_reference_picture",
+    )
     open(os.path.join(dst, "decctx.cc"), "w").write(t)
+
+    # --- de265.cc: the deferred read-back is awaited when the picture is handed to the application ---
+    t = open(os.path.join(src, "de265.cc")).read()
+    t = sub_once(t, r'(#include "de265.h"\n)', r"\1" + inc, "de265.cc include")
+    t = sub_once(
+        t,
+        r"(de265_image\* img = ctx->get_next_picture_in_output_queue\(\);\n)(\s*return img;)",
+        r"\1    b200_hook_wait_image(ctx, img);\n\2",
+        "de265_peek_next_picture",
+    )
+    open(os.path.join(dst, "de265.cc"), "w").write(t)
+
+    # --- de265.h: the acceleration level ---
+    t = open(os.path.join(src, "de265.h")).read()
+    t = sub_once(t, r"(  de265_acceleration_NEON = 80,\n)", r"\1  de265_acceleration_B200 = 200, // reconstruction on a B200 GPU (libde265_hooks.h)\n", "de265_acceleration enum")
+    open(os.path.join(dst, "de265.h"), "w").write(t)
 
     # --- decctx.h: per-context hook state ---
     t = open(os.path.join(src, "decctx.h")).read()

@@ -87,6 +87,38 @@ def test_real_intra_stream_end_to_end(b200lib, name):
     assert n == exp["pictures"] and md.hexdigest() == exp["md5_of_all_planes_in_output_order"]
 
 
+@pytest.mark.parametrize("lag", [0, 1])
+@pytest.mark.skipif(oracle_lib.ref_path("libde265_hooked.so") is None, reason="oracle/_ref not shipped")
+def test_girlshy_through_the_acceleration_code(b200lib, lag):
+    """The drop-in switch itself: de265_set_parameter_int(ctx, DE265_DECODER_PARAM_ACCELERATION_CODE, de265_acceleration_B200)
+    on a libde265 built with the binding of INTEGRATION.md — no sink, no Python in the data path: the decoder owns a B200 engine,
+    submits every picture asynchronously at picture end and awaits the read-back when the picture is handed out.  Golden md5 of
+    scripts/ci-run.sh:91-92, with the dec265 loop (lag 0) and with pictures fetched one de265_decode call late (lag 1)."""
+    dec = de265.Decoder(oracle_lib.ref_path("libde265_hooked.so"))
+    dec.select_b200()
+    md = hashlib.md5()
+    n = dec.decode_stream(open(os.path.join(GOLDEN, "girlshy.h265"), "rb").read(), lambda img: [md.update(img.plane_bytes(c)) for c in range(3)], lag=lag)
+    dec.close()
+    assert n == 75 and md.hexdigest() == GOLDEN_MD5
+
+
+@pytest.mark.skipif(oracle_lib.ref_path("libde265_hooked.so") is None or oracle_lib.ref_path("libde265_ref.so") is None, reason="oracle/_ref not shipped")
+def test_concatenated_intra_streams_through_the_acceleration_code(b200lib):
+    """The real 1080p intra stream three times back to back (every copy starts with its own parameter sets and an IDR picture)
+    through the asynchronous built-in backend, pictures fetched one call late so that parsing overlaps the GPU: the same
+    pictures as the unmodified reference decoder produces from the same bytes."""
+    data = open(os.path.join(GOLDEN, "intra1080.h265"), "rb").read() * 3
+    want, got = [], []
+    ref = de265.Decoder(oracle_lib.ref_path("libde265_ref.so"))
+    ref.decode_stream(data, lambda img: want.append(hashlib.md5(b"".join(img.plane_bytes(c) for c in range(3))).hexdigest()))
+    ref.close()
+    dec = de265.Decoder(oracle_lib.ref_path("libde265_hooked.so"))
+    dec.select_b200()
+    dec.decode_stream(data, lambda img: got.append(hashlib.md5(b"".join(img.plane_bytes(c) for c in range(3))).hexdigest()), lag=1)
+    dec.close()
+    assert len(want) == 6 and got == want
+
+
 # ---- synthetic pictures vs the oracle -----------------------------------------------------------------
 def run_sequence(eng, orc, W, H, bd, log2_ctb=6, stages=False, **kw):
     ref = synth.random_planes(W, H, bd, 99)

@@ -3,6 +3,8 @@
 settings given as environment assignments, e.g.:  sweep_bench.py "B200_IND_STREAMS=1" "B200_IND_STREAMS=2 B200_INTRA_I_GRID=64"
 Optional first argument --timeline=FILE records a B200_TIMELINE for the LAST setting."""
 import os, sys, time
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA initialises: one hardware queue per engine stream (see capi.py)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
