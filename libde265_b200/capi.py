@@ -151,7 +151,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("B200_LIB") or LIB_PATH  # B200_LIB: an experiment build of the same sources (build.py)
     if not os.path.exists(p):
         raise OSError(f"{p} not found: run `python -c 'import __graft_entry__ as g; g.build()'` first "
                       "(there is no CPU fallback for the reconstruction engine)")

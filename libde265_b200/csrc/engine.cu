@@ -309,7 +309,7 @@ struct b200_engine {
   long long slot_depth[B200_MAX_SLOTS] = {}, tail_depth[B200_MAX_CTX] = {}, key_depth = 0;  // pick_ctx: dependency depths
   bool sched_rr = false;        // B200_SCHED=rr: plain round-robin placement (A/B measurements)
   int n_ind = 2, next_ind = 0;  // streams for pictures that read no reference (intra pictures), used round-robin (B200_IND_STREAMS)
-  int intra_i_grid = 0;         // grid cap of k_intra for such pictures (0: one CTA per SM; B200_INTRA_I_GRID)
+  int intra_i_grid = 64;        // grid cap of k_intra for such pictures: the DAG is at most ~160 tasks wide, 64 CTAs (512 warps) cover it and leave the other SMs to the P/B pictures (0: one CTA per SM; B200_INTRA_I_GRID)
   int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
   int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
   // B200_TIMELINE=<file>: a CUDA event before and after every launch; the intervals of all streams (ms since the first launch)
@@ -795,7 +795,7 @@ static int plan_begin(b200_engine* en, const b200_picture* pic, PicLayout* L, si
   for (int i : k_raw_sections) { L->off[i] = total; total += align_up(sz[i], 256); }
   L->raw_total = total;
   // upper bound of the lists: every TU in one list, one task per TU; MC units cannot outnumber 4x8 blocks unless PUs overlap
-  L->unit_cap = ((size_t)w4 * h4 / 2 + 64 + 8 * MCT_MAX_TILES) * 9 / 8 + 64;  // + the padding of the class-pure batches + the batch table
+  L->unit_cap = ((size_t)w4 * h4 / 2 + 64 + 8 * MCT_MAX_TILES) * 3 / 2 + 64;  // + the padding of the class-pure batches + the batch table
   *cap_total = total + 3 * align_up(sizeof(uint32_t) * ((size_t)pic->n_tu + 1), 256) + align_up(sizeof(uint32_t) * L->unit_cap, 256) + 256;
   return B200_OK;
 }

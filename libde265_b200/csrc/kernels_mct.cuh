@@ -34,10 +34,14 @@
 #define MCT_HD __host__ __device__ __forceinline__
 
 #define MCT_THREADS 128
-#define MCT_MAX_TL 32                    // tile-list items per batch: 32 with the small boxes, 16 with the big ones
-#define MCT_MAX_TILES 32                 // tiles per batch (small, uni-predicted)
-#define MCT_WIN_BYTES 40960              // window region: 16 x (1280 + 896) big  |  32 x (640 + 640) small
-#define MCT_INT_WORDS 6400               // intermediate region: 16 x (240 + 144) big  |  32 x (100 + 100) small
+#ifndef MCT_TLS
+#define MCT_TLS 32                       // tile-list items per batch with the small boxes (a power of two); half as many with the big ones
+#endif
+#define MCT_L2TLS (MCT_TLS == 32 ? 5 : MCT_TLS == 16 ? 4 : 3)
+#define MCT_MAX_TL MCT_TLS
+#define MCT_MAX_TILES MCT_TLS            // tiles per batch (small, uni-predicted)
+#define MCT_WIN_BYTES (MCT_TLS * 1280)   // window region: TLS/2 x (1280 + 896) big  |  TLS x (640 + 640) small
+#define MCT_INT_WORDS (MCT_TLS * 200)    // intermediate region: TLS/2 x (240 + 144) big  |  TLS x (100 + 100) small
 // big boxes (tiles wider or taller than 8): luma 48 bytes x 26 rows (16-byte aligned origin + up to 15 + 23 columns; 23 rows + up
 // to 3 rows of bank skew), chroma 32 bytes x 14 rows x {Cb, Cr}
 #define MCT_LWB_PITCH 48
@@ -61,7 +65,7 @@
 #define MCT_TILE_WORD(pu, tx, ty, cls) ((uint32_t)(pu) | ((uint32_t)(tx) << 20) | ((uint32_t)(ty) << 22) | ((uint32_t)(cls) << 24))
 #define MCT_INVALID 0xFFFFFFFFu
 // tiles per batch of a class: 32 tile-list items with the small boxes (narrow and short), 16 otherwise
-#define MCT_CLASS_TILES(cls) ((((cls) & (MCT_CLASS_WIDE | MCT_CLASS_TALL)) ? 16 : 32) >> (((cls) & MCT_CLASS_BI) ? 1 : 0))
+#define MCT_CLASS_TILES(cls) ((((cls) & (MCT_CLASS_WIDE | MCT_CLASS_TALL)) ? MCT_TLS / 2 : MCT_TLS) >> (((cls) & MCT_CLASS_BI) ? 1 : 0))
 // batch word (host planner -> kernel): bits 0-27 index of the batch's first tile word, 28-30 class
 #define MCT_BATCH_WORD(first, cls) ((uint32_t)(first) | ((uint32_t)(cls) << 28))
 
@@ -93,26 +97,26 @@ MCT_HD MctGeom mct_geom(int cls)
   const bool wide = cls & MCT_CLASS_WIDE, tall = cls & MCT_CLASS_TALL;
   g.small = !wide && !tall;
   g.nl = (cls & MCT_CLASS_BI) ? 2 : 1;
-  g.ntl = g.small ? 32 : 16;
+  g.ntl = g.small ? MCT_TLS : MCT_TLS / 2;
   g.ntiles = g.ntl / g.nl;
   g.nco = wide ? 2 : 1;
   g.nrp = tall ? 12 : 8;
   g.nrpc = tall ? 6 : 4;
   g.nu = tall ? 8 : 4;
   g.nuc = tall ? 4 : 2;
-  g.l2ntl = g.small ? 5 : 4; g.l2nu = tall ? 3 : 2; g.l2nuc = tall ? 2 : 1;
+  g.l2ntl = g.small ? MCT_L2TLS : MCT_L2TLS - 1; g.l2nu = tall ? 3 : 2; g.l2nuc = tall ? 2 : 1;
   g.n1l = g.nrp * g.ntl * g.nco;
   g.n1c = g.nrpc * g.ntl * 2;
   g.n2l = g.ntiles * g.nco * g.nu;   // 8 columns x 2 rows per task
   g.n2c = g.ntiles * 2 * g.nuc;
   if (g.small) {
-    g.lw_pitch = MCT_LWS_PITCH; g.lw_slot = MCT_LWS_SLOT; g.cw_off = 32 * MCT_LWS_SLOT; g.cw_pitch = MCT_CWS_PITCH;
+    g.lw_pitch = MCT_LWS_PITCH; g.lw_slot = MCT_LWS_SLOT; g.cw_off = MCT_TLS * MCT_LWS_SLOT; g.cw_pitch = MCT_CWS_PITCH;
     g.cw_plane = MCT_CWS_PITCH * MCT_CWS_ROWS; g.cw_slot = MCT_CWS_SLOT;
-    g.li_pitch = 12; g.li_words = 100; g.ci_off = 32 * 100; g.ci_pitch = 12; g.ci_plane = 48; g.ci_words = 100;
+    g.li_pitch = 12; g.li_words = 100; g.ci_off = MCT_TLS * 100; g.ci_pitch = 12; g.ci_plane = 48; g.ci_words = 100;
   } else {
-    g.lw_pitch = MCT_LWB_PITCH; g.lw_slot = MCT_LWB_SLOT; g.cw_off = 16 * MCT_LWB_SLOT; g.cw_pitch = MCT_CWB_PITCH;
+    g.lw_pitch = MCT_LWB_PITCH; g.lw_slot = MCT_LWB_SLOT; g.cw_off = MCT_TLS / 2 * MCT_LWB_SLOT; g.cw_pitch = MCT_CWB_PITCH;
     g.cw_plane = MCT_CWB_PITCH * MCT_CWB_ROWS; g.cw_slot = MCT_CWB_SLOT;
-    g.li_pitch = 20; g.li_words = 240; g.ci_off = 16 * 240; g.ci_pitch = 12; g.ci_plane = 72; g.ci_words = 144;
+    g.li_pitch = 20; g.li_words = 240; g.ci_off = MCT_TLS / 2 * 240; g.ci_pitch = 12; g.ci_plane = 72; g.ci_words = 144;
   }
   return g;
 }
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(MCT_CTA_THREADS) k_inter_pred_tma(DevPic pic, 
                            mct_smem(sm.win + g.cw_off + lane * g.cw_slot)),
                        "l"(&maps.chroma[k][mi]), "r"(bx.cx + B200_PAD_CX), "r"(bx.cy + B200_PAD_CY - skew), "r"(0), "r"(full)
                        : "memory");
-      } else {
+      } else if (lane < MCT_MAX_TL) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
       }
     }
@@ -582,14 +586,17 @@ __global__ void __launch_bounds__(MCT_CTA_THREADS) k_inter_pred_tma(DevPic pic, 
     mct_mbar_wait(full, it & 1);  // this batch's windows and tile info
     const MctTile* info = sm.info[it & 1];
     const MctGeom g = sm.geom[it & 1];
-    for (int t = tid; t < g.n1l; t += MCT_THREADS) mct_pass1_luma(t, g, info, sm.win, sm.interm, sm.tab);
-    if (has_chroma)
-      for (int t = tid; t < g.n1c; t += MCT_THREADS) mct_pass1_chroma(t, g, info, sm.win, sm.interm, sm.tab);
+    const int n1 = g.n1l + (has_chroma ? g.n1c : 0), n2 = g.n2l + (has_chroma ? g.n2c : 0);
+    for (int t = tid; t < n1; t += MCT_THREADS) {  // one flat list: luma tasks, then chroma tasks
+      if (t < g.n1l) mct_pass1_luma(t, g, info, sm.win, sm.interm, sm.tab);
+      else mct_pass1_chroma(t - g.n1l, g, info, sm.win, sm.interm, sm.tab);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(MCT_THREADS) : "memory");
     if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty) : "memory");  // the windows are free: the producer fetches ahead
-    for (int t = tid; t < g.n2l; t += MCT_THREADS) mct_pass2_luma(t, g, info, sm.interm, sm.tab, pic.cur[0], pic.pitch[0]);
-    if (has_chroma)
-      for (int t = tid; t < g.n2c; t += MCT_THREADS) mct_pass2_chroma(t, g, info, sm.interm, sm.tab, pic.cur[1], pic.cur[2], pic.pitch[1]);
+    for (int t = tid; t < n2; t += MCT_THREADS) {
+      if (t < g.n2l) mct_pass2_luma(t, g, info, sm.interm, sm.tab, pic.cur[0], pic.pitch[0]);
+      else mct_pass2_chroma(t - g.n2l, g, info, sm.interm, sm.tab, pic.cur[1], pic.cur[2], pic.pitch[1]);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(MCT_THREADS) : "memory");
   }
 }

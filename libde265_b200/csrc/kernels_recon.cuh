@@ -58,7 +58,7 @@ struct IntraSmem {  // k_intra
   P blk[RC_WARPS][RC_BLK];            // a region tile, or a large TU's samples (row stride nT)
   int16_t coef[RC_WARPS][32 * RC_GSTRIDE];
   int16_t g[RC_WARPS][32 * RC_GSTRIDE];
-  int32_t res[RC_WARPS][32 * 32];     // the task's residuals, TU after TU (row stride nT inside a TU)
+  res_t res[RC_WARPS][32 * 32];       // the task's residuals (saturated int16), TU after TU (row stride nT inside a TU)
   P border[RC_WARPS][2][4 * 32 + 4];  // large TUs: [0] gathered/substituted, [1] filtered / angular ref
   b200_tu tu_s[RC_WARPS][16];
   ResTables tb;
@@ -66,7 +66,7 @@ struct IntraSmem {  // k_intra
 
 // -------------------------------------------------------------------------------------------------
 // Residual of one LARGE TU (16x16 or 32x32) by one warp; smaller TUs take the sub-warp paths of
-// kernels_residual.cuh.  TO_RES: write the int32 residual r(x,y) to res[x + y*nT] (the caller adds it later); else
+// kernels_residual.cuh.  TO_RES: write the residual r(x,y), saturated to int16, to res[x + y*nT] (the caller adds it later); else
 // dst(x,y) = Clip(dst + r) on samples at `dst` (row stride dstride, in GLOBAL memory: each sample is read and written
 // by the same lane exactly once).
 //   coefT  dequantised coefficients, COLUMN-major int16: coefficient (row j, column c) at coefT[c*RC_GSTRIDE + j], so a
@@ -76,7 +76,7 @@ struct IntraSmem {  // k_intra
 // 8 dp2a) and only touch the rows / columns up to the last significant coefficient.
 // -------------------------------------------------------------------------------------------------
 template <typename P, bool TO_RES>
-__device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8_t* __restrict__ scaling, P* dst, int dstride, int32_t* res,
+__device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8_t* __restrict__ scaling, P* dst, int dstride, res_t* res,
                             int bd, int16_t* coefT, int16_t* g, const ResTables& tb, int lane)
 {
   const int log2 = tu.log2_size, nT = 1 << log2, n = tu.n_coeff;
@@ -112,7 +112,7 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8
   __syncwarp();
 
   auto emit4 = [&](int x, int y, const int (&r)[4]) {  // 4 horizontally adjacent samples, x % 4 == 0
-    if (TO_RES) *reinterpret_cast<int4*>(res + x + (y << log2)) = make_int4(r[0], r[1], r[2], r[3]);
+    if (TO_RES) res_store4(res + x + (y << log2), r[0], r[1], r[2], r[3]);
     else add_row<P, 4>(dst + x + (size_t)y * dstride, r, bd);
   };
 
@@ -132,7 +132,7 @@ __device__ void tu_residual(const b200_tu& tu, const b200_coeff* co, const uint8
         for (int k = 0; k < nT; k++) {
           const int x = vert ? lane : k, y = vert ? k : lane;
           sum += value(x, y);
-          if (TO_RES) res[x + (y << log2)] = sum;
+          if (TO_RES) res[x + (y << log2)] = (res_t)clip16(sum);
           else dst[x + (size_t)y * dstride] = (P)clip_bd((int)dst[x + (size_t)y * dstride] + sum, bd);
         }
       }
@@ -203,7 +203,7 @@ __constant__ int16_t k_inv_angle[15] = {-4096, -1638, -910, -630, -482, -390, -3
 // res = this TU's precomputed residual (row stride nT) or nullptr.  intrapred.h:185-433,529-674.
 // -------------------------------------------------------------------------------------------------
 template <typename P>
-__device__ __forceinline__ void tu_intra_small(const b200_tu& tu, P* dst, int ts, int bd, bool filter_plane, const int32_t* res, int lane)
+__device__ __forceinline__ void tu_intra_small(const b200_tu& tu, P* dst, int ts, int bd, bool filter_plane, const res_t* res, int lane)
 {
   const int log2 = tu.log2_size, nT = 1 << log2, mode = tu.intra_mode, cidx = tu.cidx;
   const uint64_t avail = tu.avail;
@@ -326,7 +326,7 @@ __device__ __forceinline__ void tu_intra_small(const b200_tu& tu, P* dst, int ts
 // This is the dependent part of the intra DAG, so what counts is its latency: ~50 mostly independent instructions.
 // -------------------------------------------------------------------------------------------------
 template <typename P, int LOG2>
-__device__ __forceinline__ void tu_intra_fast(const b200_tu& tu, P* dst, int ts, int bd, bool filter_plane, const int32_t* res, int lane)
+__device__ __forceinline__ void tu_intra_fast(const b200_tu& tu, P* dst, int ts, int bd, bool filter_plane, const res_t* res, int lane)
 {
   constexpr int nT = 1 << LOG2;
   const int mode = tu.intra_mode, cidx = tu.cidx;
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
   for (int i = tid; i < (int)(sizeof(ResTables) / 4); i += RC_THREADS) reinterpret_cast<uint32_t*>(&sm.tb)[i] = reinterpret_cast<const uint32_t*>(&c_res)[i];
   __syncthreads();
   b200_tu* tus = sm.tu_s[warp];
-  int32_t* res = sm.res[warp];
+  res_t* res = sm.res[warp];
   P* blk = sm.blk[warp];
   // Persistent warps: each warp keeps claiming the next task of the topological order.
   for (;;) {
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
       for (uint32_t i = 0; i < count; i++) {
         const b200_tu& tu = tus[i];
         P* tdst = tile + (tu.y - ry) * TS + (tu.x - rx);
-        const int32_t* tres = (tu.flags & B200_TU_CBF) ? res + rbase : nullptr;
+        const res_t* tres = (tu.flags & B200_TU_CBF) ? res + rbase : nullptr;
         if (!intra_fast_ok(tu)) tu_intra_small<P>(tu, tdst, TS, bd, filter_plane, tres, lane);
         else if (tu.log2_size == 2) tu_intra_fast<P, 2>(tu, tdst, TS, bd, filter_plane, tres, lane);
         else tu_intra_fast<P, 3>(tu, tdst, TS, bd, filter_plane, tres, lane);

@@ -39,6 +39,13 @@ __device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c)
   return d;
 }
 __device__ __forceinline__ int clip16(int v) { return min(max(v, -32768), 32767); }
+// Residual scratch of the intra kernel: int16 with saturation.  Exact: the residual is only ever added to a prediction sample in
+// [0, 2^bd) and clipped to that range (fallback-dct.h:65-73), and a residual beyond +-32767 saturates the sum either way.
+typedef int16_t res_t;
+__device__ __forceinline__ void res_store4(res_t* p, int a, int b, int c, int d)  // p 8-byte aligned
+{
+  *reinterpret_cast<uint2*>(p) = make_uint2(((uint32_t)clip16(a) & 0xffffu) | ((uint32_t)clip16(b) << 16), ((uint32_t)clip16(c) & 0xffffu) | ((uint32_t)clip16(d) << 16));
+}
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
@@ -107,12 +114,12 @@ __device__ __forceinline__ void add_row(P* p, const int (&r)[N], int bd)
 
 // -------------------------------------------------------------------------------------------------
 // One 4x4 TU per lane.  sc = this warp's scratch, 8 x 32 words, word k of lane l at sc[k*32 + l].
-// TO_RES: res[x + 4y] (int32, 16-byte aligned) receives the residual; else it is added onto dst (global memory).
+// TO_RES: res[x + 4y] (res_t, 8-byte aligned) receives the residual; else it is added onto dst (global memory).
 // No warp-level synchronisation inside: lanes are independent, inactive lanes simply do not call.
 // -------------------------------------------------------------------------------------------------
 template <typename P, bool TO_RES>
 __device__ __forceinline__ void res4_lane(const b200_tu& tu, const b200_coeff* __restrict__ co, const uint8_t* __restrict__ scaling, P* dst, int dstride,
-                                          int32_t* res, int bd, uint32_t* sc, int lane, const ResTables& tb)
+                                          res_t* res, int bd, uint32_t* sc, int lane, const ResTables& tb)
 {
 #pragma unroll
   for (int k = 0; k < 8; k++) sc[k * 32 + lane] = 0;
@@ -180,7 +187,7 @@ __device__ __forceinline__ void res4_lane(const b200_tu& tu, const b200_coeff* _
   }
   if (TO_RES) {
 #pragma unroll
-    for (int y = 0; y < 4; y++) *reinterpret_cast<int4*>(res + 4 * y) = make_int4(r[4 * y], r[4 * y + 1], r[4 * y + 2], r[4 * y + 3]);
+    for (int y = 0; y < 4; y++) res_store4(res + 4 * y, r[4 * y], r[4 * y + 1], r[4 * y + 2], r[4 * y + 3]);
   } else {
 #pragma unroll
     for (int y = 0; y < 4; y++) {
@@ -193,11 +200,11 @@ __device__ __forceinline__ void res4_lane(const b200_tu& tu, const b200_coeff* _
 // -------------------------------------------------------------------------------------------------
 // One 8x8 TU per quarter-warp.  qs = this quarter's scratch, 64 words: [0,32) coefficients, column-major int16
 // (column c = 4 words = vertical pairs), [32,64) first-stage rows.  ALL 32 lanes must call (two __syncwarp inside);
-// quarters without a TU pass active = false.  TO_RES: res[x + 8y] (int32, 16-byte aligned).
+// quarters without a TU pass active = false.  TO_RES: res[x + 8y] (res_t, 8-byte aligned).
 // -------------------------------------------------------------------------------------------------
 template <typename P, bool TO_RES>
 __device__ __forceinline__ void res8_quarter(bool active, const b200_tu& tu, const b200_coeff* __restrict__ co, const uint8_t* __restrict__ scaling, P* dst,
-                                             int dstride, int32_t* res, int bd, uint32_t* qs, int sub, const ResTables& tb)
+                                             int dstride, res_t* res, int bd, uint32_t* qs, int sub, const ResTables& tb)
 {
   *reinterpret_cast<uint4*>(qs + sub * 4) = make_uint4(0, 0, 0, 0);
   __syncwarp();
@@ -228,7 +235,7 @@ __device__ __forceinline__ void res8_quarter(bool active, const b200_tu& tu, con
       int c = c16[x * 8 + y];
       if (ts) c = ((int)((unsigned)c << 8) + rnd2) >> post_shift;  // tsShift = 5 + log2(nT)
       sum = acc ? sum + c : c;
-      if (TO_RES) res[x + 8 * y] = sum;
+      if (TO_RES) res[x + 8 * y] = (res_t)clip16(sum);
       else dst[x + (size_t)y * dstride] = (P)clip_bd((int)dst[x + (size_t)y * dstride] + sum, bd);
     }
   } else if (active) {
@@ -259,8 +266,8 @@ __device__ __forceinline__ void res8_quarter(bool active, const b200_tu& tu, con
       r[i] = s >> post_shift;
     }
     if (TO_RES) {
-      *reinterpret_cast<int4*>(res + 8 * sub) = make_int4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<int4*>(res + 8 * sub + 4) = make_int4(r[4], r[5], r[6], r[7]);
+      res_store4(res + 8 * sub, r[0], r[1], r[2], r[3]);
+      res_store4(res + 8 * sub + 4, r[4], r[5], r[6], r[7]);
     } else {
       add_row<P, 8>(dst + (size_t)sub * dstride, r, bd);
     }
