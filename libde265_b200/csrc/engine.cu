@@ -281,11 +281,10 @@ struct HostPool {
 // not depend on each other (the B pictures of one hierarchy level, the next intra period's I picture) overlap, and a
 // latency-bound kernel (the intra DAG) of one picture leaves the SMs to the others.
 #define B200_MAX_CTX 12
+#define B200_STAGE_SETS 24
 struct PipeCtx {
   cudaStream_t stream = nullptr;
   Surface scratch;              // pre-SAO picture
-  StagingSet stage[2];
-  int cur_stage = 0;
   uint8_t* sync_buf = nullptr;  // [256 B ticket | pending map Y | Cb | Cr | SAO masks]
   size_t sync_cap = 0;
   cudaEvent_t tail = nullptr;   // b200_engine_join
@@ -298,9 +297,20 @@ struct SlotSync {
   bool read_pending[B200_MAX_CTX] = {};
 };
 
+#define PLAN_PU_PARTS 4
+#define PLAN_INTRA_PARTS 8
+struct IntraPart {
+  uint32_t i0 = 0, i1 = 0, task_base = 0;
+  std::vector<uint32_t> intra_idx, task_of, task_first, diag_cnt, diag_off, fill;
+};
+
 struct b200_engine {
   int device = 0;
   PipeCtx ctx[B200_MAX_CTX];
+  // Record staging: pinned host buffer + device arena per picture in flight, handed out round-robin whatever stream the picture
+  // runs on (a set is reused when the kernels of the picture that used it B200_STAGE_SETS pictures ago have finished)
+  StagingSet stage_pool[B200_STAGE_SETS];
+  unsigned next_stage = 0;
   int n_ctx = 1, next_ctx = 0;
   Surface slot[B200_MAX_SLOTS];
   SlotSync ssync[B200_MAX_SLOTS];
@@ -308,7 +318,7 @@ struct b200_engine {
   int num_sms = 148;
   long long slot_depth[B200_MAX_SLOTS] = {}, tail_depth[B200_MAX_CTX] = {}, key_depth = 0;  // pick_ctx: dependency depths
   bool sched_rr = false;        // B200_SCHED=rr: plain round-robin placement (A/B measurements)
-  int n_ind = 2, next_ind = 0;  // streams for pictures that read no reference (intra pictures), used round-robin (B200_IND_STREAMS)
+  int n_ind = 2, next_ind = 0, ind_run = 0;  // streams for pictures that read no reference (intra pictures), used round-robin (B200_IND_STREAMS)
   int intra_i_grid = 64;        // grid cap of k_intra for such pictures: the DAG is at most ~160 tasks wide, 64 CTAs (512 warps) cover it and leave the other SMs to the P/B pictures (0: one CTA per SM; B200_INTRA_I_GRID)
   int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
   int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
@@ -329,6 +339,10 @@ struct b200_engine {
   uint64_t host_n = 0;
   // host scratch reused across pictures
   std::vector<uint32_t> part_a[4][3];  // plan_tus_validate: per part, per k_residual class
+  std::vector<uint32_t> pu_tiles[PLAN_PU_PARTS];  // plan_pus_part
+  size_t pu_count[PLAN_PU_PARTS][8] = {};
+  uint32_t pu_ref_mask[PLAN_PU_PARTS] = {};
+  IntraPart ipart[PLAN_INTRA_PARTS];              // plan_intra_*
   std::vector<uint32_t> ctb_count, tiles, tiles_sorted, list_a, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
 };
 
@@ -460,8 +474,8 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
     PipeCtx& cx = en->ctx[k];
     CU(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&cx.tail, cudaEventDisableTiming));
-    for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&cx.stage[i].done, cudaEventDisableTiming));
   }
+  for (auto& st : en->stage_pool) CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
   for (auto& ss : en->ssync) {
     CU(cudaEventCreateWithFlags(&ss.written, cudaEventDisableTiming));
     for (int k = 0; k < B200_MAX_CTX; k++) CU(cudaEventCreateWithFlags(&ss.read[k], cudaEventDisableTiming));
@@ -487,14 +501,14 @@ extern "C" void b200_engine_destroy(b200_engine* en)
   for (auto& s : en->slot) surface_free(s);
   for (auto& cx : en->ctx) {
     surface_free(cx.scratch);
-    for (auto& st : cx.stage) {
-      if (st.host) cudaFreeHost(st.host);
-      if (st.dev) cudaFree(st.dev);
-      if (st.done) cudaEventDestroy(st.done);
-    }
     if (cx.sync_buf) cudaFree(cx.sync_buf);
     if (cx.tail) cudaEventDestroy(cx.tail);
     if (cx.stream) cudaStreamDestroy(cx.stream);
+  }
+  for (auto& st : en->stage_pool) {
+    if (st.host) cudaFreeHost(st.host);
+    if (st.dev) cudaFree(st.dev);
+    if (st.done) cudaEventDestroy(st.done);
   }
   for (auto& ss : en->ssync) {
     if (ss.written) cudaEventDestroy(ss.written);
@@ -800,14 +814,18 @@ static int plan_begin(b200_engine* en, const b200_picture* pic, PicLayout* L, si
   return B200_OK;
 }
 
-// PU validation + MC work list (runs on a pool thread next to plan_tus)
-static int plan_pus(b200_engine* en, const b200_picture* pic, PicLayout* L)
+// PU validation + MC work list for the PU range [i0, i1) into the part's own tile list (parts run on pool threads;
+// plan_pus_merge sorts them into class-pure batches)
+static int plan_pus_part(b200_engine* en, const b200_picture* pic, int part, uint32_t i0, uint32_t i1)
 {
   const b200_pic_params& p = pic->params;
-  std::vector<uint32_t>& tiles = en->tiles;
+  std::vector<uint32_t>& tiles = en->pu_tiles[part];
   tiles.clear();
+  uint32_t ref_mask = 0;
+  size_t* count = en->pu_count[part];
+  for (int c = 0; c < 8; c++) count[c] = 0;
   const bool wide = p.bit_depth_luma > 8;  // same rule as the launch_picture<P> dispatch
-  for (uint32_t i = 0; i < pic->n_pu; i++) {
+  for (uint32_t i = i0; i < i1; i++) {
     const b200_pu& pu = pic->pus[i];
     if (pu.w == 0 || pu.h == 0 || pu.w > 64 || pu.h > 64 || (pu.w & 3) || (pu.h & 3) || (pu.x & 3) || (pu.y & 3) ||
         pu.x + pu.w > p.width || pu.y + pu.h > p.height)
@@ -815,45 +833,59 @@ static int plan_pus(b200_engine* en, const b200_picture* pic, PicLayout* L)
     if ((pu.flags & B200_PU_WEIGHTED) && pu.wt_idx >= pic->n_weights) return set_err(B200_ERR_INVALID, "PU %u weight index", i);
     if (pu.ref_slot[0] >= B200_MAX_SLOTS || pu.ref_slot[1] >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "PU %u reference slot", i);
     if (!(pu.flags & (B200_PU_PRED_L0 | B200_PU_PRED_L1))) continue;
-    if ((pu.flags & B200_PU_PRED_L0) && pu.ref_slot[0] >= 0) L->ref_mask |= 1u << pu.ref_slot[0];
-    if ((pu.flags & B200_PU_PRED_L1) && pu.ref_slot[1] >= 0) L->ref_mask |= 1u << pu.ref_slot[1];
+    if ((pu.flags & B200_PU_PRED_L0) && pu.ref_slot[0] >= 0) ref_mask |= 1u << pu.ref_slot[0];
+    if ((pu.flags & B200_PU_PRED_L1) && pu.ref_slot[1] >= 0) ref_mask |= 1u << pu.ref_slot[1];
     if (wide) {  // 16-bit path: <= 16x16 tiles, one warp each (kernels_mc.cuh)
       for (int ty = 0; ty * MC_TILE < pu.h; ty++)
         for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
     } else if (en->mc_legacy) {  // first-generation 8-bit path: <= 8x16 units, one quarter-warp each (kernels_mc8.cuh)
       for (int uy = 0; uy * MC8_UH < pu.h; uy++)
         for (int ux = 0; ux * MC8_UW < pu.w; ux++) tiles.push_back(MC8_UNIT(i, ux, uy));
-    } else {     // 8-bit path: <= 16x16 tiles with their class (kernels_mct.cuh), sorted into class-pure batches below
+    } else {     // 8-bit path: <= 16x16 tiles with their class (kernels_mct.cuh), sorted into class-pure batches by the merge
       const int bi = ((pu.flags & B200_PU_PRED_L0) && (pu.flags & B200_PU_PRED_L1)) ? MCT_CLASS_BI : 0;
       for (int ty = 0; ty * 16 < pu.h; ty++)
         for (int tx = 0; tx * 16 < pu.w; tx++) {
           const int tw = std::min(16, pu.w - 16 * tx), th = std::min(16, pu.h - 16 * ty);
-          tiles.push_back(MCT_TILE_WORD(i, tx, ty, bi | (tw > 8 ? MCT_CLASS_WIDE : 0) | (th > 8 ? MCT_CLASS_TALL : 0)));
+          const int cls = bi | (tw > 8 ? MCT_CLASS_WIDE : 0) | (th > 8 ? MCT_CLASS_TALL : 0);
+          tiles.push_back(MCT_TILE_WORD(i, tx, ty, cls));
+          count[cls]++;
         }
     }
   }
+  en->pu_ref_mask[part] = ref_mask;
+  return B200_OK;
+}
+
+// Concatenates the parts; 8-bit: counting sort by class, every class padded to whole batches (MCT_CLASS_TILES tiles of one class,
+// padding = MCT_INVALID), the batch table (first tile index | class) behind the tile words in the same section.
+static int plan_pus_merge(b200_engine* en, const b200_picture* pic, PicLayout* L)
+{
+  const bool wide = pic->params.bit_depth_luma > 8;
+  std::vector<uint32_t>& tiles = en->tiles;
   L->n_batches = 0;
-  size_t n_words = tiles.size();
-  if (!wide && !en->mc_legacy && !tiles.empty()) {
-    // counting sort by class; every class padded to whole batches (MCT_CLASS_TILES tiles of one class, padding = MCT_INVALID);
-    // the batch table (first tile index | class) follows the tile words in the same section
-    std::vector<uint32_t>& sorted = en->tiles_sorted;
-    size_t count[8] = {}, start[8];
-    for (uint32_t t : tiles) count[(t >> 24) & 7]++;
-    size_t total = 0, nb = 0;
+  for (int part = 0; part < PLAN_PU_PARTS; part++) L->ref_mask |= en->pu_ref_mask[part];
+  size_t n_words;
+  if (wide || en->mc_legacy) {
+    tiles.clear();
+    for (int part = 0; part < PLAN_PU_PARTS; part++) tiles.insert(tiles.end(), en->pu_tiles[part].begin(), en->pu_tiles[part].end());
+    n_words = tiles.size();
+  } else {
+    size_t count[8] = {}, start[8], total = 0, nb = 0;
+    for (int part = 0; part < PLAN_PU_PARTS; part++)
+      for (int c = 0; c < 8; c++) count[c] += en->pu_count[part][c];
     for (int c = 0; c < 8; c++) {
       const size_t per = MCT_CLASS_TILES(c), batches = (count[c] + per - 1) / per;
       start[c] = total;
       total += batches * per;
       nb += batches;
     }
-    sorted.assign(total + nb, MCT_INVALID);
+    tiles.assign(total + nb, MCT_INVALID);
     size_t bi = total;
     for (int c = 0; c < 8; c++)
       for (size_t f = start[c]; f < start[c] + (count[c] + MCT_CLASS_TILES(c) - 1) / MCT_CLASS_TILES(c) * MCT_CLASS_TILES(c); f += MCT_CLASS_TILES(c))
-        sorted[bi++] = MCT_BATCH_WORD(f, c);
-    for (uint32_t t : tiles) sorted[start[(t >> 24) & 7]++] = t;
-    tiles.swap(sorted);
+        tiles[bi++] = MCT_BATCH_WORD(f, c);
+    for (int part = 0; part < PLAN_PU_PARTS; part++)
+      for (uint32_t t : en->pu_tiles[part]) tiles[start[(t >> 24) & 7]++] = t;
     n_words = total;
     L->n_batches = (int)nb;
   }
@@ -893,72 +925,132 @@ static int plan_tus_validate(b200_engine* en, const b200_picture* pic, int part,
 }
 
 // Intra work list (runs next to plan_tus_validate, so it must not trust the records: malformed TUs are skipped here and
-// rejected there).
-static int plan_tus_intra(b200_engine* en, const b200_picture* pic, PicLayout* L)
+// rejected there).  Intra tasks: the TUs of one plane inside one aligned 16x16-luma / 8x8-chroma region (contiguous per plane in
+// decode order); a TU at least as large as the region is a task of its own.  Tasks are emitted in a topological order: CTB
+// anti-diagonal x + 2y, ties in decode order.  The TU list is cut at CTB boundaries into PLAN_INTRA_PARTS ranges (a region
+// never crosses a CTB, so no task spans two ranges) and the phases A, C, E run per range on the pool threads:
+//   A  per range: intra TUs, their (range-local) task ids, tasks per diagonal          B  serial: task / rank offsets of the ranges
+//   C  per range: rank of every task, TUs per task                                      D  serial: prefix sum -> task_start
+//   E  per range: list_b (TU indices grouped by task in rank order)
+
+static inline size_t plan_diag_of(const b200_pic_params& p, const b200_tu& tu)
+{
+  const int sh = tu.cidx ? 1 : 0;
+  return (size_t)((tu.x << sh) >> p.log2_ctb_size) + 2 * (size_t)((tu.y << sh) >> p.log2_ctb_size);
+}
+static inline uint32_t plan_ctb_of(const b200_pic_params& p, const b200_tu& tu)
+{
+  const int sh = (tu.cidx && tu.cidx <= 2) ? 1 : 0;
+  return (uint32_t)(((uint32_t)tu.x << sh) >> p.log2_ctb_size) | ((uint32_t)(((uint32_t)tu.y << sh) >> p.log2_ctb_size) << 16);
+}
+
+static void plan_intra_ranges(b200_engine* en, const b200_picture* pic)
 {
   const b200_pic_params& p = pic->params;
-  const int S = 1 << p.log2_ctb_size;
-  const int wctb = (p.width + S - 1) / S, hctb = (p.height + S - 1) / S;
-  {
-    std::vector<uint32_t>& lb = en->list_b;
-    std::vector<uint32_t>& dc = en->diag_count;
-    const int n_diag = wctb + 2 * hctb;
-    std::vector<uint32_t>& intra_idx = en->intra_idx;  // intra TUs in decode order
-    intra_idx.clear();
-    // ---- intra tasks: the TUs of one plane inside one aligned 16x16-luma / 8x8-chroma region (contiguous per plane in
-    //      decode order); a TU at least as large as the region is a task of its own ----
-    std::vector<uint32_t>& task_of = en->task_of;        // per intra TU (in decode order): task id
-    std::vector<uint32_t>& task_first = en->task_first;  // per task: TU index of its first TU
-    task_of.clear();
-    task_first.clear();
-    {
-      long long cur_key[3] = {-1, -1, -1};
-      uint32_t cur_task[3] = {0, 0, 0};
-      for (uint32_t i = 0; i < pic->n_tu; i++) {
-        const b200_tu& tu = pic->tus[i];
-        if (!(tu.flags & B200_TU_INTRA)) continue;
-        if (tu.cidx > 2 || tu.log2_size < 2 || tu.log2_size > 5 || (((size_t)tu.x << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)wctb ||
-            (((size_t)tu.y << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)hctb)
-          continue;
-        intra_idx.push_back(i);
-        const int c = tu.cidx, G = en->region >> (c ? 1 : 0), nT = 1 << tu.log2_size;
-        long long key = (nT >= G) ? -2 - (long long)i : (((long long)(tu.y / G)) << 20) | (tu.x / G);
-        if (key != cur_key[c]) {
-          cur_key[c] = key;
-          cur_task[c] = (uint32_t)task_first.size();
-          task_first.push_back(i);
-        }
-        task_of.push_back(cur_task[c]);
-      }
-    }
-    const uint32_t n_task = (uint32_t)task_first.size(), n_intra = (uint32_t)intra_idx.size();
-    // topological order of tasks: CTB anti-diagonal x + 2y, ties in decode order of the first TU
-    dc.assign((size_t)n_diag + 1, 0);
-    auto diag_of = [&](uint32_t tu_idx) {
-      const b200_tu& tu = pic->tus[tu_idx];
-      const int sh = tu.cidx ? 1 : 0;
-      return (size_t)((tu.x << sh) >> p.log2_ctb_size) + 2 * (size_t)((tu.y << sh) >> p.log2_ctb_size);
-    };
-    for (uint32_t t = 0; t < n_task; t++) dc[diag_of(task_first[t]) + 1]++;
-    for (int d = 0; d < n_diag; d++) dc[d + 1] += dc[d];
-    std::vector<uint32_t>& order = en->task_order;  // rank of each task in the topological order
-    order.resize(n_task);
-    for (uint32_t t = 0; t < n_task; t++) order[t] = dc[diag_of(task_first[t])]++;
-    // task sizes -> start offsets in topological order
-    std::vector<uint32_t>& ts = en->task_start;
-    ts.assign((size_t)n_task + 1, 0);
-    for (uint32_t k = 0; k < n_intra; k++) ts[order[task_of[k]] + 1]++;
-    for (uint32_t t = 0; t < n_task; t++) ts[t + 1] += ts[t];
-    lb.resize(n_intra);
-    {
-      std::vector<uint32_t>& fill = en->ctb_count;  // reuse as per-task fill cursor
-      fill.assign(ts.begin(), ts.end() - 1);
-      for (uint32_t k = 0; k < n_intra; k++) lb[fill[order[task_of[k]]]++] = intra_idx[k];
-    }
-    L->n_task = (int)n_task;
-    L->n_b = (int)lb.size();
+  uint32_t prev = 0;
+  for (int k = 0; k < PLAN_INTRA_PARTS; k++) {
+    uint32_t end = (k == PLAN_INTRA_PARTS - 1) ? pic->n_tu : (uint32_t)((uint64_t)pic->n_tu * (k + 1) / PLAN_INTRA_PARTS);
+    if (end < prev) end = prev;
+    // move the cut forward to the next CTB change (all TUs of a CTB are contiguous in decode order)
+    while (end > 0 && end < pic->n_tu && plan_ctb_of(p, pic->tus[end]) == plan_ctb_of(p, pic->tus[end - 1])) end++;
+    en->ipart[k].i0 = prev;
+    en->ipart[k].i1 = end;
+    prev = end;
   }
-  return B200_OK;
+}
+
+static void plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_diag, int wctb, int hctb)
+{
+  const b200_pic_params& p = pic->params;
+  IntraPart& ip = en->ipart[k];
+  ip.intra_idx.clear();
+  ip.task_of.clear();
+  ip.task_first.clear();
+  ip.diag_cnt.assign((size_t)n_diag, 0);
+  long long cur_key[3] = {-1, -1, -1};
+  uint32_t cur_task[3] = {0, 0, 0};
+  for (uint32_t i = ip.i0; i < ip.i1; i++) {
+    const b200_tu& tu = pic->tus[i];
+    if (!(tu.flags & B200_TU_INTRA)) continue;
+    if (tu.cidx > 2 || tu.log2_size < 2 || tu.log2_size > 5 || (((size_t)tu.x << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)wctb ||
+        (((size_t)tu.y << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)hctb)
+      continue;
+    ip.intra_idx.push_back(i);
+    const int c = tu.cidx, G = en->region >> (c ? 1 : 0), nT = 1 << tu.log2_size;
+    const long long key = (nT >= G) ? -2 - (long long)i : (((long long)(tu.y / G)) << 20) | (tu.x / G);
+    if (key != cur_key[c]) {
+      cur_key[c] = key;
+      cur_task[c] = (uint32_t)ip.task_first.size();
+      ip.task_first.push_back(i);
+      ip.diag_cnt[plan_diag_of(p, tu)]++;
+    }
+    ip.task_of.push_back(cur_task[c]);
+  }
+}
+
+static void plan_intra_B(b200_engine* en, int n_diag, uint32_t* n_task, uint32_t* n_intra)
+{
+  uint32_t nt = 0, ni = 0;
+  for (int k = 0; k < PLAN_INTRA_PARTS; k++) {
+    en->ipart[k].task_base = nt;
+    nt += (uint32_t)en->ipart[k].task_first.size();
+    ni += (uint32_t)en->ipart[k].intra_idx.size();
+    en->ipart[k].diag_off.assign((size_t)n_diag, 0);
+  }
+  uint32_t run = 0;
+  for (int d = 0; d < n_diag; d++)
+    for (int k = 0; k < PLAN_INTRA_PARTS; k++) {  // ranges are in decode order: within a diagonal, earlier ranges rank first
+      en->ipart[k].diag_off[d] = run;
+      run += en->ipart[k].diag_cnt[d];
+    }
+  *n_task = nt;
+  *n_intra = ni;
+  en->task_order.resize(nt);
+  en->task_start.assign((size_t)nt + 1, 0);
+  en->list_b.resize(ni);
+}
+
+static void plan_intra_C(b200_engine* en, const b200_picture* pic, int k)
+{
+  const b200_pic_params& p = pic->params;
+  IntraPart& ip = en->ipart[k];
+  uint32_t* order = en->task_order.data() + ip.task_base;
+  for (size_t t = 0; t < ip.task_first.size(); t++) order[t] = ip.diag_off[plan_diag_of(p, pic->tus[ip.task_first[t]])]++;
+  uint32_t* ts = en->task_start.data();
+  for (size_t j = 0; j < ip.task_of.size(); j++) ts[order[ip.task_of[j]] + 1]++;  // a task belongs to exactly one range: no two threads touch one entry
+}
+
+static void plan_intra_E(b200_engine* en, int k)
+{
+  IntraPart& ip = en->ipart[k];
+  const uint32_t* order = en->task_order.data() + ip.task_base;
+  const uint32_t* ts = en->task_start.data();
+  ip.fill.resize(ip.task_first.size());
+  for (size_t t = 0; t < ip.task_first.size(); t++) ip.fill[t] = ts[order[t]];
+  uint32_t* lb = en->list_b.data();
+  for (size_t j = 0; j < ip.intra_idx.size(); j++) lb[ip.fill[ip.task_of[j]]++] = ip.intra_idx[j];
+}
+
+// Runs `f(k)` for k = 0..n-1 on the pool (or inline without one) and waits.
+template <typename F>
+static void plan_parallel(b200_engine* en, int n, F f)
+{
+  for (int k = 0; k < n; k++) en->pool.run([=] { f(k); });
+  en->pool.wait();
+}
+
+// The serial glue of the intra planner after phase A has run for every range (also used by plan_and_pack, where phase A runs
+// next to the other planning work).
+static void plan_intra_finish(b200_engine* en, const b200_picture* pic, PicLayout* L, int n_diag)
+{
+  uint32_t n_task = 0, n_intra = 0;
+  plan_intra_B(en, n_diag, &n_task, &n_intra);
+  plan_parallel(en, PLAN_INTRA_PARTS, [=](int k) { plan_intra_C(en, pic, k); });
+  uint32_t* ts = en->task_start.data();
+  for (uint32_t t = 0; t < n_task; t++) ts[t + 1] += ts[t];
+  plan_parallel(en, PLAN_INTRA_PARTS, [=](int k) { plan_intra_E(en, k); });
+  L->n_task = (int)n_task;
+  L->n_b = (int)n_intra;
 }
 
 static void plan_finish(PicLayout* L)
@@ -1046,14 +1138,19 @@ static int plan_and_pack(b200_engine* en, const b200_picture* pic, PicLayout* L,
   if (rc) return rc;
   const double t1 = now();
   uint8_t* hb = ss.host;
-  int rc_pu = B200_OK;
-  std::string err_pu;
-  en->pool.run([&] {
-    rc_pu = plan_pus(en, pic, L);
-    if (rc_pu) err_pu = g_err;  // the worker's thread-local message
-  });
-  int rc_tv[PLAN_TU_PARTS] = {};
-  std::string err_tv[PLAN_TU_PARTS];
+  const b200_pic_params& pp = pic->params;
+  const int S = 1 << pp.log2_ctb_size, wctb = (pp.width + S - 1) / S, hctb = (pp.height + S - 1) / S, n_diag = wctb + 2 * hctb;
+  int rc_pu[PLAN_PU_PARTS] = {}, rc_tv[PLAN_TU_PARTS] = {};
+  std::string err_pu[PLAN_PU_PARTS], err_tv[PLAN_TU_PARTS];
+  plan_intra_ranges(en, pic);
+  for (int k = 0; k < PLAN_INTRA_PARTS; k++) en->pool.run([=] { plan_intra_A(en, pic, k, n_diag, wctb, hctb); });  // the longest items first
+  for (int part = 0; part < PLAN_PU_PARTS; part++) {
+    const uint32_t i0 = (uint32_t)((uint64_t)pic->n_pu * part / PLAN_PU_PARTS), i1 = (uint32_t)((uint64_t)pic->n_pu * (part + 1) / PLAN_PU_PARTS);
+    en->pool.run([&, part, i0, i1] {
+      rc_pu[part] = plan_pus_part(en, pic, part, i0, i1);
+      if (rc_pu[part]) err_pu[part] = g_err;  // the worker's thread-local message
+    });
+  }
   for (int part = 0; part < PLAN_TU_PARTS; part++) {
     const uint32_t i0 = (uint32_t)((uint64_t)pic->n_tu * part / PLAN_TU_PARTS), i1 = (uint32_t)((uint64_t)pic->n_tu * (part + 1) / PLAN_TU_PARTS);
     en->pool.run([&, part, i0, i1] {
@@ -1062,13 +1159,15 @@ static int plan_and_pack(b200_engine* en, const b200_picture* pic, PicLayout* L,
     });
   }
   for (int part = 0; part < 3; part++) en->pool.run([=] { pack_raw(pic, *L, hb, part); });
-  rc = plan_tus_intra(en, pic, L);
   en->pool.wait();
   for (int part = 0; part < PLAN_TU_PARTS; part++)
     if (rc_tv[part]) return set_err(rc_tv[part], "%s", err_tv[part].c_str());
-  if (rc) return rc;
+  for (int part = 0; part < PLAN_PU_PARTS; part++)
+    if (rc_pu[part]) return set_err(rc_pu[part], "%s", err_pu[part].c_str());
+  plan_intra_finish(en, pic, L, n_diag);
   merge_list_a(en, L);
-  if (rc_pu) return set_err(rc_pu, "%s", err_pu.c_str());
+  rc = plan_pus_merge(en, pic, L);
+  if (rc) return rc;
   plan_finish(L);
   pack_lists(en, *L, hb);
   if (t_plan_pack) { t_plan_pack[0] = t1 - t0; t_plan_pack[1] = now() - t1; }
@@ -1084,11 +1183,27 @@ extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
   PicLayout L;
   size_t cap = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const bool prof = getenv("B200_HOST_PROF") != nullptr;
+  double t[5] = {now(), 0, 0, 0, 0};
   int rc = plan_begin(en, pic, &L, &cap);
-  if (!rc) rc = plan_pus(en, pic, &L);
+  t[1] = now();
+  for (int part = 0; part < PLAN_PU_PARTS && !rc; part++)
+    rc = plan_pus_part(en, pic, part, (uint32_t)((uint64_t)pic->n_pu * part / PLAN_PU_PARTS), (uint32_t)((uint64_t)pic->n_pu * (part + 1) / PLAN_PU_PARTS));
+  if (!rc) rc = plan_pus_merge(en, pic, &L);
+  t[2] = now();
   for (int part = 0; part < PLAN_TU_PARTS && !rc; part++)
     rc = plan_tus_validate(en, pic, part, (uint32_t)((uint64_t)pic->n_tu * part / PLAN_TU_PARTS), (uint32_t)((uint64_t)pic->n_tu * (part + 1) / PLAN_TU_PARTS));
-  if (!rc) rc = plan_tus_intra(en, pic, &L);
+  t[3] = now();
+  if (!rc) {
+    const b200_pic_params& pp = pic->params;
+    const int S = 1 << pp.log2_ctb_size, wctb = (pp.width + S - 1) / S, hctb = (pp.height + S - 1) / S, n_diag = wctb + 2 * hctb;
+    plan_intra_ranges(en, pic);
+    for (int k = 0; k < PLAN_INTRA_PARTS; k++) plan_intra_A(en, pic, k, n_diag, wctb, hctb);
+    plan_intra_finish(en, pic, &L, n_diag);
+  }
+  t[4] = now();
+  if (prof) fprintf(stderr, "[b200] plan (one thread) ms: begin %.3f  PUs %.3f  TU validate %.3f  intra tasks %.3f\n", 1e3 * (t[1] - t[0]), 1e3 * (t[2] - t[1]), 1e3 * (t[3] - t[2]), 1e3 * (t[4] - t[3]));
   if (!rc) {
     merge_list_a(en, &L);
     plan_finish(&L);
@@ -1223,8 +1338,12 @@ static int pick_ctx(b200_engine* en, uint32_t ref_mask, int dst_slot)
     if ((ref_mask >> r) & 1) depth = std::max(depth, en->slot_depth[r] + 1);
   int k;
   if (ref_mask == 0 && en->n_ctx + en->n_ind <= B200_MAX_CTX) {  // the long intra DAGs of consecutive intra pictures overlap each other too
-    k = en->n_ctx + en->next_ind;
-    en->next_ind = (en->next_ind + 1) % en->n_ind;
+    // an all-intra stream (several pictures in a row that read no reference) spreads over ALL streams: every picture is a
+    // latency-bound DAG on a quarter of the SMs, so many of them fit side by side
+    en->ind_run++;
+    const int pool = en->ind_run > 2 ? en->n_ctx + en->n_ind : en->n_ind, base = en->ind_run > 2 ? 0 : en->n_ctx;
+    k = base + en->next_ind % pool;
+    en->next_ind = (en->next_ind + 1) % pool;
     depth = en->key_depth + 1;  // what references it comes after the pictures already queued
   } else if (en->sched_rr) {
     k = en->next_ctx;
@@ -1237,6 +1356,7 @@ static int pick_ctx(b200_engine* en, uint32_t ref_mask, int dst_slot)
     }
     k = best >= 0 ? best : shallow;
   }
+  if (ref_mask != 0) en->ind_run = 0;
   en->tail_depth[k] = depth;
   if (dst_slot >= 0 && dst_slot < B200_MAX_SLOTS) en->slot_depth[dst_slot] = depth;
   en->key_depth = std::max(en->key_depth, depth);
@@ -1251,8 +1371,7 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const int k = pick_ctx(en, ref_mask_of(pic), pic->params.dst_slot);
   PipeCtx& cx = en->ctx[k];
-  StagingSet& ss = cx.stage[cx.cur_stage];
-  cx.cur_stage ^= 1;
+  StagingSet& ss = en->stage_pool[en->next_stage++ % B200_STAGE_SETS];
   double tp[2] = {0, 0};
   int rc = plan_and_pack(en, pic, &L, ss, tp);
   if (rc) return rc;
@@ -1273,8 +1392,7 @@ extern "C" int b200_engine_prepare_picture(b200_engine* en, const b200_picture* 
   b200_prepared* pp = new (std::nothrow) b200_prepared();
   if (!pp) return set_err(B200_ERR_NOMEM, "out of memory");
   PipeCtx& cx = en->ctx[0];
-  StagingSet& ss = cx.stage[cx.cur_stage];
-  cx.cur_stage ^= 1;
+  StagingSet& ss = en->stage_pool[en->next_stage++ % B200_STAGE_SETS];
   int rc = plan_and_pack(en, pic, &pp->L, ss, nullptr);
   if (rc) { delete pp; return rc; }
   cudaError_t e = cudaMalloc(&pp->dev, pp->L.total);

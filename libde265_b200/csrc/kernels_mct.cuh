@@ -71,12 +71,21 @@
 
 struct MctTile {
   int dst_y, dst_c;       // byte offsets of the tile's first luma / chroma sample in the destination planes
-  uint8_t tw, th, nl, valid;
-  uint8_t xo[2], hidx[2], yf[2], sh6[2];      // per list slot: window byte offset, pass-1 tap table index, vertical phase, final shift
-  uint8_t cxo[2], chidx[2], cyf[2], csh6[2];  // chroma
-  uint8_t missing[2], plain, pad;             // plain: no explicit weights (fallback-motion.cc:33-62)
+  uint32_t shape;         // tw | th << 8 | nl << 16 | valid << 24 | plain << 25 (plain: no explicit weights, fallback-motion.cc:33-62)
+  uint32_t l[2];          // per list slot, luma: window byte offset | pass-1 tap table index << 8 | vertical phase << 16 | final shift << 24 | missing << 31
+  uint32_t c[2];          // the same for chroma
   Mc8Weight w[3];
 };
+#define MCT_TW(sh) ((int)((sh) & 0xff))
+#define MCT_TH(sh) ((int)(((sh) >> 8) & 0xff))
+#define MCT_NL(sh) ((int)(((sh) >> 16) & 0xff))
+#define MCT_VALID(sh) (((sh) >> 24) & 1)
+#define MCT_PLAIN(sh) (((sh) >> 25) & 1)
+#define MCT_XO(w) ((int)((w) & 0xff))
+#define MCT_HIDX(w) ((int)(((w) >> 8) & 0xff))
+#define MCT_YF(w) ((int)(((w) >> 16) & 0xff))
+#define MCT_SH6(w) ((int)(((w) >> 24) & 0x7f))
+#define MCT_MISSING(w) ((w) >> 31)
 
 // ---- task-space and shared-memory geometry of a batch class ----
 struct MctGeom {
@@ -126,7 +135,7 @@ struct MctShared {
   alignas(16) uint32_t interm[MCT_INT_WORDS];
   MctTile info[2][MCT_MAX_TILES];
   MctGeom geom[2];
-  Mc8Tables tab;
+  alignas(16) Mc8Tables tab;
   alignas(8) unsigned long long bar, bar_empty;
 };
 
@@ -191,14 +200,16 @@ MCT_HD void mct_pass1_luma(int t, const MctGeom& g, const MctTile* info, const u
   const int tli = u & (g.ntl - 1), rp = u >> g.l2ntl;
   const int tile = g.nl == 2 ? (tli >> 1) : tli, s = g.nl == 2 ? (tli & 1) : 0;
   const MctTile& ti = info[tile];
-  if (!ti.valid || ti.missing[s] || 2 * rp >= ti.th + 7 || 8 * co >= ti.tw) return;
-  const uint32_t* tp = &tab.qh[ti.hidx[s]][0][0];
+  const uint32_t shape = ti.shape, lw = ti.l[s];
+  if (!MCT_VALID(shape) || MCT_MISSING(lw) || 2 * rp >= MCT_TH(shape) + 7 || 8 * co >= MCT_TW(shape)) return;
   uint32_t T[4][3];
-#pragma unroll
-  for (int j = 0; j < 4; j++)
-#pragma unroll
-    for (int k = 0; k < 3; k++) T[j][k] = tp[j * 3 + k];
-  const int b = ti.xo[s] + 8 * co, sh = (b & 3) * 8;
+  {  // 12 words = three 16-byte loads (qh[f] is 48 bytes, the table 16-byte aligned)
+    const uint4* tp = reinterpret_cast<const uint4*>(&tab.qh[MCT_HIDX(lw)][0][0]);
+    const uint4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
+    T[0][0] = t0.x; T[0][1] = t0.y; T[0][2] = t0.z; T[1][0] = t0.w; T[1][1] = t1.x; T[1][2] = t1.y;
+    T[2][0] = t1.z; T[2][1] = t1.w; T[2][2] = t2.x; T[3][0] = t2.y; T[3][1] = t2.z; T[3][2] = t2.w;
+  }
+  const int b = MCT_XO(lw) + 8 * co, sh = (b & 3) * 8;
   const uint8_t* base = win + tli * g.lw_slot + (2 * rp + (tli & 3)) * g.lw_pitch + (b & ~3);
   int o[2][8];
 #pragma unroll
@@ -232,14 +243,15 @@ MCT_HD void mct_pass1_chroma(int t, const MctGeom& g, const MctTile* info, const
   const int tli = u & (g.ntl - 1), rp = u >> g.l2ntl;
   const int tile = g.nl == 2 ? (tli >> 1) : tli, s = g.nl == 2 ? (tli & 1) : 0;
   const MctTile& ti = info[tile];
-  if (!ti.valid || ti.missing[s] || 2 * rp >= (ti.th >> 1) + 3) return;
-  const uint32_t* tp = &tab.eh[ti.chidx[s]][0][0];
+  const uint32_t shape = ti.shape, cw_ = ti.c[s];
+  if (!MCT_VALID(shape) || MCT_MISSING(cw_) || 2 * rp >= (MCT_TH(shape) >> 1) + 3) return;
   uint32_t T[4][2];
-#pragma unroll
-  for (int j = 0; j < 4; j++)
-#pragma unroll
-    for (int k = 0; k < 2; k++) T[j][k] = tp[j * 2 + k];
-  const int b = ti.cxo[s], sh = (b & 3) * 8;
+  {  // 8 words = two 16-byte loads (eh starts 320 bytes into the table, eh[f] is 32 bytes)
+    const uint4* tp = reinterpret_cast<const uint4*>(&tab.eh[MCT_HIDX(cw_)][0][0]);
+    const uint4 t0 = tp[0], t1 = tp[1];
+    T[0][0] = t0.x; T[0][1] = t0.y; T[1][0] = t0.z; T[1][1] = t0.w; T[2][0] = t1.x; T[2][1] = t1.y; T[3][0] = t1.z; T[3][1] = t1.w;
+  }
+  const int b = MCT_XO(cw_), sh = (b & 3) * 8;
   const uint8_t* base = win + g.cw_off + tli * g.cw_slot + pl * g.cw_plane + (2 * rp + (tli & 3)) * g.cw_pitch + (b & ~3);
   int o[2][8];
 #pragma unroll
@@ -318,19 +330,28 @@ MCT_HD void mct_vpair4(const uint32_t* src, int pitch, const uint32_t (&tv)[3], 
   }
 }
 
+// four values saturated to bytes, v0 in the lowest byte: two cvt.pack.sat (I2IP) instead of four saturating converts + merges
+MCT_HD uint32_t mct_pack_sat4(int v0, int v1, int v2, int v3)
+{
+#ifdef __CUDA_ARCH__
+  uint32_t hi, d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(hi));
+  return d;
+#else
+  return (uint32_t)mct_sat_u8(v0) | ((uint32_t)mct_sat_u8(v1) << 8) | ((uint32_t)mct_sat_u8(v2) << 16) | ((uint32_t)mct_sat_u8(v3) << 24);
+#endif
+}
 MCT_HD uint32_t mct_weight4(const int* a, const int* b, const Mc8Weight& w)
 {
-  uint32_t r = 0;
+  int v[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8(((a[k] * w.w0 + b[k] * w.w1 + w.rnd) >> w.shift) + w.off) << (8 * k);
-  return r;
+  for (int k = 0; k < 4; k++) v[k] = ((a[k] * w.w0 + b[k] * w.w1 + w.rnd) >> w.shift) + w.off;
+  return mct_pack_sat4(v[0], v[1], v[2], v[3]);
 }
 MCT_HD uint32_t mct_plain4(const int* a, const int* b, int rnd, int shift)  // (a + 32) >> 6 resp. (a + b + 64) >> 7 (fallback-motion.cc:33-62); b = 0 for uni
 {
-  uint32_t r = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) r |= (uint32_t)mct_sat_u8((a[k] + b[k] + rnd) >> shift) << (8 * k);
-  return r;
+  return mct_pack_sat4((a[0] + b[0] + rnd) >> shift, (a[1] + b[1] + rnd) >> shift, (a[2] + b[2] + rnd) >> shift, (a[3] + b[3] + rnd) >> shift);
 }
 
 // Row segment store: nbytes (<= 8; multiple of 4 for luma, of 2 for chroma) of the two words to dst, widest aligned form available.
@@ -352,18 +373,20 @@ MCT_HD void mct_pass2_luma(int t, const MctGeom& g, const MctTile* info, const u
   const int u = t & (g.nu - 1), tc = t >> g.l2nu;
   const int co = g.nco == 2 ? (tc & 1) : 0, tile = g.nco == 2 ? (tc >> 1) : tc;
   const MctTile& ti = info[tile];
-  const int y0 = 2 * u;
-  if (!ti.valid || y0 >= ti.th || 8 * co >= ti.tw) return;
+  const uint32_t shape = ti.shape;
+  const int y0 = 2 * u, tw = MCT_TW(shape), th = MCT_TH(shape), nl = MCT_NL(shape);
+  if (!MCT_VALID(shape) || y0 >= th || 8 * co >= tw) return;
   int v[2][2][8];
 #pragma unroll
   for (int s = 0; s < 2; s++) {
-    if (s < ti.nl && !ti.missing[s]) {
+    const uint32_t lw = s < nl ? ti.l[s] : 0x80000000u;
+    if (!MCT_MISSING(lw)) {
       uint32_t tv[5];
 #pragma unroll
-      for (int k = 0; k < 5; k++) tv[k] = tab.qv[ti.yf[s]][k];
-      mct_vpair8(interm + (tile * g.nl + s) * g.li_words + u * g.li_pitch + 8 * co, g.li_pitch, tv, ti.sh6[s], v[s]);
+      for (int k = 0; k < 5; k++) tv[k] = tab.qv[MCT_YF(lw)][k];
+      mct_vpair8(interm + (tile * g.nl + s) * g.li_words + u * g.li_pitch + 8 * co, g.li_pitch, tv, MCT_SH6(lw), v[s]);
     } else {
-      const int fill = s < ti.nl ? (1 << 13) : 0;  // missing reference: mid-grey intermediate (motion.cc:362)
+      const int fill = s < nl ? (1 << 13) : 0;  // missing reference: mid-grey intermediate (motion.cc:362)
 #pragma unroll
       for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -371,10 +394,10 @@ MCT_HD void mct_pass2_luma(int t, const MctGeom& g, const MctTile* info, const u
     }
   }
   const Mc8Weight w = ti.w[0];
-  const int nbytes = ti.tw - 8 * co < 8 ? ti.tw - 8 * co : 8;
+  const int nbytes = tw - 8 * co < 8 ? tw - 8 * co : 8;
   uint8_t* dst = plane + ti.dst_y + (size_t)y0 * pitch + 8 * co;
-  const int nr = ti.th - y0 < 2 ? 1 : 2;
-  if (ti.plain) {
+  const int nr = th - y0 < 2 ? 1 : 2;
+  if (MCT_PLAIN(shape)) {
 #pragma unroll
     for (int i = 0; i < 2; i++)
       if (i < nr) mct_store_row(dst + (size_t)i * pitch, mct_plain4(&v[0][i][0], &v[1][i][0], w.rnd, w.shift), mct_plain4(&v[0][i][4], &v[1][i][4], w.rnd, w.shift), nbytes);
@@ -391,18 +414,20 @@ MCT_HD void mct_pass2_chroma(int t, const MctGeom& g, const MctTile* info, const
   const int u = t & (g.nuc - 1), tp_ = t >> g.l2nuc;
   const int pl = tp_ & 1, tile = tp_ >> 1;
   const MctTile& ti = info[tile];
-  const int y0 = 2 * u, ch = ti.th >> 1, cwd = ti.tw >> 1;
-  if (!ti.valid || y0 >= ch) return;
+  const uint32_t shape = ti.shape;
+  const int y0 = 2 * u, ch = MCT_TH(shape) >> 1, cwd = MCT_TW(shape) >> 1, nl = MCT_NL(shape);
+  if (!MCT_VALID(shape) || y0 >= ch) return;
   int v[2][2][8];
 #pragma unroll
   for (int s = 0; s < 2; s++) {
-    if (s < ti.nl && !ti.missing[s]) {
+    const uint32_t cw_ = s < nl ? ti.c[s] : 0x80000000u;
+    if (!MCT_MISSING(cw_)) {
       uint32_t tv[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) tv[k] = tab.ev[ti.cyf[s]][k];
-      mct_vpair4(interm + g.ci_off + (tile * g.nl + s) * g.ci_words + pl * g.ci_plane + u * g.ci_pitch, g.ci_pitch, tv, ti.csh6[s], v[s]);
+      for (int k = 0; k < 3; k++) tv[k] = tab.ev[MCT_YF(cw_)][k];
+      mct_vpair4(interm + g.ci_off + (tile * g.nl + s) * g.ci_words + pl * g.ci_plane + u * g.ci_pitch, g.ci_pitch, tv, MCT_SH6(cw_), v[s]);
     } else {
-      const int fill = s < ti.nl ? (1 << 13) : 0;
+      const int fill = s < nl ? (1 << 13) : 0;
 #pragma unroll
       for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -412,7 +437,7 @@ MCT_HD void mct_pass2_chroma(int t, const MctGeom& g, const MctTile* info, const
   const Mc8Weight w = ti.w[1 + pl];
   uint8_t* dst = (pl ? cr : cb) + ti.dst_c + (size_t)y0 * pitch;
   const int nr = ch - y0 < 2 ? 1 : 2;
-  if (ti.plain) {
+  if (MCT_PLAIN(shape)) {
 #pragma unroll
     for (int i = 0; i < 2; i++)
       if (i < nr) mct_store_row(dst + (size_t)i * pitch, mct_plain4(&v[0][i][0], &v[1][i][0], w.rnd, w.shift), mct_plain4(&v[0][i][4], &v[1][i][4], w.rnd, w.shift), cwd);
@@ -435,7 +460,7 @@ MCT_HD MctBox mct_decode_tile(uint32_t word, int s, const b200_pu* pus, const b2
   MctBox bx;
   bx.active = 0; bx.slot = -1; bx.lx = bx.ly = bx.cx = bx.cy = 0;
   if (word == MCT_INVALID) {
-    if (s == 0) ti->valid = 0;
+    if (s == 0) ti->shape = 0;
     return bx;
   }
   const b200_pu pu = pus[word & 0xFFFFF];
@@ -446,12 +471,11 @@ MCT_HD MctBox mct_decode_tile(uint32_t word, int s, const b200_pu* pus, const b2
   const int nl = (use0 && use1) ? 2 : 1;
   const int first = use0 ? 0 : 1;
   if (s == 0) {
-    ti->valid = (use0 || use1) ? 1 : 0;
-    ti->tw = (uint8_t)tw; ti->th = (uint8_t)th; ti->nl = (uint8_t)nl;
+    const bool wgt_ = pu.flags & B200_PU_WEIGHTED;
+    ti->shape = (uint32_t)tw | ((uint32_t)th << 8) | ((uint32_t)nl << 16) | ((use0 || use1) ? 1u << 24 : 0u) | (wgt_ ? 0u : 1u << 25);
     ti->dst_y = y0 * pic.pitch[0] + x0;
     ti->dst_c = (y0 >> 1) * pic.pitch[1] + (x0 >> 1);
     const bool wgt = pu.flags & B200_PU_WEIGHTED;
-    ti->plain = wgt ? 0 : 1;
     const b200_weight_entry* we = wts + (wgt ? pu.wt_idx : 0);
 #pragma unroll
     for (int c = 0; c < 3; c++) ti->w[c] = mc8_weight(nl == 2, wgt, first, we, c);
@@ -462,20 +486,15 @@ MCT_HD MctBox mct_decode_tile(uint32_t word, int s, const b200_pu* pus, const b2
   const bool missing = slot < 0 || !((valid_slots >> slot) & 1);
   const int mvx = pu.mv[l][0], mvy = pu.mv[l][1];
   const int xf = mvx & 3, yf = mvy & 3, cxf = mvx & 7, cyf = mvy & 7;
-  ti->missing[s] = missing;
-  ti->hidx[s] = (uint8_t)((xf == 0 && yf == 0) ? 4 : xf);  // full-sample position: gain 64 (<< 6) in pass 1, identity in pass 2
-  ti->yf[s] = (uint8_t)yf;
-  ti->sh6[s] = (uint8_t)((xf && yf) ? 6 : 0);
-  ti->chidx[s] = (uint8_t)((cxf == 0 && cyf == 0) ? 8 : cxf);
-  ti->cyf[s] = (uint8_t)cyf;
-  ti->csh6[s] = (uint8_t)((cxf && cyf) ? 6 : 0);
+  const uint32_t hidx = (xf == 0 && yf == 0) ? 4 : xf;      // full-sample position: gain 64 (<< 6) in pass 1, identity in pass 2
+  const uint32_t chidx = (cxf == 0 && cyf == 0) ? 8 : cxf;
   // window origin = first sample the 8-tap (4-tap) filters touch, moved to the border's rim when further out (see engine.cu)
   const int wx = mct_clip3(-B200_PAD_X, pic.w + B200_PAD_X - 23, x0 + (mvx >> 2) - 3);
   const int wy = mct_clip3(-B200_PAD_Y, pic.h + B200_PAD_Y - 23, y0 + (mvy >> 2) - 3);
   const int cwx = mct_clip3(-B200_PAD_CX, pic.cw + B200_PAD_CX - 11, (x0 >> 1) + (mvx >> 3) - 1);
   const int cwy = mct_clip3(-B200_PAD_CY, pic.ch + B200_PAD_CY - 11, (y0 >> 1) + (mvy >> 3) - 1);
-  ti->xo[s] = (uint8_t)(wx & 15);
-  ti->cxo[s] = (uint8_t)(cwx & 15);
+  ti->l[s] = (uint32_t)(wx & 15) | (hidx << 8) | ((uint32_t)yf << 16) | ((xf && yf) ? 6u << 24 : 0u) | (missing ? 0x80000000u : 0u);
+  ti->c[s] = (uint32_t)(cwx & 15) | (chidx << 8) | ((uint32_t)cyf << 16) | ((cxf && cyf) ? 6u << 24 : 0u) | (missing ? 0x80000000u : 0u);
   bx.active = !missing;
   bx.slot = slot;
   bx.lx = wx & ~15; bx.ly = wy;
@@ -548,14 +567,12 @@ __global__ void __launch_bounds__(MCT_CTA_THREADS) k_inter_pred_tma(DevPic pic, 
       MctTile* dst = &sm.info[it & 1][tile];
       if (lane < g.ntl) {
         if (s == 0) {  // slot-0 lane owns the common fields; with two lists the slot-1 lane adds its own
-          dst->dst_y = mine.dst_y; dst->dst_c = mine.dst_c; dst->tw = mine.tw; dst->th = mine.th; dst->nl = mine.nl; dst->valid = mine.valid;
-          dst->plain = mine.plain;
+          dst->dst_y = mine.dst_y; dst->dst_c = mine.dst_c; dst->shape = mine.shape;
 #pragma unroll
           for (int c = 0; c < 3; c++) dst->w[c] = mine.w[c];
         }
-        dst->xo[s] = mine.xo[s]; dst->hidx[s] = mine.hidx[s]; dst->yf[s] = mine.yf[s]; dst->sh6[s] = mine.sh6[s];
-        dst->cxo[s] = mine.cxo[s]; dst->chidx[s] = mine.chidx[s]; dst->cyf[s] = mine.cyf[s]; dst->csh6[s] = mine.csh6[s];
-        dst->missing[s] = mine.missing[s];
+        dst->l[s] = mine.l[s];
+        dst->c[s] = mine.c[s];
       }
       if (lane == 0) sm.geom[it & 1] = g;
       if (mi >= 0) {
