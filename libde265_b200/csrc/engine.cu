@@ -317,6 +317,7 @@ struct b200_engine {
   HostPool pool;
   int num_sms = 148;
   long long slot_depth[B200_MAX_SLOTS] = {}, tail_depth[B200_MAX_CTX] = {}, key_depth = 0;  // pick_ctx: dependency depths
+  bool intra_split_planes = false;  // B200_INTRA_SPLIT=1: one intra task per plane in every picture (A/B measurements)
   bool sched_rr = false;        // B200_SCHED=rr: plain round-robin placement (A/B measurements)
   int n_ind = 2, next_ind = 0, ind_run = 0;  // streams for pictures that read no reference (intra pictures), used round-robin (B200_IND_STREAMS)
   int intra_i_grid = 64;        // grid cap of k_intra for such pictures: the DAG is at most ~160 tasks wide, 64 CTAs (512 warps) cover it and leave the other SMs to the P/B pictures (0: one CTA per SM; B200_INTRA_I_GRID)
@@ -337,6 +338,7 @@ struct b200_engine {
   uint64_t launches = 0;
   double host_s[4] = {0, 0, 0, 0};  // submit_picture host time: [0] validate + staging wait, [1] plan + pack, [3] launches (B200_HOST_PROF=1 prints at destroy)
   uint64_t host_n = 0;
+  int host_skip = 0;
   // host scratch reused across pictures
   std::vector<uint32_t> part_a[4][3];  // plan_tus_validate: per part, per k_residual class
   std::vector<uint32_t> pu_tiles[PLAN_PU_PARTS];  // plan_pus_part
@@ -461,12 +463,14 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
     en->pool.start(nt);
   }
   if (const char* e = getenv("B200_INTRA_CTAS")) en->intra_ctas = std::max(1, std::min(4, atoi(e)));
+  if (const char* e = getenv("B200_INTRA_SPLIT")) en->intra_split_planes = atoi(e) != 0;
   if (const char* e = getenv("B200_SCHED")) en->sched_rr = !strcmp(e, "rr");
   if (const char* e = getenv("B200_IND_STREAMS")) en->n_ind = std::max(1, std::min(3, atoi(e)));
   if (const char* e = getenv("B200_INTRA_I_GRID")) en->intra_i_grid = std::max(0, atoi(e));
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
   en->tl_path = getenv("B200_TIMELINE");
+  if (const char* e = getenv("B200_HOST_PROF_SKIP")) en->host_skip = std::max(0, atoi(e));
   if (const char* e = getenv("B200_MC_LEGACY")) en->mc_legacy = atoi(e) != 0;
   if (const char* e = getenv("B200_MC_CTAS")) en->mc_ctas = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("B200_STREAMS")) en->n_ctx = std::max(1, std::min(B200_MAX_CTX, atoi(e)));
@@ -967,25 +971,73 @@ static void plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_
   ip.task_of.clear();
   ip.task_first.clear();
   ip.diag_cnt.assign((size_t)n_diag, 0);
+  // Pictures with inter prediction have few, scattered intra blocks: the per-task overhead of k_intra dominates there, so the
+  // small TUs of ALL planes of a region form one task (luma, then Cb, then Cr) when they are at most 16; intra pictures keep
+  // one task per plane (three shorter dependency chains side by side).
+  const bool merged = pic->n_pu > 0 && !en->intra_split_planes;
   long long cur_key[3] = {-1, -1, -1};
   uint32_t cur_task[3] = {0, 0, 0};
+  uint32_t run[48];  // merged mode: the small intra TUs of the current region (at most 16 + 4 + 4, sized generously)
+  int n_run = 0;
+  long long run_key = -1;
+  auto new_task = [&](uint32_t first_tu) {
+    ip.task_first.push_back(first_tu);
+    ip.diag_cnt[plan_diag_of(p, pic->tus[first_tu])]++;
+    return (uint32_t)ip.task_first.size() - 1;
+  };
+  auto flush_run = [&]() {
+    if (!n_run) return;
+    int cnt[3] = {0, 0, 0};
+    for (int j = 0; j < n_run; j++) cnt[pic->tus[run[j]].cidx]++;
+    const bool one = n_run <= 16;
+    uint32_t t = 0;
+    if (one) t = new_task(run[0]);
+    for (int c = 0; c < 3; c++) {  // plane by plane, decode order inside a plane
+      if (!cnt[c]) continue;
+      bool first = true;
+      for (int j = 0; j < n_run; j++) {
+        if (pic->tus[run[j]].cidx != c) continue;
+        if (!one && first) t = new_task(run[j]);
+        first = false;
+        ip.intra_idx.push_back(run[j]);
+        ip.task_of.push_back(t);
+      }
+    }
+    n_run = 0;
+  };
   for (uint32_t i = ip.i0; i < ip.i1; i++) {
     const b200_tu& tu = pic->tus[i];
     if (!(tu.flags & B200_TU_INTRA)) continue;
     if (tu.cidx > 2 || tu.log2_size < 2 || tu.log2_size > 5 || (((size_t)tu.x << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)wctb ||
         (((size_t)tu.y << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)hctb)
       continue;
-    ip.intra_idx.push_back(i);
     const int c = tu.cidx, G = en->region >> (c ? 1 : 0), nT = 1 << tu.log2_size;
+    if (merged) {
+      if (nT >= G) {  // a TU at least as large as the region is a task of its own
+        flush_run();
+        run_key = -1;
+        ip.intra_idx.push_back(i);
+        ip.task_of.push_back(new_task(i));
+        continue;
+      }
+      const int sh = c ? 1 : 0;
+      const long long key = (((long long)((tu.y << sh) / en->region)) << 20) | ((tu.x << sh) / en->region);
+      if (key != run_key || n_run == 48) {
+        flush_run();
+        run_key = key;
+      }
+      run[n_run++] = i;
+      continue;
+    }
+    ip.intra_idx.push_back(i);
     const long long key = (nT >= G) ? -2 - (long long)i : (((long long)(tu.y / G)) << 20) | (tu.x / G);
     if (key != cur_key[c]) {
       cur_key[c] = key;
-      cur_task[c] = (uint32_t)ip.task_first.size();
-      ip.task_first.push_back(i);
-      ip.diag_cnt[plan_diag_of(p, tu)]++;
+      cur_task[c] = new_task(i);
     }
     ip.task_of.push_back(cur_task[c]);
   }
+  flush_run();
 }
 
 static void plan_intra_B(b200_engine* en, int n_diag, uint32_t* n_task, uint32_t* n_intra)
@@ -1380,8 +1432,8 @@ extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* p
   if (rc) return rc;
   CU(cudaEventRecord(ss.done, cx.stream));
   ss.in_flight = true;
-  en->host_s[0] += tp[0]; en->host_s[1] += tp[1]; en->host_s[3] += now() - t3;
-  en->host_n++;
+  if (en->host_skip > 0) en->host_skip--;  // B200_HOST_PROF_SKIP: leave the warm-up (first-use allocations) out of the profile
+  else { en->host_s[0] += tp[0]; en->host_s[1] += tp[1]; en->host_s[3] += now() - t3; en->host_n++; }
   return B200_OK;
 }
 

@@ -674,14 +674,15 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     if (lane < (int)count) tus[lane] = args.tus[args.list[first + lane]];
     __syncwarp();
     const b200_tu tu0 = tus[0];
-    const int c = tu0.cidx, sh = c ? 1 : 0;
-    const int bd = c ? pic.bd_c : pic.bd_y;
-    const int G = args.region >> sh;  // region size in this plane's samples
-    const bool region = (1 << tu0.log2_size) <= min(G, 8);  // small TUs on a shared-memory tile; larger ones straight from the picture
-    const int rx = region ? tu0.x & ~(G - 1) : tu0.x, ry = region ? tu0.y & ~(G - 1) : tu0.y;  // dependency frame origin
-    const bool filter_plane = !(pic.flags & B200_PIC_INTRA_SMOOTHING_OFF) && (c == 0 || pic.chroma == 3);
-    const int pwid = c ? pic.cw : pic.w, phei = c ? pic.ch : pic.h;
-    int covered = 0;
+    // A task is one large TU, or the small TUs of one region: of one plane, or (pictures with inter prediction) of all planes,
+    // sorted luma | Cb | Cr: up to three SEGMENTS, each with its own plane, tile and dependency frame.
+    const int G0 = args.region >> (tu0.cidx ? 1 : 0);
+    const bool region = (1 << tu0.log2_size) <= min(G0, 8);  // small TUs on a shared-memory tile; larger ones straight from the picture
+    unsigned seg_starts;  // bit i: TU i starts a segment
+    {
+      const int mc = (lane < (int)count) ? tus[lane].cidx : -1, pc = (lane > 0 && lane < (int)count) ? tus[lane - 1].cidx : -1;
+      seg_starts = __ballot_sync(RC_FULL, lane < (int)count && (lane == 0 || mc != pc));
+    }
     {
       // residuals of all the task's TUs, in parallel where the sizes allow: lane i owns TU i's record; 4x4 TUs run one
       // per lane, 8x8 TUs one per quarter-warp, larger ones one after the other on the whole warp.  res holds the TUs'
@@ -689,6 +690,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
       const bool mine = lane < (int)count;
       const b200_tu& mytu = tus[mine ? lane : 0];
       const int l2 = mytu.log2_size, sz = mine ? 1 << (2 * l2) : 0;
+      const int mybd = mytu.cidx ? pic.bd_c : pic.bd_y;
       int incl = sz;
 #pragma unroll
       for (int d = 1; d < 16; d <<= 1) {
@@ -696,11 +698,10 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
         if (lane >= d) incl += up;
       }
       const int my_rbase = incl - sz;
-      covered = __shfl_sync(RC_FULL, incl, 31);  // samples this task writes
       const bool cbf = mine && (mytu.flags & B200_TU_CBF);
       const unsigned m8 = __ballot_sync(RC_FULL, cbf && l2 == 3), mw = __ballot_sync(RC_FULL, cbf && l2 > 3);
       uint32_t* scratch = reinterpret_cast<uint32_t*>(sm.coef[warp]);
-      if (cbf && l2 == 2) res4_lane<P, true>(mytu, args.coeffs + mytu.coeff_off, args.scaling, nullptr, 0, res + my_rbase, bd, scratch, lane, sm.tb);
+      if (cbf && l2 == 2) res4_lane<P, true>(mytu, args.coeffs + mytu.coeff_off, args.scaling, nullptr, 0, res + my_rbase, mybd, scratch, lane, sm.tb);
       __syncwarp();
       for (unsigned rem = m8; rem;) {
         const int q = lane >> 3;
@@ -708,7 +709,8 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
         const bool active = idx < 32u;
         const b200_tu& tu = tus[active ? idx : 0];
         const int rb = __shfl_sync(RC_FULL, my_rbase, active ? idx : 0);
-        res8_quarter<P, true>(active, tu, args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rb, bd, scratch + q * 64, lane & 7, sm.tb);
+        res8_quarter<P, true>(active, tu, args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rb, tu.cidx ? pic.bd_c : pic.bd_y, scratch + q * 64,
+                              lane & 7, sm.tb);
 #pragma unroll
         for (int k = 0; k < 4; k++) rem &= rem - 1;  // (0 & -1 stays 0)
       }
@@ -716,15 +718,20 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
         const int idx = __ffs(rem) - 1;
         const b200_tu& tu = tus[idx];
         const int rb = __shfl_sync(RC_FULL, my_rbase, idx);
-        tu_residual<P, true>(tu, args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rb, bd, sm.coef[warp], sm.g[warp], sm.tb, lane);
+        tu_residual<P, true>(tu, args.coeffs + tu.coeff_off, args.scaling, nullptr, 0, res + rb, tu.cidx ? pic.bd_c : pic.bd_y, sm.coef[warp], sm.g[warp],
+                             sm.tb, lane);
       }
     }
-    // ---- wait: one flag per distinct external neighbour unit, one lane each ----
-    {
-      const int span = region ? (2 * G) >> 2 : (1 << tu0.log2_size) >> 1;
+    // ---- wait: one flag per distinct external neighbour unit, one lane each; segment after segment ----
+    for (unsigned ss = seg_starts; ss; ss &= ss - 1) {
+      const int s0 = __ffs(ss) - 1, s1 = (ss & (ss - 1)) ? __ffs(ss & (ss - 1)) - 1 : (int)count;
+      const b200_tu& ts0 = tus[s0];
+      const int c = ts0.cidx, G = args.region >> (c ? 1 : 0);
+      const int rx = region ? ts0.x & ~(G - 1) : ts0.x, ry = region ? ts0.y & ~(G - 1) : ts0.y;  // dependency frame origin
+      const int span = region ? (2 * G) >> 2 : (1 << ts0.log2_size) >> 1;
       unsigned left = 0, top = 0;
       bool corner = false;
-      if (lane < (int)count) dep_units_of(tus[lane], rx, ry, span, left, corner, top);
+      if (lane >= s0 && lane < s1) dep_units_of(tus[lane], rx, ry, span, left, corner, top);
       left = __reduce_or_sync(RC_FULL, left);
       top = __reduce_or_sync(RC_FULL, top);
       corner = __any_sync(RC_FULL, corner);
@@ -749,6 +756,8 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
 
     if (!region) {
       // ---- one large TU: borders straight from the picture ----
+      const int c = tu0.cidx, bd = c ? pic.bd_c : pic.bd_y;
+      const bool filter_plane = !(pic.flags & B200_PIC_INTRA_SMOOTHING_OFF) && (c == 0 || pic.chroma == 3);
       const int nT = 1 << tu0.log2_size;
       const int gstride = pic.pitch[c] / (int)sizeof(P);
       const P* gsrc = row_ptr<P>(pic.cur[c], pic.pitch[c], tu0.y) + tu0.x;
@@ -759,62 +768,73 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
       }
       block_store<P>(blk, pic.cur[c], pic.pitch[c], tu0.x, tu0.y, nT, lane);
     } else {
-      // ---- a region of small TUs: stage region + top row (2G) + left column (2G) in shared memory, run the TUs in order ----
-      const int TS = RC_TILE_STRIDE;
-      P* tile = blk + TS + 4;  // tile(0,0) = region origin, 4-byte aligned; tile(-1,-1) is blk[3]
-      const int gw = min(G, pwid - rx), gh = min(G, phei - ry);
-      const bool full = (gw == G) && (gh == G);
-      // the interior is only needed where this task does not write it itself (regions partly covered by inter blocks)
-      if (covered < gw * gh) {
-        if (full) {  // whole rows as 4-byte words, like the store below
-          const int wpr = G * (int)sizeof(P) / 4;
+      // ---- regions of small TUs: stage region + top row (2G) + left column (2G) in shared memory, run the TUs in order ----
+      int rbase = 0;
+      for (unsigned ss = seg_starts; ss; ss &= ss - 1) {
+        const int s0 = __ffs(ss) - 1, s1 = (ss & (ss - 1)) ? __ffs(ss & (ss - 1)) - 1 : (int)count;
+        const b200_tu& ts0 = tus[s0];
+        const int c = ts0.cidx, bd = c ? pic.bd_c : pic.bd_y, G = args.region >> (c ? 1 : 0);
+        const int rx = ts0.x & ~(G - 1), ry = ts0.y & ~(G - 1);
+        const bool filter_plane = !(pic.flags & B200_PIC_INTRA_SMOOTHING_OFF) && (c == 0 || pic.chroma == 3);
+        const int pwid = c ? pic.cw : pic.w, phei = c ? pic.ch : pic.h;
+        int covered = 0;  // samples this segment writes
+        for (int i = s0; i < s1; i++) covered += 1 << (2 * tus[i].log2_size);
+        const int TS = RC_TILE_STRIDE;
+        P* tile = blk + TS + 4;  // tile(0,0) = region origin, 4-byte aligned; tile(-1,-1) is blk[3]
+        const int gw = min(G, pwid - rx), gh = min(G, phei - ry);
+        const bool full = (gw == G) && (gh == G);
+        // the interior is only needed where this task does not write it itself (regions partly covered by inter blocks)
+        if (covered < gw * gh) {
+          if (full) {  // whole rows as 4-byte words, like the store below
+            const int wpr = G * (int)sizeof(P) / 4;
+            for (int o = lane; o < G * wpr; o += 32) {
+              const int y = o / wpr, u = o % wpr;  // wpr is a power of two
+              reinterpret_cast<uint32_t*>(tile + y * TS)[u] = __ldcg(reinterpret_cast<const uint32_t*>(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx) + u);
+            }
+          } else {
+            for (int o = lane; o < gw * gh; o += 32) {
+              const int x = o % gw, y = o / gw;
+              tile[y * TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx + x);
+            }
+          }
+        }
+        if (ry > 0)
+          for (int x = lane - 1; x < 2 * G; x += 32)
+            if (rx + x >= 0 && rx + x < pwid) tile[-TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry - 1) + rx + x);
+        if (rx > 0)  // left column incl. the bottom-left reach (available when the region is a top-left child of its parent block)
+          for (int y = lane; y < 2 * G; y += 32)
+            if (ry + y < phei) tile[y * TS - 1] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx - 1);
+        __syncwarp();
+        for (int i = s0; i < s1; i++) {
+          const b200_tu& tu = tus[i];
+          P* tdst = tile + (tu.y - ry) * TS + (tu.x - rx);
+          const res_t* tres = (tu.flags & B200_TU_CBF) ? res + rbase : nullptr;
+          if (!intra_fast_ok(tu)) tu_intra_small<P>(tu, tdst, TS, bd, filter_plane, tres, lane);
+          else if (tu.log2_size == 2) tu_intra_fast<P, 2>(tu, tdst, TS, bd, filter_plane, tres, lane);
+          else tu_intra_fast<P, 3>(tu, tdst, TS, bd, filter_plane, tres, lane);
+          rbase += 1 << (2 * tu.log2_size);
+        }
+        if (full) {  // whole rows as 4-byte words (tile rows are 4-byte aligned: TS * sizeof(P) and the origin offset are multiples of 4)
+          const int wpr = G * (int)sizeof(P) / 4;  // words per row
           for (int o = lane; o < G * wpr; o += 32) {
             const int y = o / wpr, u = o % wpr;  // wpr is a power of two
-            reinterpret_cast<uint32_t*>(tile + y * TS)[u] = __ldcg(reinterpret_cast<const uint32_t*>(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx) + u);
+            reinterpret_cast<uint32_t*>(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx)[u] = reinterpret_cast<const uint32_t*>(tile + y * TS)[u];
           }
         } else {
           for (int o = lane; o < gw * gh; o += 32) {
             const int x = o % gw, y = o / gw;
-            tile[y * TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx + x);
+            row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y)[rx + x] = tile[y * TS + x];
           }
         }
-      }
-      if (ry > 0)
-        for (int x = lane - 1; x < 2 * G; x += 32)
-          if (rx + x >= 0 && rx + x < pwid) tile[-TS + x] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry - 1) + rx + x);
-      if (rx > 0)  // left column incl. the bottom-left reach (available when the region is a top-left child of its parent block)
-        for (int y = lane; y < 2 * G; y += 32)
-          if (ry + y < phei) tile[y * TS - 1] = __ldcg(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx - 1);
-      __syncwarp();
-      int rbase = 0;
-      for (uint32_t i = 0; i < count; i++) {
-        const b200_tu& tu = tus[i];
-        P* tdst = tile + (tu.y - ry) * TS + (tu.x - rx);
-        const res_t* tres = (tu.flags & B200_TU_CBF) ? res + rbase : nullptr;
-        if (!intra_fast_ok(tu)) tu_intra_small<P>(tu, tdst, TS, bd, filter_plane, tres, lane);
-        else if (tu.log2_size == 2) tu_intra_fast<P, 2>(tu, tdst, TS, bd, filter_plane, tres, lane);
-        else tu_intra_fast<P, 3>(tu, tdst, TS, bd, filter_plane, tres, lane);
-        rbase += 1 << (2 * tu.log2_size);
-      }
-      if (full) {  // whole rows as 4-byte words (tile rows are 4-byte aligned: TS * sizeof(P) and the origin offset are multiples of 4)
-        const int wpr = G * (int)sizeof(P) / 4;  // words per row
-        for (int o = lane; o < G * wpr; o += 32) {
-          const int y = o / wpr, u = o % wpr;  // wpr is a power of two
-          reinterpret_cast<uint32_t*>(row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y) + rx)[u] = reinterpret_cast<const uint32_t*>(tile + y * TS)[u];
-        }
-      } else {
-        for (int o = lane; o < gw * gh; o += 32) {
-          const int x = o % gw, y = o / gw;
-          row_ptr<P>(pic.cur[c], pic.pitch[c], ry + y)[rx + x] = tile[y * TS + x];
-        }
+        __syncwarp();  // the tile is reused by the next segment
       }
     }
     __threadfence();  // release: samples before flags
     __syncwarp();
     if (lane < (int)count) {  // one lane per TU clears the TU's pending units
       const b200_tu& tu = tus[lane];
-      const int n4 = 1 << (tu.log2_size - 2), pw = args.pend_w[c];
-      volatile uint8_t* pend = args.pend[c] + (tu.y >> 2) * pw + (tu.x >> 2);
+      const int n4 = 1 << (tu.log2_size - 2), pw = args.pend_w[tu.cidx];
+      volatile uint8_t* pend = args.pend[tu.cidx] + (tu.y >> 2) * pw + (tu.x >> 2);
       for (int j = 0; j < n4; j++)
         for (int i = 0; i < n4; i++) pend[j * pw + i] = 0;
     }
@@ -822,7 +842,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
     if (args.trace && lane == 0) {
       const unsigned long long c2 = clock64();
       unsigned long long* tr = args.trace + 4ull * t;
-      tr[0] = tr_t0; tr[1] = tr_c1 - tr_c0; tr[2] = c2 - tr_c1; tr[3] = count | ((unsigned long long)c << 8) | ((unsigned long long)tu0.log2_size << 16);
+      tr[0] = tr_t0; tr[1] = tr_c1 - tr_c0; tr[2] = c2 - tr_c1; tr[3] = count | ((unsigned long long)tu0.cidx << 8) | ((unsigned long long)tu0.log2_size << 16);
     }
   }
 }

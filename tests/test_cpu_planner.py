@@ -73,19 +73,29 @@ def check_picture(lib, pic):
     assert ts[0] == 0 and ts[-1] == len(lb) and (np.diff(ts.astype(np.int64)) >= 1).all() and (np.diff(ts.astype(np.int64)) <= 16).all()
     owner = [np.full(((pic.params.height >> (1 if c else 0)) // 4 + 1, (pic.params.width >> (1 if c else 0)) // 4 + 1), -1, np.int64) for c in range(3)]
     task_of = {}
+    merged = len(pus) > 0  # pictures with inter prediction: the small TUs of ALL planes of a region form one task (luma | Cb | Cr)
+    n_merged = 0
     for t in range(len(ts) - 1):
         members = lb[ts[t]:ts[t + 1]]
-        c0 = int(tus["cidx"][members[0]])
-        G = 16 >> (1 if c0 else 0)
-        assert (np.diff(members.astype(np.int64)) > 0).all(), "decode order inside a task"
-        for i in members:
-            tu = tus[i]
-            assert int(tu["cidx"]) == c0
-            nT = 1 << int(tu["log2_size"])
-            if len(members) > 1:
-                assert nT < G and int(tu["x"]) // G == int(tus["x"][members[0]]) // G and int(tu["y"]) // G == int(tus["y"][members[0]]) // G
-            task_of[int(i)] = t
-            owner[c0][int(tu["y"]) // 4:(int(tu["y"]) + nT) // 4, int(tu["x"]) // 4:(int(tu["x"]) + nT) // 4] = t
+        planes = [int(tus["cidx"][i]) for i in members]
+        assert planes == sorted(planes), "planes in the order luma, Cb, Cr inside a task"
+        if len(set(planes)) > 1:
+            assert merged
+            n_merged += 1
+        rx0, ry0 = (int(tus["x"][members[0]]) << (1 if planes[0] else 0)) // 16, (int(tus["y"][members[0]]) << (1 if planes[0] else 0)) // 16
+        for c0 in sorted(set(planes)):
+            seg = np.array([i for i in members if int(tus["cidx"][i]) == c0])
+            G = 16 >> (1 if c0 else 0)
+            assert (np.diff(seg.astype(np.int64)) > 0).all(), "decode order inside a plane of a task"
+            for i in seg:
+                tu = tus[i]
+                nT = 1 << int(tu["log2_size"])
+                if len(members) > 1:
+                    sh = 1 if c0 else 0
+                    assert nT < G and (int(tu["x"]) << sh) // 16 == rx0 and (int(tu["y"]) << sh) // 16 == ry0
+                task_of[int(i)] = t
+                owner[c0][int(tu["y"]) // 4:(int(tu["y"]) + nT) // 4, int(tu["x"]) // 4:(int(tu["x"]) + nT) // 4] = t
+    assert merged or n_merged == 0
     # ---- topological order ----
     for i, t in task_of.items():
         tu = tus[i]
