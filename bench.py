@@ -377,11 +377,15 @@ def run_config(name, eng, torch, dist, stream, a, rank, local_rank, world, headl
         for h in prepared[32 * v:32 * (v + 1)]:
             eng.run_prepared(h)
 
+    # e2e goes through the asynchronous submission call (pictures planned by the engine's planner threads, issued in order; the
+    # read-back is queued behind its picture); B200_E2E_SYNC=1 measures the one-picture-at-a-time b200_engine_submit_picture instead
+    submit = eng.submit if os.environ.get("B200_E2E_SYNC") else eng.submit_async
+
     def step_e2e():
         v = counter["step"] % STEP_VARIANTS
         counter["step"] += 1
         for i, p in enumerate(seq[32 * v:32 * (v + 1)]):
-            eng.submit(p)
+            submit(p)
             o = outs[i & 7]
             capi.check(eng.lib.b200_engine_read_slot_async(eng.handle, p.params.dst_slot, capi.PlaneArray(*[t.data_ptr() for t in o]),
                                                            capi.StrideArray(*[t.stride(0) * bps for t in o])), "read_slot_async")

@@ -226,6 +226,16 @@ B200_API void b200_engine_destroy(b200_engine*);
  * engine's stream, leaving the picture resident in DPB slot params.dst_slot. */
 B200_API int  b200_engine_submit_picture(b200_engine*, const b200_picture*);
 
+/* Asynchronous submission: queues the picture and returns; planner threads validate / plan / pack whole pictures in parallel and one
+ * sequencer thread issues them to the GPU in submission order, exactly as b200_engine_submit_picture would (same stream placement,
+ * same results).  The record ARRAYS the picture points to must stay valid until b200_engine_flush (or _sync, _read_slot, _wait_slot)
+ * returns; the b200_picture struct itself is copied.  b200_engine_read_slot_async calls are queued behind the pictures submitted
+ * before them.  Errors of queued pictures (malformed records) are reported by the next flush / sync: the picture is skipped.
+ * For hosts that produce pictures faster than one thread can plan them (parallel parsers, cached records, bench.py e2e). */
+B200_API int  b200_engine_submit_picture_async(b200_engine*, const b200_picture*);
+/* Blocks until everything queued has been issued to the GPU (not until the GPU has finished: see b200_engine_sync). */
+B200_API int  b200_engine_flush(b200_engine*);
+
 /* Prepared pictures: validate + upload the records ONCE and keep them resident in HBM; running a prepared
  * picture only launches the kernels (bench.py `value`: inputs already resident when the timed region starts;
  * also the replay path for cached pictures).  A prepared picture keeps its own device arena until freed. */

@@ -304,8 +304,10 @@ struct IntraPart {
   std::vector<uint32_t> intra_idx, task_of, task_first, diag_cnt, diag_off, fill;
 };
 
+struct AsyncState;
 struct b200_engine {
   int device = 0;
+  AsyncState* async = nullptr;  // b200_engine_submit_picture_async: planner threads + the in-order sequencer (created on first use)
   PipeCtx ctx[B200_MAX_CTX];
   // Record staging: pinned host buffer + device arena per picture in flight, handed out round-robin whatever stream the picture
   // runs on (a set is reused when the kernels of the picture that used it B200_STAGE_SETS pictures ago have finished)
@@ -321,6 +323,8 @@ struct b200_engine {
   bool sched_rr = false;        // B200_SCHED=rr: plain round-robin placement (A/B measurements)
   int n_ind = 2, next_ind = 0, ind_run = 0;  // streams for pictures that read no reference (intra pictures), used round-robin (B200_IND_STREAMS)
   int intra_i_grid = 64;        // grid cap of k_intra for such pictures: the DAG is at most ~160 tasks wide, 64 CTAs (512 warps) cover it and leave the other SMs to the P/B pictures (0: one CTA per SM; B200_INTRA_I_GRID)
+  unsigned int *intra_err = nullptr, *intra_err_host = nullptr;  // k_intra gave up a dependency wait (device word; mapped host copy)
+  unsigned long long spin_limit_ns = 2000000000ull;              // B200_INTRA_SPIN_LIMIT_MS
   int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
   int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
   // B200_TIMELINE=<file>: a CUDA event before and after every launch; the intervals of all streams (ms since the first launch)
@@ -338,6 +342,11 @@ struct b200_engine {
   uint64_t launches = 0;
   double host_s[4] = {0, 0, 0, 0};  // submit_picture host time: [0] validate + staging wait, [1] plan + pack, [3] launches (B200_HOST_PROF=1 prints at destroy)
   uint64_t host_n = 0;
+  // asynchronous path, same switch: [0] planner busy (sum over threads), [1] sequencer waiting for a plan, [2] sequencer issuing pictures,
+  // [3] sequencer issuing read-backs; run_layout segments: [4] surfaces + H2D copy, [5] order_before, [6] kernels, [7] border + order_after
+  double async_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t async_n = 0;
+  bool host_prof = false;
   int host_skip = 0;
   // host scratch reused across pictures
   std::vector<uint32_t> part_a[4][3];  // plan_tus_validate: per part, per k_residual class
@@ -347,6 +356,9 @@ struct b200_engine {
   IntraPart ipart[PLAN_INTRA_PARTS];              // plan_intra_*
   std::vector<uint32_t> ctb_count, tiles, tiles_sorted, list_a, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
 };
+
+static int async_flush(b200_engine* en);
+static void async_stop(b200_engine* en);
 
 #define TIMING_RING 256
 
@@ -468,8 +480,10 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   if (const char* e = getenv("B200_IND_STREAMS")) en->n_ind = std::max(1, std::min(3, atoi(e)));
   if (const char* e = getenv("B200_INTRA_I_GRID")) en->intra_i_grid = std::max(0, atoi(e));
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
+  if (const char* e = getenv("B200_INTRA_SPIN_LIMIT_MS")) en->spin_limit_ns = 1000000ull * (unsigned long long)std::max(1, std::min(60000, atoi(e)));
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
   en->tl_path = getenv("B200_TIMELINE");
+  en->host_prof = getenv("B200_HOST_PROF") != nullptr;
   if (const char* e = getenv("B200_HOST_PROF_SKIP")) en->host_skip = std::max(0, atoi(e));
   if (const char* e = getenv("B200_MC_LEGACY")) en->mc_legacy = atoi(e) != 0;
   if (const char* e = getenv("B200_MC_CTAS")) en->mc_ctas = std::max(1, std::min(8, atoi(e)));
@@ -480,6 +494,10 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
     CU(cudaEventCreateWithFlags(&cx.tail, cudaEventDisableTiming));
   }
   for (auto& st : en->stage_pool) CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  CU(cudaMalloc(&en->intra_err, 256));
+  CU(cudaMemset(en->intra_err, 0, 256));
+  CU(cudaHostAlloc(&en->intra_err_host, 64, cudaHostAllocMapped));
+  *en->intra_err_host = 0;
   for (auto& ss : en->ssync) {
     CU(cudaEventCreateWithFlags(&ss.written, cudaEventDisableTiming));
     for (int k = 0; k < B200_MAX_CTX; k++) CU(cudaEventCreateWithFlags(&ss.read[k], cudaEventDisableTiming));
@@ -496,9 +514,16 @@ extern "C" void b200_engine_destroy(b200_engine* en)
 {
   if (!en) return;
   cudaSetDevice(en->device);
+  async_stop(en);
   cudaDeviceSynchronize();
   tl_flush(en);
   if (en->tl_base) cudaEventDestroy(en->tl_base);
+  if (getenv("B200_HOST_PROF") && en->async_n)
+    fprintf(stderr, "[b200] submit_picture_async host ms/picture over %llu pictures: planner busy (all threads) %.3f | sequencer: waiting for a plan %.3f  "
+            "pictures %.3f (surfaces+H2D %.3f  order_before %.3f  kernels %.3f  borders+order_after %.3f)  read-backs %.3f\n",
+            (unsigned long long)en->async_n, 1e3 * en->async_s[0] / en->async_n, 1e3 * en->async_s[1] / en->async_n, 1e3 * en->async_s[2] / en->async_n,
+            1e3 * en->async_s[4] / en->async_n, 1e3 * en->async_s[5] / en->async_n, 1e3 * en->async_s[6] / en->async_n, 1e3 * en->async_s[7] / en->async_n,
+            1e3 * en->async_s[3] / en->async_n);
   if (getenv("B200_HOST_PROF") && en->host_n)
     fprintf(stderr, "[b200] submit_picture host ms/picture over %llu pictures: validate+staging-wait %.3f  plan+pack (threaded) %.3f  launch %.3f\n",
             (unsigned long long)en->host_n, 1e3 * en->host_s[0] / en->host_n, 1e3 * en->host_s[1] / en->host_n, 1e3 * en->host_s[3] / en->host_n);
@@ -521,10 +546,23 @@ extern "C" void b200_engine_destroy(b200_engine* en)
   }
   for (auto& e : en->tev)
     if (e) cudaEventDestroy(e);
+  if (en->intra_err) cudaFree(en->intra_err);
+  if (en->intra_err_host) cudaFreeHost(en->intra_err_host);
   delete en;
 }
 
 extern "C" void* b200_engine_stream(b200_engine* en) { return en ? (void*)en->ctx[0].stream : nullptr; }
+
+// After a synchronisation point: did k_intra give up a dependency wait (ReconArgs::err)?  Reported once, then cleared.
+static int check_intra_err(b200_engine* en)
+{
+  if (!en->intra_err_host || !*(volatile unsigned int*)en->intra_err_host) return B200_OK;
+  const unsigned int t = *(volatile unsigned int*)en->intra_err_host - 1;
+  for (int k = 0; k < B200_MAX_CTX; k++) cudaStreamSynchronize(en->ctx[k].stream);
+  *(volatile unsigned int*)en->intra_err_host = 0;
+  cudaMemset(en->intra_err, 0, sizeof(unsigned int));
+  return set_err(B200_ERR_INVALID, "intra task %u: a neighbour named by the avail bits is never reconstructed before it (dependency wait gave up); picture damaged", t);
+}
 
 static int sync_all(b200_engine* en)
 {
@@ -534,13 +572,14 @@ static int sync_all(b200_engine* en)
     ss.writer = -1;
     for (auto& r : ss.read_pending) r = false;
   }
-  return B200_OK;
+  return check_intra_err(en);
 }
 
 extern "C" int b200_engine_set_streams(b200_engine* en, int n)
 {
   if (!en || n < 1 || n > B200_MAX_CTX) return set_err(B200_ERR_INVALID, "stream count must be 1..%d", B200_MAX_CTX);
   CU(cudaSetDevice(en->device));
+  { const int frc = async_flush(en); if (frc) return frc; }
   int rc = sync_all(en);
   if (rc) return rc;
   en->n_ctx = n;
@@ -555,6 +594,7 @@ extern "C" int b200_engine_join(b200_engine* en)
 {
   if (!en) return set_err(B200_ERR_INVALID, "null engine");
   CU(cudaSetDevice(en->device));
+  { const int frc = async_flush(en); if (frc) return frc; }
   for (int k = 1; k < B200_MAX_CTX; k++) {
     CU(cudaEventRecord(en->ctx[k].tail, en->ctx[k].stream));
     CU(cudaStreamWaitEvent(en->ctx[0].stream, en->ctx[k].tail, 0));
@@ -690,6 +730,9 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
     ra.ticket = (unsigned int*)cx.sync_buf;
     ra.region = en->region;
     ra.poll_ns = en->poll_ns;
+    ra.err = en->intra_err;
+    ra.err_host = en->intra_err_host;
+    ra.spin_limit_ns = en->spin_limit_ns;
     const size_t cw4 = (size_t)((dp.cw + 3) / 4), ch4 = (size_t)((dp.ch + 3) / 4);
     ra.pend[0] = cx.sync_buf + 256;
     ra.pend[1] = ra.pend[0] + (size_t)dp.w4 * dp.h4;
@@ -919,6 +962,16 @@ static int plan_tus_validate(b200_engine* en, const b200_picture* pic, int part,
     if ((tu.flags & B200_TU_PCM) && tu.n_coeff != nT * nT) return set_err(B200_ERR_INVALID, "PCM TU %u sample count", i);
     if (tu.flags & B200_TU_INTRA) {
       if (tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
+      // avail bits must name samples inside the picture (k_intra reads the border and the pending flags at those positions)
+      const int half = nT >> 1;  // groups of 4 samples per side
+      const uint32_t gm = half >= 32 ? 0xffffffffu : (1u << half) - 1u;
+      const uint32_t left = (uint32_t)tu.avail & 0xffffu, top = (uint32_t)(tu.avail >> B200_AVAIL_TOP_BIT0) & 0xffffu;
+      const bool corner = (tu.avail >> B200_AVAIL_CORNER_BIT) & 1;
+      const int rows_below = (ph - tu.y) >> 2, cols_right = (pw - tu.x) >> 2;  // groups that still lie inside the plane
+      const uint32_t lm = rows_below >= 16 ? 0xffffu : (1u << rows_below) - 1u, tm = cols_right >= 16 ? 0xffffu : (1u << cols_right) - 1u;
+      if ((left & ~gm) || (top & ~gm) || (tu.avail >> (B200_AVAIL_TOP_BIT0 + 16)) || (left && tu.x == 0) || (top && tu.y == 0) ||
+          (corner && (tu.x == 0 || tu.y == 0)) || (left & ~lm) || (top & ~tm))
+        return set_err(B200_ERR_INVALID, "TU %u intra availability names samples outside the picture", i);
     } else if (tu.flags & (B200_TU_CBF | B200_TU_PCM)) {
       if ((tu.flags & B200_TU_PCM) || tu.log2_size > 3) la.push_back(i);
       else if (tu.log2_size == 3) la8.push_back(i);
@@ -1255,7 +1308,23 @@ extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8
     plan_intra_finish(en, pic, &L, n_diag);
   }
   t[4] = now();
-  if (prof) fprintf(stderr, "[b200] plan (one thread) ms: begin %.3f  PUs %.3f  TU validate %.3f  intra tasks %.3f\n", 1e3 * (t[1] - t[0]), 1e3 * (t[2] - t[1]), 1e3 * (t[3] - t[2]), 1e3 * (t[4] - t[3]));
+  if (prof) {
+    double u[4];
+    u[0] = now();
+    for (int part = 0; part < PLAN_PU_PARTS && !rc; part++) en->pu_ref_mask[part] = 0;
+    if (!rc) rc = plan_pus_merge(en, pic, &L);
+    u[1] = now();
+    if (!rc) {
+      const b200_pic_params& pp = pic->params;
+      const int S = 1 << pp.log2_ctb_size, wctb = (pp.width + S - 1) / S, hctb = (pp.height + S - 1) / S;
+      plan_intra_finish(en, pic, &L, wctb + 2 * hctb);
+    }
+    u[2] = now();
+    merge_list_a(en, &L);
+    u[3] = now();
+    fprintf(stderr, "[b200] plan (one thread) ms: begin %.3f  PUs %.3f  TU validate %.3f  intra tasks %.3f | serial tail: PU merge %.3f  intra finish %.3f  list_a merge %.3f\n",
+            1e3 * (t[1] - t[0]), 1e3 * (t[2] - t[1]), 1e3 * (t[3] - t[2]), 1e3 * (t[4] - t[3]), 1e3 * (u[1] - u[0]), 1e3 * (u[2] - u[1]), 1e3 * (u[3] - u[2]));
+  }
   if (!rc) {
     merge_list_a(en, &L);
     plan_finish(&L);
@@ -1314,6 +1383,9 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
   PipeCtx& cx = en->ctx[k];
   const b200_pic_params& p = L.params;
   Surface& dst = en->slot[p.dst_slot];
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const bool prof = en->host_prof && en->async && en->host_skip <= 0;
+  double tseg[5] = {prof ? now() : 0.0, 0, 0, 0, 0};
   int rc = surface_ensure(dst, p, cx.stream);
   if (rc) return rc;
   Surface* cur = &dst;
@@ -1344,12 +1416,15 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
   en->ev = en->timing ? &en->tev[(size_t)(en->tcount % TIMING_RING) * 7] : nullptr;
   if (en->timing) CU(cudaEventRecord(en->ev[0], st));
   if (upload_from) CU(cudaMemcpyAsync(dbase, upload_from, L.total, cudaMemcpyHostToDevice, st));  // records first: overlaps the waits below
+  if (prof) tseg[1] = now();
   rc = order_before(en, k, L);
   if (rc) return rc;
+  if (prof) tseg[2] = now();
   const DevPic dp = make_devpic(p, *cur, dst);
   if (p.bit_depth_luma > 8) rc = launch_picture<uint16_t>(en, cx, L, dp, refs, dbase);
   else rc = launch_picture<uint8_t>(en, cx, L, dp, refs, dbase);
   if (rc) return rc;
+  if (prof) tseg[3] = now();
   if (en->tl_path) tl_begin(en, st, "extend", L.params.poc, k);
   launch_extend_borders(dst, st);  // the finished picture may be referenced: replicate its edges into the border
   if (en->tl_path) tl_end(en, st);
@@ -1359,6 +1434,10 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
   rc = order_after(en, k, L);
   if (rc) return rc;
   dst.valid = true;
+  if (prof) {
+    tseg[4] = now();
+    for (int i = 0; i < 4; i++) en->async_s[4 + i] += tseg[i + 1] - tseg[i];
+  }
   return B200_OK;
 }
 
@@ -1415,10 +1494,219 @@ static int pick_ctx(b200_engine* en, uint32_t ref_mask, int dst_slot)
   return k;
 }
 
+// ---- asynchronous submission ------------------------------------------------------------------------------------------------
+// b200_engine_submit_picture spends ~1 ms of host time per 4K picture (validation, work lists, packing), spread over the pool
+// threads but with serial joins; a host that produces pictures faster than that (a parser with several slice / WPP threads, a
+// cache of recorded pictures, bench.py's e2e leg) is held up by it.  The asynchronous path plans WHOLE pictures in parallel: the
+// caller only queues the picture; N planner threads (each with private scratch: a "shadow" engine without CUDA state) validate /
+// plan / pack one picture each into its staging set; ONE sequencer thread takes the queue in submission order, waits for the
+// picture's plan, and issues the copies and kernels exactly as the synchronous path does — so stream placement, DPB ordering and
+// results are identical.  Reads of finished pictures (b200_engine_read_slot_async) are queued behind the picture they follow.
+struct AsyncCmd {
+  int kind = 0;  // 0 picture, 1 read slot
+  b200_picture pic{};
+  PicLayout L;
+  StagingSet* ss = nullptr;
+  int rc = B200_OK;
+  std::string err;
+  int state = 0;  // 0 queued, 1 being planned, 2 planned (guarded by AsyncState::m)
+  int slot = 0;
+  void* planes[3] = {nullptr, nullptr, nullptr};
+  size_t strides[3] = {0, 0, 0};
+};
+struct AsyncState {
+  std::mutex m;
+  std::condition_variable cv_plan, cv_seq, cv_space;
+  std::deque<AsyncCmd*> q;  // submission order; the front is the next one the sequencer executes
+  std::vector<std::thread> planners;
+  std::thread sequencer;
+  std::vector<b200_engine*> shadows;
+  bool stop = false;
+  int first_rc = B200_OK;
+  std::string first_err;
+};
+#define B200_ASYNC_DEPTH 16  // < B200_STAGE_SETS: a staging set is never handed out again before its previous picture was launched
+
+static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase, const uint8_t* upload_from);
+static int pick_ctx(b200_engine* en, uint32_t ref_mask, int dst_slot);
+static int read_slot_async_now(b200_engine* en, int slot, void* const planes[3], const size_t strides[3]);
+
+static inline double prof_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static void async_planner(b200_engine* en, b200_engine* shadow)
+{
+  AsyncState* as = en->async;
+  cudaSetDevice(en->device);
+  for (;;) {
+    AsyncCmd* cmd = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(as->m);
+      for (;;) {
+        if (as->stop) return;
+        for (AsyncCmd* c : as->q)
+          if (c->kind == 0 && c->state == 0) { cmd = c; break; }
+        if (cmd) break;
+        as->cv_plan.wait(lk);
+      }
+      cmd->state = 1;
+    }
+    const double tp0 = en->host_prof ? prof_now() : 0.0;
+    const int rc = plan_and_pack(shadow, &cmd->pic, &cmd->L, *cmd->ss, nullptr);
+    const double tp1 = en->host_prof ? prof_now() : 0.0;
+    {
+      std::lock_guard<std::mutex> lk(as->m);
+      if (en->host_skip <= 0) en->async_s[0] += tp1 - tp0;
+      cmd->rc = rc;
+      if (rc) cmd->err = g_err;
+      cmd->state = 2;
+    }
+    as->cv_seq.notify_all();
+  }
+}
+
+static void async_sequencer(b200_engine* en)
+{
+  AsyncState* as = en->async;
+  cudaSetDevice(en->device);
+  for (;;) {
+    AsyncCmd* cmd = nullptr;
+    double ts[3] = {0, 0, 0};
+    {
+      std::unique_lock<std::mutex> lk(as->m);
+      as->cv_seq.wait(lk, [&] { return as->stop || !as->q.empty(); });  // an empty queue is idle time, not waiting for a plan
+      if (as->stop) return;
+      if (en->host_prof) ts[0] = prof_now();
+      as->cv_seq.wait(lk, [&] { return as->stop || (!as->q.empty() && (as->q.front()->kind != 0 || as->q.front()->state == 2)); });
+      if (as->stop) return;
+      cmd = as->q.front();
+    }
+    if (en->host_prof) ts[1] = prof_now();
+    int rc = cmd->rc;
+    if (cmd->kind == 0) {
+      if (!rc) {
+        const int k = pick_ctx(en, cmd->L.ref_mask, cmd->L.params.dst_slot);
+        rc = run_layout(en, k, cmd->L, cmd->ss->dev, cmd->ss->host);
+        if (!rc) {
+          cudaEventRecord(cmd->ss->done, en->ctx[k].stream);
+          cmd->ss->in_flight = true;
+        }
+      }
+    } else {
+      rc = read_slot_async_now(en, cmd->slot, cmd->planes, cmd->strides);
+    }
+    if (en->host_prof && en->host_skip > 0) {
+      if (cmd->kind == 0) en->host_skip--;  // B200_HOST_PROF_SKIP: warm-up pictures (first-use allocations) stay out of the profile
+    } else if (en->host_prof) {
+      ts[2] = prof_now();
+      en->async_s[1] += ts[1] - ts[0];
+      en->async_s[cmd->kind == 0 ? 2 : 3] += ts[2] - ts[1];
+      if (cmd->kind == 0) en->async_n++;
+    }
+    {
+      std::lock_guard<std::mutex> lk(as->m);
+      if (rc && !as->first_rc) { as->first_rc = rc; as->first_err = cmd->err.empty() ? std::string(g_err) : cmd->err; }
+      as->q.pop_front();
+    }
+    delete cmd;
+    as->cv_space.notify_all();
+    as->cv_seq.notify_all();
+  }
+}
+
+static int async_start(b200_engine* en)
+{
+  if (en->async) return B200_OK;
+  AsyncState* as = new (std::nothrow) AsyncState();
+  if (!as) return set_err(B200_ERR_NOMEM, "out of memory");
+  en->async = as;
+  int n = 6;
+  if (const char* e = getenv("B200_ASYNC_THREADS")) n = std::max(1, std::min(16, atoi(e)));
+  for (int i = 0; i < n; i++) {
+    b200_engine* sh = new b200_engine();  // no CUDA state: only the planner's scratch and the flags the planner reads
+    sh->device = en->device;
+    sh->region = en->region;
+    sh->mc_legacy = en->mc_legacy;
+    sh->intra_split_planes = en->intra_split_planes;
+    as->shadows.push_back(sh);
+    as->planners.emplace_back(async_planner, en, sh);
+  }
+  as->sequencer = std::thread(async_sequencer, en);
+  return B200_OK;
+}
+
+// Blocks until every queued command has been issued to the GPU; returns (and clears) the first error of a queued command.
+static int async_flush(b200_engine* en)
+{
+  AsyncState* as = en->async;
+  if (!as) return B200_OK;
+  std::unique_lock<std::mutex> lk(as->m);
+  as->cv_space.wait(lk, [&] { return as->q.empty(); });
+  const int rc = as->first_rc;
+  if (rc) set_err(rc, "%s", as->first_err.c_str());
+  as->first_rc = B200_OK;
+  as->first_err.clear();
+  return rc;
+}
+
+static void async_stop(b200_engine* en)
+{
+  AsyncState* as = en->async;
+  if (!as) return;
+  async_flush(en);
+  {
+    std::lock_guard<std::mutex> lk(as->m);
+    as->stop = true;
+  }
+  as->cv_plan.notify_all();
+  as->cv_seq.notify_all();
+  for (auto& t : as->planners) t.join();
+  as->sequencer.join();
+  for (b200_engine* sh : as->shadows) delete sh;
+  delete as;
+  en->async = nullptr;
+}
+
+static int async_enqueue(b200_engine* en, AsyncCmd* cmd)
+{
+  AsyncState* as = en->async;
+  {
+    std::unique_lock<std::mutex> lk(as->m);
+    as->cv_space.wait(lk, [&] { return as->q.size() < B200_ASYNC_DEPTH; });
+    as->q.push_back(cmd);
+  }
+  if (cmd->kind == 0) as->cv_plan.notify_one();
+  as->cv_seq.notify_all();
+  return B200_OK;
+}
+
+extern "C" int b200_engine_submit_picture_async(b200_engine* en, const b200_picture* pic)
+{
+  if (!en || !pic) return set_err(B200_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(en->device));
+  int rc = async_start(en);
+  if (rc) return rc;
+  AsyncCmd* cmd = new (std::nothrow) AsyncCmd();
+  if (!cmd) return set_err(B200_ERR_NOMEM, "out of memory");
+  cmd->kind = 0;
+  cmd->pic = *pic;  // the record ARRAYS must stay valid until b200_engine_flush / _sync returns
+  cmd->ss = &en->stage_pool[en->next_stage++ % B200_STAGE_SETS];
+  return async_enqueue(en, cmd);
+}
+
+extern "C" int b200_engine_flush(b200_engine* en)
+{
+  if (!en) return set_err(B200_ERR_INVALID, "null engine");
+  return async_flush(en);
+}
+
 extern "C" int b200_engine_submit_picture(b200_engine* en, const b200_picture* pic)
 {
   if (!en || !pic) return set_err(B200_ERR_INVALID, "null argument");
   CU(cudaSetDevice(en->device));
+  {
+    const int frc = async_flush(en);  // keep submission order with pictures queued asynchronously
+    if (frc) return frc;
+  }
   PicLayout L;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const int k = pick_ctx(en, ref_mask_of(pic), pic->params.dst_slot);
@@ -1441,6 +1729,7 @@ extern "C" int b200_engine_prepare_picture(b200_engine* en, const b200_picture* 
 {
   if (!en || !pic || !out) return set_err(B200_ERR_INVALID, "null argument");
   CU(cudaSetDevice(en->device));
+  { const int frc = async_flush(en); if (frc) return frc; }
   b200_prepared* pp = new (std::nothrow) b200_prepared();
   if (!pp) return set_err(B200_ERR_NOMEM, "out of memory");
   PipeCtx& cx = en->ctx[0];
@@ -1463,6 +1752,7 @@ extern "C" int b200_engine_run_prepared(b200_engine* en, b200_prepared* pp)
 {
   if (!en || !pp) return set_err(B200_ERR_INVALID, "null argument");
   CU(cudaSetDevice(en->device));
+  { const int frc = async_flush(en); if (frc) return frc; }
   return run_layout(en, pick_ctx(en, pp->L.ref_mask, pp->L.params.dst_slot), pp->L, pp->dev, nullptr);
 }
 
@@ -1470,6 +1760,7 @@ extern "C" void b200_engine_free_prepared(b200_engine* en, b200_prepared* pp)
 {
   if (!en || !pp) return;
   cudaSetDevice(en->device);
+  async_flush(en);
   sync_all(en);
   if (pp->dev) cudaFree(pp->dev);
   delete pp;
@@ -1479,6 +1770,7 @@ extern "C" int b200_engine_sync(b200_engine* en)
 {
   if (!en) return set_err(B200_ERR_INVALID, "null engine");
   CU(cudaSetDevice(en->device));
+  { const int frc = async_flush(en); if (frc) return frc; }
   return sync_all(en);
 }
 
@@ -1495,6 +1787,7 @@ extern "C" int b200_engine_fill_slot(b200_engine* en, int slot, const b200_pic_p
   int rc = check_params(*p);
   if (rc) return rc;
   CU(cudaSetDevice(en->device));
+  { const int frc = async_flush(en); if (frc) return frc; }
   rc = sync_all(en);  // utility call: quiesce, then write on stream 0
   if (rc) return rc;
   cudaStream_t st = en->ctx[0].stream;
@@ -1523,6 +1816,7 @@ extern "C" int b200_engine_upload_slot(b200_engine* en, int slot, const b200_pic
   int rc = check_params(*p);
   if (rc) return rc;
   CU(cudaSetDevice(en->device));
+  { const int frc = async_flush(en); if (frc) return frc; }
   rc = sync_all(en);  // utility call: quiesce, then write on stream 0
   if (rc) return rc;
   cudaStream_t st = en->ctx[0].stream;
@@ -1545,6 +1839,19 @@ extern "C" int b200_engine_upload_slot(b200_engine* en, int slot, const b200_pic
 extern "C" int b200_engine_read_slot_async(b200_engine* en, int slot, void* const planes[3], const size_t strides[3])
 {
   if (!en || !planes || !strides || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
+  if (en->async) {  // pictures are queued: the read takes its place behind them (the picture it reads may not be launched yet)
+    AsyncCmd* cmd = new (std::nothrow) AsyncCmd();
+    if (!cmd) return set_err(B200_ERR_NOMEM, "out of memory");
+    cmd->kind = 1;
+    cmd->slot = slot;
+    for (int c = 0; c < 3; c++) { cmd->planes[c] = planes[c]; cmd->strides[c] = strides[c]; }
+    return async_enqueue(en, cmd);
+  }
+  return read_slot_async_now(en, slot, planes, strides);
+}
+
+static int read_slot_async_now(b200_engine* en, int slot, void* const planes[3], const size_t strides[3])
+{
   const Surface& s = en->slot[slot];
   if (!s.valid) return set_err(B200_ERR_INVALID, "slot %d holds no picture", slot);
   CU(cudaSetDevice(en->device));
@@ -1566,20 +1873,23 @@ extern "C" int b200_engine_read_slot(b200_engine* en, int slot, void* const plan
 {
   int rc = b200_engine_read_slot_async(en, slot, planes, strides);
   if (rc) return rc;
+  rc = async_flush(en);
+  if (rc) return rc;
   const int k = en->ssync[slot].writer >= 0 ? en->ssync[slot].writer : 0;
   CU(cudaStreamSynchronize(en->ctx[k].stream));
-  return B200_OK;
+  return check_intra_err(en);
 }
 
 extern "C" int b200_engine_wait_slot(b200_engine* en, int slot)
 {
   if (!en || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(en->device));
+  { const int frc = async_flush(en); if (frc) return frc; }
   SlotSync& ss = en->ssync[slot];
   if (ss.writer >= 0) CU(cudaEventSynchronize(ss.written));
   for (int c = 0; c < B200_MAX_CTX; c++)
     if (ss.read_pending[c]) CU(cudaEventSynchronize(ss.read[c]));
-  return B200_OK;
+  return check_intra_err(en);
 }
 
 extern "C" void* b200_host_alloc(size_t bytes)

@@ -45,6 +45,9 @@ struct ReconArgs {
   unsigned long long* trace;  // optional [n_task][4]: globaltimer at claim, cycles waiting, cycles working, #TUs (debug)
   uint8_t* pend[3];           // per plane, one byte per 4x4 samples: 1 = covered by an intra TU that is not finished
   int pend_w[3];
+  unsigned int* err;          // k_intra: set (task index + 1) when a dependency wait exceeded spin_limit_ns: records whose avail bits name
+  unsigned int* err_host;     //          units of LATER tasks (or of the task itself) can never be satisfied; err_host = mapped host copy
+  unsigned long long spin_limit_ns;
 };
 
 struct ResidualSmem {  // k_residual
@@ -744,11 +747,31 @@ __global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args
       const volatile uint8_t* f2 = nullptr;  // 32x32 TU: 33 units, lane 0 takes the last top unit as well
       if (span == 16 && lane == 0 && ((top >> 15) & 1)) f2 = pend - pw + 15;
       unsigned ns = 32;
+      unsigned long long t_wait0 = 0;
       for (;;) {
         const bool busy = (f && *f) || (f2 && *f2);
         if (!__any_sync(RC_FULL, busy)) break;
         __nanosleep(ns);
         if (ns < (unsigned)args.poll_ns) ns *= 2;
+        else {
+          // Bounded: in a well-formed picture every dependency belongs to an earlier task, so the wait ends.  A record whose avail
+          // bits name a unit of a later task (or its own) would spin forever: give up after spin_limit_ns (and at once when another
+          // task already gave up), flag the picture and go on with whatever the neighbours hold.  The host reports
+          // B200_ERR_INVALID at the next synchronisation point.
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (!t_wait0) t_wait0 = now;
+          bool give_up = now - t_wait0 > args.spin_limit_ns || *(volatile unsigned int*)args.err != 0;
+          give_up = __shfl_sync(RC_FULL, give_up, 0);
+          if (give_up) {
+            if (lane == 0) {
+              atomicCAS(args.err, 0u, t + 1);
+              *(volatile unsigned int*)args.err_host = t + 1;
+              __threadfence_system();
+            }
+            break;
+          }
+        }
       }
     }
     __threadfence();  // acquire: the neighbours' samples were published before their flags were cleared

@@ -32,6 +32,15 @@ class Engine:
         cp = getattr(pic, "c", pic)
         capi.check(self.lib.b200_engine_submit_picture(self._h, C.byref(cp)), "b200_engine_submit_picture")
 
+    def submit_async(self, pic):
+        """Queues the picture (planned by the engine's planner threads, issued in submission order).  The picture's record arrays
+        must stay alive until flush() / sync() / read_slot() returns."""
+        cp = getattr(pic, "c", pic)
+        capi.check(self.lib.b200_engine_submit_picture_async(self._h, C.byref(cp)), "b200_engine_submit_picture_async")
+
+    def flush(self):
+        capi.check(self.lib.b200_engine_flush(self._h), "b200_engine_flush")
+
     def sync(self):
         capi.check(self.lib.b200_engine_sync(self._h), "b200_engine_sync")
 

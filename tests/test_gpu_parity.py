@@ -254,13 +254,13 @@ def test_pipelined_streams_match_serial_and_oracle(oracle_mod):
         orc.reconstruct(p)
         expect.append(md5_planes(orc.read_slot(p.params.dst_slot, p.params)))
     orc.close()
-    for n in (1, 4):
+    for n, submit_async in ((1, False), (4, False), (8, True)):  # the asynchronous call: planner threads + in-order sequencer, reads queued
         e = Engine(0)
         e.set_streams(n)
         bufs = [[np.empty((H, W), np.uint8), np.empty((H // 2, W // 2), np.uint8), np.empty((H // 2, W // 2), np.uint8)] for _ in pics]
         for rep in range(3):  # repeated: later rounds overwrite slots that earlier pictures still read
             for p, b in zip(pics, bufs):
-                e.submit(p)
+                (e.submit_async if submit_async else e.submit)(p)
                 capi.check(e.lib.b200_engine_read_slot_async(e.handle, p.params.dst_slot, capi.PlaneArray(*[x.ctypes.data for x in b]),
                                                              capi.StrideArray(*[x.strides[0] for x in b])), "read_slot_async")
             e.sync()
@@ -296,6 +296,58 @@ def test_malformed_records_are_rejected(eng):
     r.c.params.chroma_format_idc = 3
     with pytest.raises(capi.B200Error):
         eng.submit(r)
+    # the asynchronous call reports a queued picture's error at the next flush; the pictures around it are not affected
+    ok = synth.make_picture(64, 64, "I", seed=44, dst_slot=2)
+    eng.submit_async(ok)
+    eng.submit_async(q)
+    eng.submit_async(ok)
+    with pytest.raises(capi.B200Error):
+        eng.flush()
+    eng.flush()  # the error was consumed
+    eng.sync()
+
+
+def test_unsatisfiable_intra_dependencies_are_reported_not_hung(monkeypatch):
+    """Availability bits that lie outside the picture are rejected on the host; bits that name a unit reconstructed LATER (here two
+    16x16+ TUs that wait for each other) cannot be seen on the host cheaply: k_intra's dependency wait is bounded, the picture is
+    flagged and the next synchronisation point returns B200_ERR_INVALID instead of hanging the stream."""
+    p = synth.make_picture(128, 128, "I", seed=40, dst_slot=1)
+    t = p.tus
+    pair = None
+    for i in range(len(t)):
+        a = t[i]
+        nT = 1 << int(a["log2_size"])
+        if a["cidx"] != 0 or nT < 16 or a["x"] % (2 * nT) != nT or a["y"] % (2 * nT) != 0 or a["y"] + 2 * nT > 128:
+            continue
+        for j in range(i + 1, len(t)):
+            b = t[j]
+            if b["cidx"] == 0 and b["log2_size"] == a["log2_size"] and b["x"] == a["x"] - nT and b["y"] == a["y"] + nT:
+                pair = (i, j, nT)
+                break
+        if pair:
+            break
+    assert pair, "no top-right / bottom-left TU pair in the synthetic picture"
+    i, j, nT = pair
+    q = nT // 4
+    below_left = sum(1 << k for k in range(q, 2 * q))
+    keep = int(t["avail"][i])
+    t["avail"][0] |= 1  # TU 0 sits at x = 0: a left neighbour is outside the picture
+    e0 = Engine(0)
+    with pytest.raises(capi.B200Error):
+        e0.submit(p)
+    t["avail"][0] &= ~np.uint64(1)
+    e0.close()
+    t["avail"][i] = keep | below_left                                  # A waits for B, which comes later ...
+    t["avail"][j] = int(t["avail"][j]) | (below_left << 17)            # ... and B (legitimately) waits for A, its top-right neighbour
+    monkeypatch.setenv("B200_INTRA_SPIN_LIMIT_MS", "50")
+    e = Engine(0)
+    e.submit(p)
+    with pytest.raises(capi.B200Error, match="dependency wait"):
+        e.sync()
+    t["avail"][i] = keep
+    e.submit(p)  # the engine keeps working
+    e.sync()
+    e.close()
 
 
 def test_empty_picture(eng, oracle_mod):

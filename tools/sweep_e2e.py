@@ -30,7 +30,7 @@ for setting in (sys.argv[1:] or [""]):
         v = n[0] % bench.STEP_VARIANTS
         n[0] += 1
         for i, p in enumerate(seq[32 * v:32 * (v + 1)]):
-            eng.submit(p)
+            (eng.submit if os.environ.get('B200_E2E_SYNC') else eng.submit_async)(p)
             o = outs[i & 7]
             capi.check(eng.lib.b200_engine_read_slot_async(eng.handle, p.params.dst_slot, capi.PlaneArray(*[t.data_ptr() for t in o]),
                                                            capi.StrideArray(*[t.stride(0) for t in o])), "read")
