@@ -408,7 +408,7 @@ def run_config(name, eng, torch, dist, stream, a, rank, local_rank, world, headl
     stage_ms, n_timed = eng.timing_sum(reset=True)
     eng.enable_timing(False)
     # ---- e2e: host records in, pictures out ----
-    for _ in range(2):
+    for _ in range(4):  # every staging set has reached its final size after the first intra pictures
         step_e2e()
     eng.sync()
     ms_e2e = timed(step_e2e, steps)

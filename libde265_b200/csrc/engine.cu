@@ -9,12 +9,14 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
 #include <mutex>
 #include <string>
+#include <sched.h>
 #include <thread>
 #include <cmath>
 #include <cstdarg>
@@ -217,53 +219,59 @@ struct StagingSet {
   size_t cap = 0;
   cudaEvent_t done = nullptr;  // recorded after the last kernel that reads `dev`
   bool in_flight = false;
+  std::atomic<size_t>* cap_hint = nullptr;  // the owning engine's largest capacity so far (ensure_staging)
 };
 
 // A few host threads for the per-picture host work (validation / work-list building of the PUs next to that of the TUs,
 // copying the record arrays into the pinned staging buffer): submit_picture is host-bound on large pictures otherwise.
 struct HostPool {
+  // Jobs belong to a group; wait(group) returns when that group's jobs are done, so several threads (the asynchronous planners)
+  // can share one pool.
+  struct Group { int pending = 0; };
   std::vector<std::thread> th;
   std::mutex m;
   std::condition_variable cv, done_cv;
-  std::deque<std::function<void()>> q;
-  int pending = 0;
+  std::deque<std::pair<Group*, std::function<void()>>> q;
+  Group own;
   bool stop = false;
   void start(int n)
   {
     for (int i = 0; i < n; i++)
       th.emplace_back([this] {
         for (;;) {
-          std::function<void()> f;
+          std::pair<Group*, std::function<void()>> job;
           {
             std::unique_lock<std::mutex> lk(m);
             cv.wait(lk, [this] { return stop || !q.empty(); });
             if (stop && q.empty()) return;
-            f = std::move(q.front());
+            job = std::move(q.front());
             q.pop_front();
           }
-          f();
+          job.second();
           {
             std::lock_guard<std::mutex> lk(m);
-            if (--pending == 0) done_cv.notify_all();
+            if (--job.first->pending == 0) done_cv.notify_all();
           }
         }
       });
   }
-  void run(std::function<void()> f)
+  void run(Group* g, std::function<void()> f)
   {
     if (th.empty()) { f(); return; }
     {
       std::lock_guard<std::mutex> lk(m);
-      q.push_back(std::move(f));
-      pending++;
+      q.emplace_back(g, std::move(f));
+      g->pending++;
     }
     cv.notify_one();
   }
-  void wait()
+  void wait(Group* g)
   {
     std::unique_lock<std::mutex> lk(m);
-    done_cv.wait(lk, [this] { return pending == 0; });
+    done_cv.wait(lk, [g] { return g->pending == 0; });
   }
+  void run(std::function<void()> f) { run(&own, std::move(f)); }
+  void wait() { wait(&own); }
   ~HostPool()
   {
     {
@@ -281,7 +289,7 @@ struct HostPool {
 // not depend on each other (the B pictures of one hierarchy level, the next intra period's I picture) overlap, and a
 // latency-bound kernel (the intra DAG) of one picture leaves the SMs to the others.
 #define B200_MAX_CTX 12
-#define B200_STAGE_SETS 24
+#define B200_STAGE_SETS 40
 struct PipeCtx {
   cudaStream_t stream = nullptr;
   Surface scratch;              // pre-SAO picture
@@ -307,6 +315,7 @@ struct IntraPart {
 struct AsyncState;
 struct b200_engine {
   int device = 0;
+  std::atomic<size_t> stage_cap_hint{0};
   AsyncState* async = nullptr;  // b200_engine_submit_picture_async: planner threads + the in-order sequencer (created on first use)
   PipeCtx ctx[B200_MAX_CTX];
   // Record staging: pinned host buffer + device arena per picture in flight, handed out round-robin whatever stream the picture
@@ -317,6 +326,21 @@ struct b200_engine {
   Surface slot[B200_MAX_SLOTS];
   SlotSync ssync[B200_MAX_SLOTS];
   HostPool pool;
+  // A shadow engine (asynchronous planner) plans a picture on its own thread; for a picture with a long plan (a large intra
+  // picture) it borrows the owning engine's pool so that the in-order sequencer is not held up by it.
+  HostPool* helper = nullptr;
+  HostPool::Group helper_group;
+  bool use_helper = false;
+  void prun(std::function<void()> f)
+  {
+    if (use_helper) helper->run(&helper_group, std::move(f));
+    else pool.run(std::move(f));
+  }
+  void pwait()
+  {
+    if (use_helper) helper->wait(&helper_group);
+    else pool.wait();
+  }
   int num_sms = 148;
   long long slot_depth[B200_MAX_SLOTS] = {}, tail_depth[B200_MAX_CTX] = {}, key_depth = 0;  // pick_ctx: dependency depths
   bool intra_split_planes = false;  // B200_INTRA_SPLIT=1: one intra task per plane in every picture (A/B measurements)
@@ -349,11 +373,13 @@ struct b200_engine {
   bool host_prof = false;
   int host_skip = 0;
   // host scratch reused across pictures
-  std::vector<uint32_t> part_a[4][3];  // plan_tus_validate: per part, per k_residual class
+  std::vector<uint32_t> part_a[8][3];  // plan_intra_A: per range, per k_residual class
   std::vector<uint32_t> pu_tiles[PLAN_PU_PARTS];  // plan_pus_part
   size_t pu_count[PLAN_PU_PARTS][8] = {};
   uint32_t pu_ref_mask[PLAN_PU_PARTS] = {};
   IntraPart ipart[PLAN_INTRA_PARTS];              // plan_intra_*
+  std::vector<uint32_t> unit_task[3], task_level, level_off;  // plan_intra_levels
+  int intra_level_order = 1;  // 1: intra pictures by DAG level (the long DAGs), 2: every picture (B200_INTRA_ORDER=level_all), 0: CTB anti-diagonal order everywhere (=diag)
   std::vector<uint32_t> ctb_count, tiles, tiles_sorted, list_a, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
 };
 
@@ -477,11 +503,12 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   if (const char* e = getenv("B200_INTRA_CTAS")) en->intra_ctas = std::max(1, std::min(4, atoi(e)));
   if (const char* e = getenv("B200_INTRA_SPLIT")) en->intra_split_planes = atoi(e) != 0;
   if (const char* e = getenv("B200_SCHED")) en->sched_rr = !strcmp(e, "rr");
-  if (const char* e = getenv("B200_IND_STREAMS")) en->n_ind = std::max(1, std::min(3, atoi(e)));
+  if (const char* e = getenv("B200_IND_STREAMS")) en->n_ind = std::max(1, std::min(4, atoi(e)));
   if (const char* e = getenv("B200_INTRA_I_GRID")) en->intra_i_grid = std::max(0, atoi(e));
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
   if (const char* e = getenv("B200_INTRA_SPIN_LIMIT_MS")) en->spin_limit_ns = 1000000ull * (unsigned long long)std::max(1, std::min(60000, atoi(e)));
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
+  if (const char* e = getenv("B200_INTRA_ORDER")) en->intra_level_order = !strcmp(e, "diag") ? 0 : !strcmp(e, "level_all") ? 2 : 1;
   en->tl_path = getenv("B200_TIMELINE");
   en->host_prof = getenv("B200_HOST_PROF") != nullptr;
   if (const char* e = getenv("B200_HOST_PROF_SKIP")) en->host_skip = std::max(0, atoi(e));
@@ -493,7 +520,10 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
     CU(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&cx.tail, cudaEventDisableTiming));
   }
-  for (auto& st : en->stage_pool) CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  for (auto& st : en->stage_pool) {
+    CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming | cudaEventBlockingSync));
+    st.cap_hint = &en->stage_cap_hint;
+  }  // planner threads sleep, not spin, on a busy set
   CU(cudaMalloc(&en->intra_err, 256));
   CU(cudaMemset(en->intra_err, 0, 256));
   CU(cudaHostAlloc(&en->intra_err_host, 64, cudaHostAllocMapped));
@@ -943,46 +973,34 @@ static int plan_pus_merge(b200_engine* en, const b200_picture* pic, PicLayout* L
 
 // TU validation + the k_residual work classes for the TU range [i0, i1) into the part's own lists (two parts run on pool
 // threads; plan_and_pack concatenates them).  Classes: warp per TU (16x16, 32x32, PCM) | quarter-warp per 8x8 | lane per 4x4.
-#define PLAN_TU_PARTS 4
-static int plan_tus_validate(b200_engine* en, const b200_picture* pic, int part, uint32_t i0, uint32_t i1)
+#define PLAN_TU_PARTS PLAN_INTRA_PARTS  // validation and the intra task formation share one pass over a range of TUs
+// One TU record against the picture; B200_OK or the error (message set).
+static inline int tu_check(const b200_pic_params& p, const b200_picture* pic, uint32_t i, const b200_tu& tu)
 {
-  const b200_pic_params& p = pic->params;
-  std::vector<uint32_t>&la = en->part_a[part][0], &la8 = en->part_a[part][1], &la4 = en->part_a[part][2];
-  la.clear();
-  la8.clear();
-  la4.clear();
-  for (uint32_t i = i0; i < i1; i++) {
-    const b200_tu& tu = pic->tus[i];
-    const int nT = 1 << tu.log2_size;
-    const int pw = tu.cidx ? p.width / 2 : p.width, ph = tu.cidx ? p.height / 2 : p.height;
-    if (tu.log2_size < 2 || tu.log2_size > 5 || tu.cidx > 2 || (tu.cidx && !p.chroma_format_idc) || tu.x + nT > pw || tu.y + nT > ph ||
-        (tu.x & 3) || (tu.y & 3) || (tu.x & (nT - 1)) || (tu.y & (nT - 1)))
-      return set_err(B200_ERR_INVALID, "TU %u out of range", i);
-    if ((size_t)tu.coeff_off + tu.n_coeff > pic->n_coeff || tu.n_coeff > nT * nT) return set_err(B200_ERR_INVALID, "TU %u coefficient range", i);
-    if ((tu.flags & B200_TU_PCM) && tu.n_coeff != nT * nT) return set_err(B200_ERR_INVALID, "PCM TU %u sample count", i);
-    if (tu.flags & B200_TU_INTRA) {
-      if (tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
-      // avail bits must name samples inside the picture (k_intra reads the border and the pending flags at those positions)
-      const int half = nT >> 1;  // groups of 4 samples per side
-      const uint32_t gm = half >= 32 ? 0xffffffffu : (1u << half) - 1u;
-      const uint32_t left = (uint32_t)tu.avail & 0xffffu, top = (uint32_t)(tu.avail >> B200_AVAIL_TOP_BIT0) & 0xffffu;
-      const bool corner = (tu.avail >> B200_AVAIL_CORNER_BIT) & 1;
-      const int rows_below = (ph - tu.y) >> 2, cols_right = (pw - tu.x) >> 2;  // groups that still lie inside the plane
-      const uint32_t lm = rows_below >= 16 ? 0xffffu : (1u << rows_below) - 1u, tm = cols_right >= 16 ? 0xffffu : (1u << cols_right) - 1u;
-      if ((left & ~gm) || (top & ~gm) || (tu.avail >> (B200_AVAIL_TOP_BIT0 + 16)) || (left && tu.x == 0) || (top && tu.y == 0) ||
-          (corner && (tu.x == 0 || tu.y == 0)) || (left & ~lm) || (top & ~tm))
-        return set_err(B200_ERR_INVALID, "TU %u intra availability names samples outside the picture", i);
-    } else if (tu.flags & (B200_TU_CBF | B200_TU_PCM)) {
-      if ((tu.flags & B200_TU_PCM) || tu.log2_size > 3) la.push_back(i);
-      else if (tu.log2_size == 3) la8.push_back(i);
-      else la4.push_back(i);
-    }
+  const int nT = 1 << tu.log2_size;
+  const int pw = tu.cidx ? p.width / 2 : p.width, ph = tu.cidx ? p.height / 2 : p.height;
+  if (tu.log2_size < 2 || tu.log2_size > 5 || tu.cidx > 2 || (tu.cidx && !p.chroma_format_idc) || tu.x + nT > pw || tu.y + nT > ph ||
+      (tu.x & 3) || (tu.y & 3) || (tu.x & (nT - 1)) || (tu.y & (nT - 1)))
+    return set_err(B200_ERR_INVALID, "TU %u out of range", i);
+  if ((size_t)tu.coeff_off + tu.n_coeff > pic->n_coeff || tu.n_coeff > nT * nT) return set_err(B200_ERR_INVALID, "TU %u coefficient range", i);
+  if ((tu.flags & B200_TU_PCM) && tu.n_coeff != nT * nT) return set_err(B200_ERR_INVALID, "PCM TU %u sample count", i);
+  if (tu.flags & B200_TU_INTRA) {
+    if (tu.intra_mode > 34) return set_err(B200_ERR_INVALID, "TU %u intra mode", i);
+    // avail bits must name samples inside the picture (k_intra reads the border and the pending flags at those positions)
+    const int half = nT >> 1;  // groups of 4 samples per side
+    const uint32_t gm = half >= 32 ? 0xffffffffu : (1u << half) - 1u;
+    const uint32_t left = (uint32_t)tu.avail & 0xffffu, top = (uint32_t)(tu.avail >> B200_AVAIL_TOP_BIT0) & 0xffffu;
+    const bool corner = (tu.avail >> B200_AVAIL_CORNER_BIT) & 1;
+    const int rows_below = (ph - tu.y) >> 2, cols_right = (pw - tu.x) >> 2;  // groups that still lie inside the plane
+    const uint32_t lm = rows_below >= 16 ? 0xffffu : (1u << rows_below) - 1u, tm = cols_right >= 16 ? 0xffffu : (1u << cols_right) - 1u;
+    if ((left & ~gm) || (top & ~gm) || (tu.avail >> (B200_AVAIL_TOP_BIT0 + 16)) || (left && tu.x == 0) || (top && tu.y == 0) ||
+        (corner && (tu.x == 0 || tu.y == 0)) || (left & ~lm) || (top & ~tm))
+      return set_err(B200_ERR_INVALID, "TU %u intra availability names samples outside the picture", i);
   }
   return B200_OK;
 }
 
-// Intra work list (runs next to plan_tus_validate, so it must not trust the records: malformed TUs are skipped here and
-// rejected there).  Intra tasks: the TUs of one plane inside one aligned 16x16-luma / 8x8-chroma region (contiguous per plane in
+// TU validation, the k_residual classes of the non-intra TUs and the intra work list, in one pass over the TU records.  Intra tasks: the TUs of one plane inside one aligned 16x16-luma / 8x8-chroma region (contiguous per plane in
 // decode order); a TU at least as large as the region is a task of its own.  Tasks are emitted in a topological order: CTB
 // anti-diagonal x + 2y, ties in decode order.  The TU list is cut at CTB boundaries into PLAN_INTRA_PARTS ranges (a region
 // never crosses a CTB, so no task spans two ranges) and the phases A, C, E run per range on the pool threads:
@@ -1016,10 +1034,14 @@ static void plan_intra_ranges(b200_engine* en, const b200_picture* pic)
   }
 }
 
-static void plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_diag, int wctb, int hctb)
+static int plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_diag, int wctb, int hctb)
 {
   const b200_pic_params& p = pic->params;
   IntraPart& ip = en->ipart[k];
+  std::vector<uint32_t>&la = en->part_a[k][0], &la8 = en->part_a[k][1], &la4 = en->part_a[k][2];  // non-intra TUs with a residual, by k_residual class
+  la.clear();
+  la8.clear();
+  la4.clear();
   ip.intra_idx.clear();
   ip.task_of.clear();
   ip.task_first.clear();
@@ -1028,6 +1050,7 @@ static void plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_
   // small TUs of ALL planes of a region form one task (luma, then Cb, then Cr) when they are at most 16; intra pictures keep
   // one task per plane (three shorter dependency chains side by side).
   const bool merged = pic->n_pu > 0 && !en->intra_split_planes;
+  const int lg_region = en->region == 16 ? 4 : 3;
   long long cur_key[3] = {-1, -1, -1};
   uint32_t cur_task[3] = {0, 0, 0};
   uint32_t run[48];  // merged mode: the small intra TUs of the current region (at most 16 + 4 + 4, sized generously)
@@ -1060,10 +1083,15 @@ static void plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_
   };
   for (uint32_t i = ip.i0; i < ip.i1; i++) {
     const b200_tu& tu = pic->tus[i];
-    if (!(tu.flags & B200_TU_INTRA)) continue;
-    if (tu.cidx > 2 || tu.log2_size < 2 || tu.log2_size > 5 || (((size_t)tu.x << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)wctb ||
-        (((size_t)tu.y << (tu.cidx ? 1 : 0)) >> p.log2_ctb_size) >= (size_t)hctb)
+    if (const int rc = tu_check(p, pic, i, tu)) return rc;
+    if (!(tu.flags & B200_TU_INTRA)) {
+      if (tu.flags & (B200_TU_CBF | B200_TU_PCM)) {
+        if ((tu.flags & B200_TU_PCM) || tu.log2_size > 3) la.push_back(i);
+        else if (tu.log2_size == 3) la8.push_back(i);
+        else la4.push_back(i);
+      }
       continue;
+    }
     const int c = tu.cidx, G = en->region >> (c ? 1 : 0), nT = 1 << tu.log2_size;
     if (merged) {
       if (nT >= G) {  // a TU at least as large as the region is a task of its own
@@ -1074,7 +1102,7 @@ static void plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_
         continue;
       }
       const int sh = c ? 1 : 0;
-      const long long key = (((long long)((tu.y << sh) / en->region)) << 20) | ((tu.x << sh) / en->region);
+      const long long key = (((long long)((tu.y << sh) >> lg_region)) << 20) | ((tu.x << sh) >> lg_region);
       if (key != run_key || n_run == 48) {
         flush_run();
         run_key = key;
@@ -1083,7 +1111,7 @@ static void plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_
       continue;
     }
     ip.intra_idx.push_back(i);
-    const long long key = (nT >= G) ? -2 - (long long)i : (((long long)(tu.y / G)) << 20) | (tu.x / G);
+    const long long key = (nT >= G) ? -2 - (long long)i : (((long long)(tu.y >> (lg_region - (c ? 1 : 0)))) << 20) | (tu.x >> (lg_region - (c ? 1 : 0)));
     if (key != cur_key[c]) {
       cur_key[c] = key;
       cur_task[c] = new_task(i);
@@ -1091,6 +1119,7 @@ static void plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_
     ip.task_of.push_back(cur_task[c]);
   }
   flush_run();
+  return B200_OK;
 }
 
 static void plan_intra_B(b200_engine* en, int n_diag, uint32_t* n_task, uint32_t* n_intra)
@@ -1115,12 +1144,92 @@ static void plan_intra_B(b200_engine* en, int n_diag, uint32_t* n_task, uint32_t
   en->list_b.resize(ni);
 }
 
-static void plan_intra_C(b200_engine* en, const b200_picture* pic, int k)
+// Ticket order by DAG LEVEL (default; B200_INTRA_ORDER=diag keeps the CTB anti-diagonal order).  level(task) = 1 + the largest level
+// among the tasks that own a neighbour unit one of its TUs reads (availability bits; units of the task itself do not count), found
+// in ONE pass in decode order through a per-plane map "4x4 unit -> task" (a unit a TU may read is always decoded before it).
+// Tasks of one level are independent, so with tickets sorted by level the lowest unfinished tickets are exactly the ready
+// tasks: the persistent warps of k_intra hold ready work instead of spinning on tasks far down the anti-diagonal, and a few
+// hundred warps (the DAG is ~80 tasks wide for a 4K intra picture) run it at its critical-path speed — the other SMs stay free
+// for the pictures it overlaps with.  The CTB anti-diagonal order is topological too, but of the ~500 consecutive tickets the
+// warps hold only the first task of every CTB chain (a few dozen) is ready.
+static void plan_intra_levels(b200_engine* en, const b200_picture* pic, uint32_t n_task, uint32_t n_intra)
+{
+  const b200_pic_params& p = pic->params;
+  const int w4[3] = {(p.width + 3) / 4, (p.width / 2 + 3) / 4, (p.width / 2 + 3) / 4};
+  const int h4[3] = {(p.height + 3) / 4, (p.height / 2 + 3) / 4, (p.height / 2 + 3) / 4};
+  for (int c = 0; c < 3; c++) {
+    const size_t n = (size_t)w4[c] * h4[c];
+    if (en->unit_task[c].size() < n) en->unit_task[c].assign(n, 0);  // kept all-zero between pictures (cleared below)
+  }
+  std::vector<uint32_t>& level = en->task_level;
+  level.assign(n_task, 0);
+  // Tasks of an intra picture hold TUs of ONE plane and a TU only reads its own plane: the three planes are independent passes
+  // (pool threads).  Merged tasks (pictures with inter prediction) span the planes: one pass.
+  const bool per_plane = pic->n_pu == 0 || en->intra_split_planes;
+  uint32_t max_level_of[3] = {0, 0, 0};
+  auto pass = [&](int only_c) {
+    uint32_t max_level = 0;
+    for (int k = 0; k < PLAN_INTRA_PARTS; k++) {
+      const IntraPart& ip = en->ipart[k];
+      for (size_t j = 0; j < ip.intra_idx.size(); j++) {
+        const b200_tu& tu = pic->tus[ip.intra_idx[j]];
+        if (only_c >= 0 && tu.cidx != only_c) continue;
+        const uint32_t t = ip.task_base + ip.task_of[j];
+        const int c = tu.cidx, pw = w4[c], ux = tu.x >> 2, uy = tu.y >> 2, n4 = 1 << (tu.log2_size - 2);
+        uint32_t* map = en->unit_task[c].data();
+        uint32_t lvl = 0;
+        auto dep = [&](size_t u) {
+          const uint32_t m = map[u];
+          if (m && m - 1 != t) lvl = std::max(lvl, level[m - 1]);
+        };
+        for (uint32_t b = (uint32_t)tu.avail & 0xffffu; b; b &= b - 1) dep((size_t)(uy + __builtin_ctz(b)) * pw + ux - 1);
+        if ((tu.avail >> B200_AVAIL_CORNER_BIT) & 1) dep((size_t)(uy - 1) * pw + ux - 1);
+        for (uint32_t b = (uint32_t)(tu.avail >> B200_AVAIL_TOP_BIT0) & 0xffffu; b; b &= b - 1) dep((size_t)(uy - 1) * pw + ux + __builtin_ctz(b));
+        if (lvl + 1 > level[t]) level[t] = lvl + 1;
+        if (level[t] > max_level) max_level = level[t];
+        for (int yy = 0; yy < n4; yy++)
+          for (int xx = 0; xx < n4; xx++) map[(size_t)(uy + yy) * pw + ux + xx] = t + 1;
+      }
+    }
+    max_level_of[only_c < 0 ? 0 : only_c] = max_level;
+  };
+  if (per_plane) {
+    for (int c = 0; c < 3; c++) en->prun([&, c] { pass(c); });
+    en->pwait();
+  } else {
+    pass(-1);
+  }
+  const uint32_t max_level = std::max(max_level_of[0], std::max(max_level_of[1], max_level_of[2]));
+  // leave the maps all-zero again
+  size_t units = 0;
+  for (int c = 0; c < 3; c++) units += (size_t)w4[c] * h4[c];
+  if ((size_t)n_intra * 8 > units) {
+    for (int c = 0; c < 3; c++) memset(en->unit_task[c].data(), 0, sizeof(uint32_t) * (size_t)w4[c] * h4[c]);
+  } else {
+    for (int k = 0; k < PLAN_INTRA_PARTS; k++)
+      for (uint32_t i : en->ipart[k].intra_idx) {
+        const b200_tu& tu = pic->tus[i];
+        const int pw = w4[tu.cidx], ux = tu.x >> 2, uy = tu.y >> 2, n4 = 1 << (tu.log2_size - 2);
+        uint32_t* map = en->unit_task[tu.cidx].data();
+        for (int yy = 0; yy < n4; yy++) memset(map + (size_t)(uy + yy) * pw + ux, 0, sizeof(uint32_t) * (size_t)n4);
+      }
+  }
+  // rank = position in (level, decode order): counting sort over the levels
+  std::vector<uint32_t>& off = en->level_off;
+  off.assign((size_t)max_level + 2, 0);
+  for (uint32_t t = 0; t < n_task; t++) off[level[t] + 1]++;
+  for (size_t l = 1; l < off.size(); l++) off[l] += off[l - 1];
+  uint32_t* order = en->task_order.data();
+  for (uint32_t t = 0; t < n_task; t++) order[t] = off[level[t]]++;
+}
+
+static void plan_intra_C(b200_engine* en, const b200_picture* pic, int k, bool by_level)
 {
   const b200_pic_params& p = pic->params;
   IntraPart& ip = en->ipart[k];
   uint32_t* order = en->task_order.data() + ip.task_base;
-  for (size_t t = 0; t < ip.task_first.size(); t++) order[t] = ip.diag_off[plan_diag_of(p, pic->tus[ip.task_first[t]])]++;
+  if (!by_level)
+    for (size_t t = 0; t < ip.task_first.size(); t++) order[t] = ip.diag_off[plan_diag_of(p, pic->tus[ip.task_first[t]])]++;
   uint32_t* ts = en->task_start.data();
   for (size_t j = 0; j < ip.task_of.size(); j++) ts[order[ip.task_of[j]] + 1]++;  // a task belongs to exactly one range: no two threads touch one entry
 }
@@ -1140,8 +1249,8 @@ static void plan_intra_E(b200_engine* en, int k)
 template <typename F>
 static void plan_parallel(b200_engine* en, int n, F f)
 {
-  for (int k = 0; k < n; k++) en->pool.run([=] { f(k); });
-  en->pool.wait();
+  for (int k = 0; k < n; k++) en->prun([=] { f(k); });
+  en->pwait();
 }
 
 // The serial glue of the intra planner after phase A has run for every range (also used by plan_and_pack, where phase A runs
@@ -1150,7 +1259,9 @@ static void plan_intra_finish(b200_engine* en, const b200_picture* pic, PicLayou
 {
   uint32_t n_task = 0, n_intra = 0;
   plan_intra_B(en, n_diag, &n_task, &n_intra);
-  plan_parallel(en, PLAN_INTRA_PARTS, [=](int k) { plan_intra_C(en, pic, k); });
+  const bool by_level = n_task && (en->intra_level_order == 2 || (en->intra_level_order == 1 && pic->n_pu == 0));
+  if (by_level) plan_intra_levels(en, pic, n_task, n_intra);
+  plan_parallel(en, PLAN_INTRA_PARTS, [=](int k) { plan_intra_C(en, pic, k, by_level); });
   uint32_t* ts = en->task_start.data();
   for (uint32_t t = 0; t < n_task; t++) ts[t + 1] += ts[t];
   plan_parallel(en, PLAN_INTRA_PARTS, [=](int k) { plan_intra_E(en, k); });
@@ -1203,14 +1314,23 @@ static void pack_lists(b200_engine* en, const PicLayout& L, uint8_t* hb)
   if (L.n_tiles) memcpy(hb + off[12], en->tiles.data(), sizeof(uint32_t) * (size_t)(L.n_tiles + L.n_batches));
 }
 
+// cap_hint = the largest staging capacity any set of the engine has needed: a set that has to grow goes straight to it, so that
+// every set is reallocated at most once after the first large (intra) picture instead of whenever such a picture happens to land
+// on it (page-locking tens of MB and cudaFree both stall the other threads' CUDA calls).
+
 static int ensure_staging(StagingSet& ss, size_t total)
 {
   if (ss.in_flight) { CU(cudaEventSynchronize(ss.done)); ss.in_flight = false; }
+  std::atomic<size_t> local{0};
+  std::atomic<size_t>& cap_hint = ss.cap_hint ? *ss.cap_hint : local;
+  size_t hint = cap_hint.load(std::memory_order_relaxed);
+  const size_t want = align_up(total + total / 2, 1 << 20);
+  while (want > hint && !cap_hint.compare_exchange_weak(hint, want, std::memory_order_relaxed)) {}
   if (ss.cap < total) {
     if (ss.host) cudaFreeHost(ss.host);
     if (ss.dev) cudaFree(ss.dev);
     ss.host = nullptr; ss.dev = nullptr;
-    ss.cap = align_up(total + total / 2, 1 << 20);
+    ss.cap = std::max(want, cap_hint.load(std::memory_order_relaxed));
     CU(cudaMallocHost(&ss.host, ss.cap));
     CU(cudaMalloc(&ss.dev, ss.cap));
   }
@@ -1245,26 +1365,24 @@ static int plan_and_pack(b200_engine* en, const b200_picture* pic, PicLayout* L,
   uint8_t* hb = ss.host;
   const b200_pic_params& pp = pic->params;
   const int S = 1 << pp.log2_ctb_size, wctb = (pp.width + S - 1) / S, hctb = (pp.height + S - 1) / S, n_diag = wctb + 2 * hctb;
+  en->use_helper = en->helper && pic->n_tu > 200000;  // shadow engines: see b200_engine::helper
   int rc_pu[PLAN_PU_PARTS] = {}, rc_tv[PLAN_TU_PARTS] = {};
   std::string err_pu[PLAN_PU_PARTS], err_tv[PLAN_TU_PARTS];
   plan_intra_ranges(en, pic);
-  for (int k = 0; k < PLAN_INTRA_PARTS; k++) en->pool.run([=] { plan_intra_A(en, pic, k, n_diag, wctb, hctb); });  // the longest items first
+  for (int k = 0; k < PLAN_INTRA_PARTS; k++)  // the longest items first: TU validation + residual classes + intra tasks of one range
+    en->prun([&, k] {
+      rc_tv[k] = plan_intra_A(en, pic, k, n_diag, wctb, hctb);
+      if (rc_tv[k]) err_tv[k] = g_err;  // the worker's thread-local message
+    });
   for (int part = 0; part < PLAN_PU_PARTS; part++) {
     const uint32_t i0 = (uint32_t)((uint64_t)pic->n_pu * part / PLAN_PU_PARTS), i1 = (uint32_t)((uint64_t)pic->n_pu * (part + 1) / PLAN_PU_PARTS);
-    en->pool.run([&, part, i0, i1] {
+    en->prun([&, part, i0, i1] {
       rc_pu[part] = plan_pus_part(en, pic, part, i0, i1);
       if (rc_pu[part]) err_pu[part] = g_err;  // the worker's thread-local message
     });
   }
-  for (int part = 0; part < PLAN_TU_PARTS; part++) {
-    const uint32_t i0 = (uint32_t)((uint64_t)pic->n_tu * part / PLAN_TU_PARTS), i1 = (uint32_t)((uint64_t)pic->n_tu * (part + 1) / PLAN_TU_PARTS);
-    en->pool.run([&, part, i0, i1] {
-      rc_tv[part] = plan_tus_validate(en, pic, part, i0, i1);
-      if (rc_tv[part]) err_tv[part] = g_err;
-    });
-  }
-  for (int part = 0; part < 3; part++) en->pool.run([=] { pack_raw(pic, *L, hb, part); });
-  en->pool.wait();
+  for (int part = 0; part < 3; part++) en->prun([=] { pack_raw(pic, *L, hb, part); });
+  en->pwait();
   for (int part = 0; part < PLAN_TU_PARTS; part++)
     if (rc_tv[part]) return set_err(rc_tv[part], "%s", err_tv[part].c_str());
   for (int part = 0; part < PLAN_PU_PARTS; part++)
@@ -1286,6 +1404,7 @@ extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8
   b200_engine* en = new (std::nothrow) b200_engine();  // no CUDA call is made on this path
   if (!en) return set_err(B200_ERR_NOMEM, "out of memory");
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
+  if (const char* e = getenv("B200_INTRA_ORDER")) en->intra_level_order = !strcmp(e, "diag") ? 0 : !strcmp(e, "level_all") ? 2 : 1;
   PicLayout L;
   size_t cap = 0;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1297,15 +1416,13 @@ extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8
     rc = plan_pus_part(en, pic, part, (uint32_t)((uint64_t)pic->n_pu * part / PLAN_PU_PARTS), (uint32_t)((uint64_t)pic->n_pu * (part + 1) / PLAN_PU_PARTS));
   if (!rc) rc = plan_pus_merge(en, pic, &L);
   t[2] = now();
-  for (int part = 0; part < PLAN_TU_PARTS && !rc; part++)
-    rc = plan_tus_validate(en, pic, part, (uint32_t)((uint64_t)pic->n_tu * part / PLAN_TU_PARTS), (uint32_t)((uint64_t)pic->n_tu * (part + 1) / PLAN_TU_PARTS));
   t[3] = now();
   if (!rc) {
     const b200_pic_params& pp = pic->params;
     const int S = 1 << pp.log2_ctb_size, wctb = (pp.width + S - 1) / S, hctb = (pp.height + S - 1) / S, n_diag = wctb + 2 * hctb;
     plan_intra_ranges(en, pic);
-    for (int k = 0; k < PLAN_INTRA_PARTS; k++) plan_intra_A(en, pic, k, n_diag, wctb, hctb);
-    plan_intra_finish(en, pic, &L, n_diag);
+    for (int k = 0; k < PLAN_INTRA_PARTS && !rc; k++) rc = plan_intra_A(en, pic, k, n_diag, wctb, hctb);
+    if (!rc) plan_intra_finish(en, pic, &L, n_diag);
   }
   t[4] = now();
   if (prof) {
@@ -1322,7 +1439,7 @@ extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8
     u[2] = now();
     merge_list_a(en, &L);
     u[3] = now();
-    fprintf(stderr, "[b200] plan (one thread) ms: begin %.3f  PUs %.3f  TU validate %.3f  intra tasks %.3f | serial tail: PU merge %.3f  intra finish %.3f  list_a merge %.3f\n",
+    fprintf(stderr, "[b200] plan (one thread) ms: begin %.3f  PUs %.3f  (-) %.3f  TU validate + intra tasks %.3f | serial tail: PU merge %.3f  intra finish %.3f  list_a merge %.3f\n",
             1e3 * (t[1] - t[0]), 1e3 * (t[2] - t[1]), 1e3 * (t[3] - t[2]), 1e3 * (t[4] - t[3]), 1e3 * (u[1] - u[0]), 1e3 * (u[2] - u[1]), 1e3 * (u[3] - u[2]));
   }
   if (!rc) {
@@ -1518,6 +1635,8 @@ struct AsyncState {
   std::mutex m;
   std::condition_variable cv_plan, cv_seq, cv_space;
   std::deque<AsyncCmd*> q;  // submission order; the front is the next one the sequencer executes
+  int n_pictures = 0;       // pictures in q (read-backs do not count towards the depth)
+  int depth = 12;           // pictures queued at most (B200_ASYNC_QUEUE; <= B200_ASYNC_DEPTH)
   std::vector<std::thread> planners;
   std::thread sequencer;
   std::vector<b200_engine*> shadows;
@@ -1525,11 +1644,26 @@ struct AsyncState {
   int first_rc = B200_OK;
   std::string first_err;
 };
-#define B200_ASYNC_DEPTH 16  // < B200_STAGE_SETS: a staging set is never handed out again before its previous picture was launched
+#define B200_ASYNC_DEPTH 32  // queued PICTURES; < B200_STAGE_SETS: a staging set is never handed out again before its previous picture was launched
 
 static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase, const uint8_t* upload_from);
 static int pick_ctx(b200_engine* en, uint32_t ref_mask, int dst_slot);
 static int read_slot_async_now(b200_engine* en, int slot, void* const planes[3], const size_t strides[3]);
+
+// Cores this process may use: the affinity mask, clamped by the cgroup v2 CPU quota.
+static int host_cores()
+{
+  int n = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char quota[32] = "";
+    long period = 0;
+    if (fscanf(f, "%31s %ld", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0) n = std::min(n, std::max(1, (int)((atol(quota) + period - 1) / period)));
+    fclose(f);
+  }
+  return std::max(1, n);
+}
 
 static inline double prof_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -1606,6 +1740,7 @@ static void async_sequencer(b200_engine* en)
       std::lock_guard<std::mutex> lk(as->m);
       if (rc && !as->first_rc) { as->first_rc = rc; as->first_err = cmd->err.empty() ? std::string(g_err) : cmd->err; }
       as->q.pop_front();
+      if (cmd->kind == 0) as->n_pictures--;
     }
     delete cmd;
     as->cv_space.notify_all();
@@ -1619,14 +1754,20 @@ static int async_start(b200_engine* en)
   AsyncState* as = new (std::nothrow) AsyncState();
   if (!as) return set_err(B200_ERR_NOMEM, "out of memory");
   en->async = as;
-  int n = 6;
-  if (const char* e = getenv("B200_ASYNC_THREADS")) n = std::max(1, std::min(16, atoi(e)));
+  // one planner takes ~3.5 ms of one core per 4K picture: half of the cores this process may use (affinity mask and cgroup quota:
+  // exceeding the quota gets the whole process throttled), at most 12 (B200_ASYNC_THREADS overrides)
+  int n = std::max(2, std::min(12, host_cores() / 2));
+  if (const char* e = getenv("B200_ASYNC_THREADS")) n = std::max(1, std::min(32, atoi(e)));
+  as->depth = std::min(B200_ASYNC_DEPTH, n + 8);
+  if (const char* e = getenv("B200_ASYNC_QUEUE")) as->depth = std::max(1, std::min(B200_ASYNC_DEPTH, atoi(e)));
   for (int i = 0; i < n; i++) {
     b200_engine* sh = new b200_engine();  // no CUDA state: only the planner's scratch and the flags the planner reads
     sh->device = en->device;
     sh->region = en->region;
     sh->mc_legacy = en->mc_legacy;
     sh->intra_split_planes = en->intra_split_planes;
+    sh->intra_level_order = en->intra_level_order;
+    sh->helper = &en->pool;
     as->shadows.push_back(sh);
     as->planners.emplace_back(async_planner, en, sh);
   }
@@ -1671,8 +1812,9 @@ static int async_enqueue(b200_engine* en, AsyncCmd* cmd)
   AsyncState* as = en->async;
   {
     std::unique_lock<std::mutex> lk(as->m);
-    as->cv_space.wait(lk, [&] { return as->q.size() < B200_ASYNC_DEPTH; });
+    as->cv_space.wait(lk, [&] { return as->n_pictures < as->depth && as->q.size() < 4 * B200_ASYNC_DEPTH; });
     as->q.push_back(cmd);
+    if (cmd->kind == 0) as->n_pictures++;
   }
   if (cmd->kind == 0) as->cv_plan.notify_one();
   as->cv_seq.notify_all();

@@ -35,7 +35,7 @@ for setting in (sys.argv[1:] or [""]):
             capi.check(eng.lib.b200_engine_read_slot_async(eng.handle, p.params.dst_slot, capi.PlaneArray(*[t.data_ptr() for t in o]),
                                                            capi.StrideArray(*[t.stride(0) for t in o])), "read")
 
-    for _ in range(3):
+    for _ in range(5):
         step()
     eng.sync()
     t0 = time.time()
