@@ -289,6 +289,7 @@ struct HostPool {
 // not depend on each other (the B pictures of one hierarchy level, the next intra period's I picture) overlap, and a
 // latency-bound kernel (the intra DAG) of one picture leaves the SMs to the others.
 #define B200_MAX_CTX 12
+#define B200_MAX_PHYS (B200_MAX_SLOTS + 32)  // physical surfaces: every name plus the renamed pictures in flight
 #define B200_STAGE_SETS 40
 struct PipeCtx {
   cudaStream_t stream = nullptr;
@@ -323,8 +324,26 @@ struct b200_engine {
   StagingSet stage_pool[B200_STAGE_SETS];
   unsigned next_stage = 0;
   int n_ctx = 1, next_ctx = 0;
-  Surface slot[B200_MAX_SLOTS];
-  SlotSync ssync[B200_MAX_SLOTS];
+  // DPB slots are NAMES (what the records' ref_slot / dst_slot say); the pictures live in a pool of physical surfaces.  A picture
+  // that writes slot d while earlier pictures on other streams still read (or write) d's current surface gets another, idle
+  // surface and the name moves — like register renaming, WAR / WAW hazards between pictures cost nothing, whatever slot policy
+  // the host's DPB has (libde265 reuses the first free image, dpb.cc: the hazard is the common case).  Only true (RAW)
+  // dependencies remain.  B200_RENAME=0 keeps every name on one surface.
+  Surface slot[B200_MAX_PHYS];
+  SlotSync ssync[B200_MAX_PHYS];
+  int lmap[B200_MAX_SLOTS];       // name -> physical surface, -1: never written
+  int owner[B200_MAX_PHYS];       // physical surface -> name it currently carries, -1: free (may still have readers in flight)
+  int last_owner[B200_MAX_PHYS];  // the name it carried last (b200_engine_wait_slot also waits for reads of a renamed-away surface)
+  bool rename = true;
+  int intra_width_pct = 0;  // off: warps beyond the DAG's width still pay (they run the dependency-free part of later levels ahead: measured)
+  bool sao_legacy = false;  // B200_SAO_LEGACY=1: k_sao for 8-bit pictures too
+  uint64_t n_renamed = 0;
+  b200_engine()
+  {
+    for (int& v : lmap) v = -1;
+    for (int& v : owner) v = -1;
+    for (int& v : last_owner) v = -1;
+  }
   HostPool pool;
   // A shadow engine (asynchronous planner) plans a picture on its own thread; for a picture with a long plan (a large intra
   // picture) it borrows the owning engine's pool so that the in-order sequencer is not held up by it.
@@ -378,8 +397,8 @@ struct b200_engine {
   size_t pu_count[PLAN_PU_PARTS][8] = {};
   uint32_t pu_ref_mask[PLAN_PU_PARTS] = {};
   IntraPart ipart[PLAN_INTRA_PARTS];              // plan_intra_*
-  std::vector<uint32_t> unit_task[3], task_level, level_off;  // plan_intra_levels
-  int intra_level_order = 1;  // 1: intra pictures by DAG level (the long DAGs), 2: every picture (B200_INTRA_ORDER=level_all), 0: CTB anti-diagonal order everywhere (=diag)
+  std::vector<uint32_t> cell_level[3], task_level, level_off;  // plan_intra_levels
+  int intra_level_order = 2;  // 2: every picture by DAG level, 1: intra pictures only (B200_INTRA_ORDER=level_i), 0: CTB anti-diagonal order everywhere (=diag)
   std::vector<uint32_t> ctb_count, tiles, tiles_sorted, list_a, list_b, intra_idx, diag_count, task_of, task_first, task_start, task_order;
 };
 
@@ -424,6 +443,7 @@ struct PicLayout {
   size_t off[14] = {}, total = 0, raw_total = 0, unit_cap = 0;
   uint32_t ref_mask = 0;  // slots the picture's PUs read
   int n_tiles = 0, n_batches = 0, n_a = 0, n_aw = 0, n_a8 = 0, n_b = 0, n_task = 0;
+  int intra_levels = 0, intra_width = 0;  // tickets in DAG-level order: number of levels, tasks in the widest level (0: anti-diagonal order)
   bool run_deblock = false, run_sao = false, has_scaling = false;
   b200_pic_params params{};
   uint32_t n_tu = 0;
@@ -505,10 +525,13 @@ extern "C" int b200_engine_create(b200_engine** out, int device)
   if (const char* e = getenv("B200_SCHED")) en->sched_rr = !strcmp(e, "rr");
   if (const char* e = getenv("B200_IND_STREAMS")) en->n_ind = std::max(1, std::min(4, atoi(e)));
   if (const char* e = getenv("B200_INTRA_I_GRID")) en->intra_i_grid = std::max(0, atoi(e));
+  if (const char* e = getenv("B200_RENAME")) en->rename = atoi(e) != 0;
+  if (const char* e = getenv("B200_INTRA_WIDTH_PCT")) en->intra_width_pct = std::max(0, atoi(e));
+  if (const char* e = getenv("B200_SAO_LEGACY")) en->sao_legacy = atoi(e) != 0;
   if (const char* e = getenv("B200_POLL_NS")) en->poll_ns = std::max(32, std::min(100000, atoi(e)));
   if (const char* e = getenv("B200_INTRA_SPIN_LIMIT_MS")) en->spin_limit_ns = 1000000ull * (unsigned long long)std::max(1, std::min(60000, atoi(e)));
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
-  if (const char* e = getenv("B200_INTRA_ORDER")) en->intra_level_order = !strcmp(e, "diag") ? 0 : !strcmp(e, "level_all") ? 2 : 1;
+  if (const char* e = getenv("B200_INTRA_ORDER")) en->intra_level_order = !strcmp(e, "diag") ? 0 : !strcmp(e, "level_i") ? 1 : 2;
   en->tl_path = getenv("B200_TIMELINE");
   en->host_prof = getenv("B200_HOST_PROF") != nullptr;
   if (const char* e = getenv("B200_HOST_PROF_SKIP")) en->host_skip = std::max(0, atoi(e));
@@ -548,6 +571,12 @@ extern "C" void b200_engine_destroy(b200_engine* en)
   cudaDeviceSynchronize();
   tl_flush(en);
   if (en->tl_base) cudaEventDestroy(en->tl_base);
+  if (getenv("B200_HOST_PROF")) {
+    int n_surf = 0;
+    for (const auto& sf : en->slot) n_surf += sf.plane[0] != nullptr;
+    fprintf(stderr, "[b200] %llu pictures took their destination name to another surface (slot renaming); %d surfaces allocated\n",
+            (unsigned long long)en->n_renamed, n_surf);
+  }
   if (getenv("B200_HOST_PROF") && en->async_n)
     fprintf(stderr, "[b200] submit_picture_async host ms/picture over %llu pictures: planner busy (all threads) %.3f | sequencer: waiting for a plan %.3f  "
             "pictures %.3f (surfaces+H2D %.3f  order_before %.3f  kernels %.3f  borders+order_after %.3f)  read-backs %.3f\n",
@@ -734,9 +763,9 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
       int n = 0;
       for (int i = 0; i < B200_MAX_SLOTS; i++) {
         maps.index_of_slot[i] = -1;
-        if (!((L.ref_mask >> i) & 1) || !refs.plane[i][0] || !en->slot[i].has_tm) continue;
+        if (!((L.ref_mask >> i) & 1) || !refs.plane[i][0] || !en->slot[en->lmap[i]].has_tm) continue;
         if (n == MCT_MAX_REFS) return set_err(B200_ERR_UNSUPPORTED, "picture references more than %d DPB slots", MCT_MAX_REFS);
-        for (int k = 0; k < 2; k++) { maps.luma[k][n] = en->slot[i].tm_luma[k]; maps.chroma[k][n] = en->slot[i].tm_chroma[k]; }
+        for (int k = 0; k < 2; k++) { maps.luma[k][n] = en->slot[en->lmap[i]].tm_luma[k]; maps.chroma[k][n] = en->slot[en->lmap[i]].tm_chroma[k]; }
         maps.index_of_slot[i] = (int8_t)n++;
         maps.valid_slots |= 1u << i;
       }
@@ -796,7 +825,11 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
       int grid = (L.n_task + RC_WARPS - 1) / RC_WARPS;
       // an intra picture's DAG is latency-bound (one CTA per SM is as fast) and should leave room for the pictures it overlaps with
       const bool background = L.ref_mask == 0 && en->n_ctx > 1;
-      const int cap = background ? (en->intra_i_grid ? en->intra_i_grid : en->num_sms) : en->num_sms * en->intra_ctas;
+      int cap = background ? (en->intra_i_grid ? en->intra_i_grid : en->num_sms) : en->num_sms * en->intra_ctas;
+      // tickets in level order: the widest level bounds how many tasks can ever run at once; more warps than that only spin and
+      // keep other pictures' CTAs off the SMs (B200_INTRA_WIDTH_PCT: warps per task of the widest level, in percent; 0 = off)
+      if (L.intra_width > 0 && en->intra_width_pct > 0)
+        cap = std::min(cap, std::max(4, (int)(((long long)L.intra_width * en->intra_width_pct / 100 + RC_WARPS - 1) / RC_WARPS)));
       if (grid > cap) grid = cap;
       TL("intra", (k_intra<P><<<grid, RC_THREADS, sizeof(IntraSmem<P>), st>>>(dp, ra)));
       en->launches += 2;
@@ -834,7 +867,17 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
     fa.sao_avail = avail;
     TL("sao_prep", (k_sao_prep<<<(2 * dp.wctb * dp.hctb + 127) / 128, 128, 0, st>>>(dp, fa, avail)));
     dim3 grid((dp.w / 8 + 127) / 128, dp.h, dp.chroma ? 3 : 1);
-    TL("sao", (k_sao<P><<<grid, 128, 0, st>>>(dp, fa)));
+    if (sizeof(P) == 1 && dp.log2ctb >= 5 && !en->sao_legacy) {  // byte-parallel kernel: a warp per CTB part (kernels_filter.cuh)
+      Sao8Layout lay;
+      lay.n_ctb = dp.wctb * dp.hctb;
+      const int S = 1 << dp.log2ctb, rows_l = (32 >> (dp.log2ctb - 4)) * SAO8_R, rows_c = (32 >> (dp.log2ctb - 5)) * SAO8_R;
+      lay.ipl = (S + rows_l - 1) / rows_l;
+      lay.ipc = dp.chroma ? (S / 2 + rows_c - 1) / rows_c : 0;
+      const int items = lay.n_ctb * (lay.ipl + 2 * lay.ipc);
+      TL("sao", (k_sao8<<<(items + SAO8_WARPS - 1) / SAO8_WARPS, SAO8_WARPS * 32, 0, st>>>(dp, fa, lay)));
+    } else {
+      TL("sao", (k_sao<P><<<grid, 128, 0, st>>>(dp, fa)));
+    }
     en->launches += 2;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[5], st));
@@ -1144,83 +1187,64 @@ static void plan_intra_B(b200_engine* en, int n_diag, uint32_t* n_task, uint32_t
   en->list_b.resize(ni);
 }
 
-// Ticket order by DAG LEVEL (default; B200_INTRA_ORDER=diag keeps the CTB anti-diagonal order).  level(task) = 1 + the largest level
-// among the tasks that own a neighbour unit one of its TUs reads (availability bits; units of the task itself do not count), found
-// in ONE pass in decode order through a per-plane map "4x4 unit -> task" (a unit a TU may read is always decoded before it).
-// Tasks of one level are independent, so with tickets sorted by level the lowest unfinished tickets are exactly the ready
-// tasks: the persistent warps of k_intra hold ready work instead of spinning on tasks far down the anti-diagonal, and a few
-// hundred warps (the DAG is ~80 tasks wide for a 4K intra picture) run it at its critical-path speed — the other SMs stay free
-// for the pictures it overlaps with.  The CTB anti-diagonal order is topological too, but of the ~500 consecutive tickets the
-// warps hold only the first task of every CTB chain (a few dozen) is ready.
-static void plan_intra_levels(b200_engine* en, const b200_picture* pic, uint32_t n_task, uint32_t n_intra)
+// Ticket order by DAG LEVEL (default; B200_INTRA_ORDER=diag keeps the CTB anti-diagonal order).  A level is assigned per task in
+// ONE pass over the tasks in decode order through a map "region cell (16x16 luma) -> highest level of a task covering it":
+//   level(task) = 1 + max over the cells its TUs may read (the column left of it from one cell above to 2x its height below —
+//   corner, left and bottom-left neighbours — and the row above it to 2x its width — top and top-right), cells not written yet
+//   (decoded later, or not intra) count 0.
+// That is a superset of the true dependencies (availability bits), which is all a valid layering needs: every neighbour a task
+// waits for has a lower level.  Tasks of one level are independent, so with tickets sorted by level the lowest unfinished
+// tickets are exactly the ready tasks: the persistent warps of k_intra hold ready work instead of spinning on tasks far down
+// the anti-diagonal, and the grid is sized to the DAG's width (the widest level) instead of the whole GPU — the other SMs stay
+// free for the pictures it overlaps with.  (The anti-diagonal order is topological too, but of the ~500 consecutive tickets
+// the warps hold only the first task of every CTB chain is ready.)  Intra pictures keep one map per plane (their tasks are
+// per plane); pictures with inter prediction one map (tasks span the planes).
+static void plan_intra_levels(b200_engine* en, const b200_picture* pic, PicLayout* L, uint32_t n_task)
 {
   const b200_pic_params& p = pic->params;
-  const int w4[3] = {(p.width + 3) / 4, (p.width / 2 + 3) / 4, (p.width / 2 + 3) / 4};
-  const int h4[3] = {(p.height + 3) / 4, (p.height / 2 + 3) / 4, (p.height / 2 + 3) / 4};
-  for (int c = 0; c < 3; c++) {
-    const size_t n = (size_t)w4[c] * h4[c];
-    if (en->unit_task[c].size() < n) en->unit_task[c].assign(n, 0);  // kept all-zero between pictures (cleared below)
-  }
-  std::vector<uint32_t>& level = en->task_level;
-  level.assign(n_task, 0);
-  // Tasks of an intra picture hold TUs of ONE plane and a TU only reads its own plane: the three planes are independent passes
-  // (pool threads).  Merged tasks (pictures with inter prediction) span the planes: one pass.
+  const int lg = en->region == 16 ? 4 : 3;
+  const int cw = (p.width + (1 << lg) - 1) >> lg, ch = (p.height + (1 << lg) - 1) >> lg;
   const bool per_plane = pic->n_pu == 0 || en->intra_split_planes;
-  uint32_t max_level_of[3] = {0, 0, 0};
-  auto pass = [&](int only_c) {
-    uint32_t max_level = 0;
-    for (int k = 0; k < PLAN_INTRA_PARTS; k++) {
-      const IntraPart& ip = en->ipart[k];
-      for (size_t j = 0; j < ip.intra_idx.size(); j++) {
-        const b200_tu& tu = pic->tus[ip.intra_idx[j]];
-        if (only_c >= 0 && tu.cidx != only_c) continue;
-        const uint32_t t = ip.task_base + ip.task_of[j];
-        const int c = tu.cidx, pw = w4[c], ux = tu.x >> 2, uy = tu.y >> 2, n4 = 1 << (tu.log2_size - 2);
-        uint32_t* map = en->unit_task[c].data();
-        uint32_t lvl = 0;
-        auto dep = [&](size_t u) {
-          const uint32_t m = map[u];
-          if (m && m - 1 != t) lvl = std::max(lvl, level[m - 1]);
-        };
-        for (uint32_t b = (uint32_t)tu.avail & 0xffffu; b; b &= b - 1) dep((size_t)(uy + __builtin_ctz(b)) * pw + ux - 1);
-        if ((tu.avail >> B200_AVAIL_CORNER_BIT) & 1) dep((size_t)(uy - 1) * pw + ux - 1);
-        for (uint32_t b = (uint32_t)(tu.avail >> B200_AVAIL_TOP_BIT0) & 0xffffu; b; b &= b - 1) dep((size_t)(uy - 1) * pw + ux + __builtin_ctz(b));
-        if (lvl + 1 > level[t]) level[t] = lvl + 1;
-        if (level[t] > max_level) max_level = level[t];
-        for (int yy = 0; yy < n4; yy++)
-          for (int xx = 0; xx < n4; xx++) map[(size_t)(uy + yy) * pw + ux + xx] = t + 1;
-      }
+  for (int c = 0; c < (per_plane ? 3 : 1); c++) en->cell_level[c].assign((size_t)cw * ch, 0);
+  std::vector<uint32_t>& level = en->task_level;
+  level.resize(n_task);
+  uint32_t max_level = 0;
+  for (int k = 0; k < PLAN_INTRA_PARTS; k++) {
+    const IntraPart& ip = en->ipart[k];
+    for (size_t t = 0; t < ip.task_first.size(); t++) {
+      const b200_tu& tu = pic->tus[ip.task_first[t]];
+      const int sh = tu.cidx ? 1 : 0;
+      const int cx = (tu.x << sh) >> lg, cy = (tu.y << sh) >> lg;
+      const int R = std::max(1, ((1 << tu.log2_size) << sh) >> lg);  // cells per side: 1 (region task) or the large TU's size
+      uint32_t* map = en->cell_level[per_plane ? tu.cidx : 0].data();
+      uint32_t lvl = 0;
+      if (cx > 0)
+        for (int y = std::max(cy - 1, 0); y < std::min(cy + 2 * R, ch); y++) lvl = std::max(lvl, map[(size_t)y * cw + cx - 1]);
+      if (cy > 0)
+        for (int x = cx; x < std::min(cx + 2 * R, cw); x++) lvl = std::max(lvl, map[(size_t)(cy - 1) * cw + x]);
+      lvl++;
+      level[ip.task_base + t] = lvl;
+      if (lvl > max_level) max_level = lvl;
+      for (int y = cy; y < std::min(cy + R, ch); y++)
+        for (int x = cx; x < std::min(cx + R, cw); x++) {
+          uint32_t& m = map[(size_t)y * cw + x];
+          if (lvl > m) m = lvl;  // several tasks may cover a cell (planes of a merged region that were split, large chroma TUs)
+        }
     }
-    max_level_of[only_c < 0 ? 0 : only_c] = max_level;
-  };
-  if (per_plane) {
-    for (int c = 0; c < 3; c++) en->prun([&, c] { pass(c); });
-    en->pwait();
-  } else {
-    pass(-1);
   }
-  const uint32_t max_level = std::max(max_level_of[0], std::max(max_level_of[1], max_level_of[2]));
-  // leave the maps all-zero again
-  size_t units = 0;
-  for (int c = 0; c < 3; c++) units += (size_t)w4[c] * h4[c];
-  if ((size_t)n_intra * 8 > units) {
-    for (int c = 0; c < 3; c++) memset(en->unit_task[c].data(), 0, sizeof(uint32_t) * (size_t)w4[c] * h4[c]);
-  } else {
-    for (int k = 0; k < PLAN_INTRA_PARTS; k++)
-      for (uint32_t i : en->ipart[k].intra_idx) {
-        const b200_tu& tu = pic->tus[i];
-        const int pw = w4[tu.cidx], ux = tu.x >> 2, uy = tu.y >> 2, n4 = 1 << (tu.log2_size - 2);
-        uint32_t* map = en->unit_task[tu.cidx].data();
-        for (int yy = 0; yy < n4; yy++) memset(map + (size_t)(uy + yy) * pw + ux, 0, sizeof(uint32_t) * (size_t)n4);
-      }
-  }
-  // rank = position in (level, decode order): counting sort over the levels
+  // rank = position in (level, decode order): counting sort over the levels; the widest level sizes the grid
   std::vector<uint32_t>& off = en->level_off;
   off.assign((size_t)max_level + 2, 0);
   for (uint32_t t = 0; t < n_task; t++) off[level[t] + 1]++;
-  for (size_t l = 1; l < off.size(); l++) off[l] += off[l - 1];
+  uint32_t width = 0;
+  for (size_t l = 1; l < off.size(); l++) {
+    if (off[l] > width) width = off[l];
+    off[l] += off[l - 1];
+  }
   uint32_t* order = en->task_order.data();
   for (uint32_t t = 0; t < n_task; t++) order[t] = off[level[t]]++;
+  L->intra_levels = (int)max_level;
+  L->intra_width = (int)width;
 }
 
 static void plan_intra_C(b200_engine* en, const b200_picture* pic, int k, bool by_level)
@@ -1260,7 +1284,8 @@ static void plan_intra_finish(b200_engine* en, const b200_picture* pic, PicLayou
   uint32_t n_task = 0, n_intra = 0;
   plan_intra_B(en, n_diag, &n_task, &n_intra);
   const bool by_level = n_task && (en->intra_level_order == 2 || (en->intra_level_order == 1 && pic->n_pu == 0));
-  if (by_level) plan_intra_levels(en, pic, n_task, n_intra);
+  L->intra_levels = L->intra_width = 0;
+  if (by_level) plan_intra_levels(en, pic, L, n_task);
   plan_parallel(en, PLAN_INTRA_PARTS, [=](int k) { plan_intra_C(en, pic, k, by_level); });
   uint32_t* ts = en->task_start.data();
   for (uint32_t t = 0; t < n_task; t++) ts[t + 1] += ts[t];
@@ -1404,7 +1429,7 @@ extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8
   b200_engine* en = new (std::nothrow) b200_engine();  // no CUDA call is made on this path
   if (!en) return set_err(B200_ERR_NOMEM, "out of memory");
   if (const char* e = getenv("B200_REGION")) en->region = (atoi(e) == 8) ? 8 : 16;
-  if (const char* e = getenv("B200_INTRA_ORDER")) en->intra_level_order = !strcmp(e, "diag") ? 0 : !strcmp(e, "level_all") ? 2 : 1;
+  if (const char* e = getenv("B200_INTRA_ORDER")) en->intra_level_order = !strcmp(e, "diag") ? 0 : !strcmp(e, "level_i") ? 1 : 2;
   PicLayout L;
   size_t cap = 0;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1439,6 +1464,7 @@ extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8
     u[2] = now();
     merge_list_a(en, &L);
     u[3] = now();
+    fprintf(stderr, "[b200] intra DAG: %d tasks in %d levels, widest level %d tasks\n", L.n_task, L.intra_levels, L.intra_width);
     fprintf(stderr, "[b200] plan (one thread) ms: begin %.3f  PUs %.3f  (-) %.3f  TU validate + intra tasks %.3f | serial tail: PU merge %.3f  intra finish %.3f  list_a merge %.3f\n",
             1e3 * (t[1] - t[0]), 1e3 * (t[2] - t[1]), 1e3 * (t[3] - t[2]), 1e3 * (t[4] - t[3]), 1e3 * (u[1] - u[0]), 1e3 * (u[2] - u[1]), 1e3 * (u[3] - u[2]));
   }
@@ -1459,35 +1485,87 @@ extern "C" int b200_plan_picture_host(const b200_picture* pic, uint32_t counts[8
   return rc;
 }
 
-// Cross-stream ordering for a picture issued on context `k` (SlotSync): wait for the writers of its reference slots and
-// for every earlier reader / writer of its destination slot that ran on another stream.
-static int order_before(b200_engine* en, int k, const PicLayout& L)
+// Is every access to physical surface `ph` issued on a stream other than `k` complete?  (Same-stream accesses are ordered anyway.)
+static bool phys_idle(b200_engine* en, int ph, int k)
+{
+  SlotSync& ss = en->ssync[ph];
+  if (ss.writer >= 0 && ss.writer != k) {
+    if (cudaEventQuery(ss.written) != cudaSuccess) return false;
+    ss.writer = -1;
+  }
+  for (int c = 0; c < B200_MAX_CTX; c++)
+    if (c != k && ss.read_pending[c]) {
+      if (cudaEventQuery(ss.read[c]) != cudaSuccess) return false;
+      ss.read_pending[c] = false;
+    }
+  cudaGetLastError();  // cudaErrorNotReady is not sticky, but leave nothing behind
+  return true;
+}
+
+static bool same_geometry(const Surface& s, const b200_pic_params& p)
+{
+  return s.plane[0] && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc &&
+         bytes_per_sample(s.bd_y) == bytes_per_sample(p.bit_depth_luma) && bytes_per_sample(s.bd_c) == bytes_per_sample(p.bit_depth_chroma);
+}
+
+// The physical surface a picture issued on stream `k` writes for the name `d` (see b200_engine::slot).
+static int phys_for_write(b200_engine* en, int d, int k, const b200_pic_params& p)
+{
+  const int cur = en->lmap[d];
+  if (cur >= 0 && (!en->rename || en->n_ctx <= 1 || en->timing || phys_idle(en, cur, k))) return cur;
+  int best = -1, empty = -1, other = -1;
+  for (int ph = 0; ph < B200_MAX_PHYS && best < 0; ph++) {
+    if (en->owner[ph] >= 0) continue;
+    const Surface& s = en->slot[ph];
+    if (!s.plane[0]) { if (empty < 0) empty = ph; continue; }
+    if (!phys_idle(en, ph, k)) continue;
+    if (same_geometry(s, p)) best = ph;
+    else if (other < 0) other = ph;
+  }
+  if (best < 0) best = empty >= 0 ? empty : other;  // a new surface, or an idle one of another format (surface_ensure reallocates it)
+  if (best < 0) return cur;                         // pool exhausted: write in place behind the readers (order_before waits)
+  if (cur >= 0) {
+    en->owner[cur] = -1;
+    en->n_renamed++;
+  }
+  en->lmap[d] = best;
+  en->owner[best] = d;
+  en->last_owner[best] = d;
+  return best;
+}
+
+// Cross-stream ordering for a picture issued on context `k` (SlotSync, per physical surface): wait for the writers of its
+// reference surfaces and for every earlier reader / writer of its destination surface that ran on another stream (none when the
+// destination was renamed to an idle surface).
+static int order_before(b200_engine* en, int k, const PicLayout& L, int dst_phys)
 {
   cudaStream_t st = en->ctx[k].stream;
   const int d = L.params.dst_slot;
   for (int r = 0; r < B200_MAX_SLOTS; r++) {
-    if (!((L.ref_mask >> r) & 1) && r != d) continue;
-    SlotSync& ss = en->ssync[r];
+    if (!((L.ref_mask >> r) & 1) || r == d || en->lmap[r] < 0) continue;
+    SlotSync& ss = en->ssync[en->lmap[r]];
     if (ss.writer >= 0 && ss.writer != k) CU(cudaStreamWaitEvent(st, ss.written, 0));
   }
-  SlotSync& sd = en->ssync[d];
+  SlotSync& sd = en->ssync[dst_phys];
+  if (sd.writer >= 0 && sd.writer != k) CU(cudaStreamWaitEvent(st, sd.written, 0));
   for (int c = 0; c < B200_MAX_CTX; c++)
     if (c != k && sd.read_pending[c]) CU(cudaStreamWaitEvent(st, sd.read[c], 0));
   return B200_OK;
 }
 
-static int order_after(b200_engine* en, int k, const PicLayout& L)
+static int order_after(b200_engine* en, int k, const PicLayout& L, int dst_phys)
 {
   cudaStream_t st = en->ctx[k].stream;
   const int d = L.params.dst_slot;
   if (en->n_ctx > 1) {
     for (int r = 0; r < B200_MAX_SLOTS; r++) {
-      if (!((L.ref_mask >> r) & 1) || r == d) continue;
-      CU(cudaEventRecord(en->ssync[r].read[k], st));
-      en->ssync[r].read_pending[k] = true;
+      if (!((L.ref_mask >> r) & 1) || r == d || en->lmap[r] < 0) continue;
+      SlotSync& sr = en->ssync[en->lmap[r]];
+      CU(cudaEventRecord(sr.read[k], st));
+      sr.read_pending[k] = true;
     }
   }
-  SlotSync& sd = en->ssync[d];
+  SlotSync& sd = en->ssync[dst_phys];
   CU(cudaEventRecord(sd.written, st));
   sd.writer = k;
   for (auto& rp : sd.read_pending) rp = false;  // this picture waited for them; later pictures wait for this one
@@ -1499,10 +1577,23 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
 {
   PipeCtx& cx = en->ctx[k];
   const b200_pic_params& p = L.params;
-  Surface& dst = en->slot[p.dst_slot];
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const bool prof = en->host_prof && en->async && en->host_skip <= 0;
   double tseg[5] = {prof ? now() : 0.0, 0, 0, 0, 0};
+  // references resolve against the names as they are BEFORE this picture takes its destination name
+  RefTable refs;
+  memset(&refs, 0, sizeof(refs));
+  for (int i = 0; i < B200_MAX_SLOTS; i++) {
+    if (i == p.dst_slot || en->lmap[i] < 0) continue;
+    const Surface& s = en->slot[en->lmap[i]];
+    if (s.valid && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc && s.bd_y == p.bit_depth_luma && s.bd_c == p.bit_depth_chroma)
+      for (int c = 0; c < 3; c++) refs.plane[i][c] = s.plane[c];
+  }
+  int dst_phys = phys_for_write(en, p.dst_slot, k, p);
+  if (dst_phys < 0) {  // first use of the name with every surface taken: cannot happen (B200_MAX_PHYS > B200_MAX_SLOTS), but stay safe
+    return set_err(B200_ERR_NOMEM, "no free picture surface");
+  }
+  Surface& dst = en->slot[dst_phys];
   int rc = surface_ensure(dst, p, cx.stream);
   if (rc) return rc;
   Surface* cur = &dst;
@@ -1510,14 +1601,6 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
     rc = surface_ensure(cx.scratch, p, cx.stream);
     if (rc) return rc;
     cur = &cx.scratch;
-  }
-  RefTable refs;
-  memset(&refs, 0, sizeof(refs));
-  for (int i = 0; i < B200_MAX_SLOTS; i++) {
-    const Surface& s = en->slot[i];
-    if (i != p.dst_slot && s.valid && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc && s.bd_y == p.bit_depth_luma &&
-        s.bd_c == p.bit_depth_chroma)
-      for (int c = 0; c < 3; c++) refs.plane[i][c] = s.plane[c];
   }
   {
     const size_t n_ctb = (size_t)((p.width + (1 << p.log2_ctb_size) - 1) >> p.log2_ctb_size) * ((p.height + (1 << p.log2_ctb_size) - 1) >> p.log2_ctb_size);
@@ -1534,7 +1617,7 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
   if (en->timing) CU(cudaEventRecord(en->ev[0], st));
   if (upload_from) CU(cudaMemcpyAsync(dbase, upload_from, L.total, cudaMemcpyHostToDevice, st));  // records first: overlaps the waits below
   if (prof) tseg[1] = now();
-  rc = order_before(en, k, L);
+  rc = order_before(en, k, L, dst_phys);
   if (rc) return rc;
   if (prof) tseg[2] = now();
   const DevPic dp = make_devpic(p, *cur, dst);
@@ -1548,7 +1631,7 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
   en->launches++;
   CU(cudaGetLastError());
   if (en->timing) { CU(cudaEventRecord(en->ev[6], st)); en->tcount++; }
-  rc = order_after(en, k, L);
+  rc = order_after(en, k, L, dst_phys);
   if (rc) return rc;
   dst.valid = true;
   if (prof) {
@@ -1933,7 +2016,9 @@ extern "C" int b200_engine_fill_slot(b200_engine* en, int slot, const b200_pic_p
   rc = sync_all(en);  // utility call: quiesce, then write on stream 0
   if (rc) return rc;
   cudaStream_t st = en->ctx[0].stream;
-  Surface& s = en->slot[slot];
+  const int ph = phys_for_write(en, slot, 0, *p);  // everything is idle after sync_all: the name keeps its surface, or gets its first one
+  if (ph < 0) return set_err(B200_ERR_NOMEM, "no free picture surface");
+  Surface& s = en->slot[ph];
   rc = surface_ensure(s, *p, st);
   if (rc) return rc;
   for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
@@ -1946,8 +2031,8 @@ extern "C" int b200_engine_fill_slot(b200_engine* en, int slot, const b200_pic_p
   launch_extend_borders(s, st);
   en->launches++;
   CU(cudaGetLastError());
-  CU(cudaEventRecord(en->ssync[slot].written, st));
-  en->ssync[slot].writer = 0;
+  CU(cudaEventRecord(en->ssync[ph].written, st));
+  en->ssync[ph].writer = 0;
   s.valid = true;
   return B200_OK;
 }
@@ -1962,7 +2047,9 @@ extern "C" int b200_engine_upload_slot(b200_engine* en, int slot, const b200_pic
   rc = sync_all(en);  // utility call: quiesce, then write on stream 0
   if (rc) return rc;
   cudaStream_t st = en->ctx[0].stream;
-  Surface& s = en->slot[slot];
+  const int ph = phys_for_write(en, slot, 0, *p);  // everything is idle after sync_all: the name keeps its surface, or gets its first one
+  if (ph < 0) return set_err(B200_ERR_NOMEM, "no free picture surface");
+  Surface& s = en->slot[ph];
   rc = surface_ensure(s, *p, st);
   if (rc) return rc;
   for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
@@ -1994,11 +2081,12 @@ extern "C" int b200_engine_read_slot_async(b200_engine* en, int slot, void* cons
 
 static int read_slot_async_now(b200_engine* en, int slot, void* const planes[3], const size_t strides[3])
 {
-  const Surface& s = en->slot[slot];
-  if (!s.valid) return set_err(B200_ERR_INVALID, "slot %d holds no picture", slot);
+  const int ph = en->lmap[slot];
+  if (ph < 0 || !en->slot[ph].valid) return set_err(B200_ERR_INVALID, "slot %d holds no picture", slot);
+  const Surface& s = en->slot[ph];
   CU(cudaSetDevice(en->device));
   // on the stream of the slot's last writer: ordered after it without an event, and a read other streams must respect
-  SlotSync& ss = en->ssync[slot];
+  SlotSync& ss = en->ssync[ph];
   const int k = ss.writer >= 0 ? ss.writer : 0;
   cudaStream_t st = en->ctx[k].stream;
   for (int c = 0; c < (s.chroma ? 3 : 1); c++) {
@@ -2017,7 +2105,8 @@ extern "C" int b200_engine_read_slot(b200_engine* en, int slot, void* const plan
   if (rc) return rc;
   rc = async_flush(en);
   if (rc) return rc;
-  const int k = en->ssync[slot].writer >= 0 ? en->ssync[slot].writer : 0;
+  const int ph = en->lmap[slot];
+  const int k = ph >= 0 && en->ssync[ph].writer >= 0 ? en->ssync[ph].writer : 0;
   CU(cudaStreamSynchronize(en->ctx[k].stream));
   return check_intra_err(en);
 }
@@ -2027,10 +2116,16 @@ extern "C" int b200_engine_wait_slot(b200_engine* en, int slot)
   if (!en || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(en->device));
   { const int frc = async_flush(en); if (frc) return frc; }
-  SlotSync& ss = en->ssync[slot];
-  if (ss.writer >= 0) CU(cudaEventSynchronize(ss.written));
-  for (int c = 0; c < B200_MAX_CTX; c++)
-    if (ss.read_pending[c]) CU(cudaEventSynchronize(ss.read[c]));
+  for (int ph = 0; ph < B200_MAX_PHYS; ph++) {
+    // the surface that carries the name, and surfaces that carried it before a later picture took the name elsewhere: a
+    // read-back requested from them may still be in flight
+    const bool current = en->lmap[slot] == ph;
+    if (!current && !(en->owner[ph] < 0 && en->last_owner[ph] == slot)) continue;
+    SlotSync& ss = en->ssync[ph];
+    if (current && ss.writer >= 0) CU(cudaEventSynchronize(ss.written));
+    for (int c = 0; c < B200_MAX_CTX; c++)
+      if (ss.read_pending[c]) CU(cudaEventSynchronize(ss.read[c]));
+  }
   return check_intra_err(en);
 }
 
@@ -2048,8 +2143,8 @@ extern "C" void b200_host_free(void* p)
 extern "C" int b200_engine_slot_device_planes(b200_engine* en, int slot, void* planes[3], size_t strides[3])
 {
   if (!en || !planes || !strides || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
-  const Surface& s = en->slot[slot];
-  if (!s.valid) return set_err(B200_ERR_INVALID, "slot %d holds no picture", slot);
+  if (en->lmap[slot] < 0 || !en->slot[en->lmap[slot]].valid) return set_err(B200_ERR_INVALID, "slot %d holds no picture", slot);
+  const Surface& s = en->slot[en->lmap[slot]];
   for (int c = 0; c < 3; c++) { planes[c] = s.plane[c]; strides[c] = (size_t)s.pitch[c]; }
   return B200_OK;
 }
