@@ -66,6 +66,9 @@ enum {
 #define B200_PIC_SKIP_DEBLOCK           0x0020 /* DE265_DECODER_PARAM_DISABLE_DEBLOCKING or no slice enables it (deblock.cc:914) */
 #define B200_PIC_SKIP_SAO               0x0040 /* DE265_DECODER_PARAM_DISABLE_SAO (decctx.cc:1798) */
 #define B200_PIC_SCALING_LIST           0x0080 /* sps.scaling_list_enable_flag: b200_picture.scaling_factors is valid */
+#define B200_PIC_RECORDS_PINNED         0x0100 /* the record arrays are page-locked (b200_host_alloc / cudaHostRegister) AND stay unchanged
+                                                  until the picture has been reconstructed (b200_engine_wait_slot / _sync): the engine
+                                                  uploads them straight from where they lie instead of through its staging copy */
 
 typedef struct b200_pic_params {
   uint16_t width, height;      /* luma samples, sps.pic_{width,height}_in_luma_samples */

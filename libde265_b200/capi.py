@@ -21,6 +21,7 @@ PIC_INTRA_SMOOTHING_OFF = 0x0010
 PIC_SKIP_DEBLOCK = 0x0020
 PIC_SKIP_SAO = 0x0040
 PIC_SCALING_LIST = 0x0080
+PIC_RECORDS_PINNED = 0x0100  # record arrays page-locked and stable until the picture is done: uploaded without the staging copy
 
 STAGE_ALL, STAGE_INTER_PRED, STAGE_RECON, STAGE_DEBLOCK = 0, 1, 2, 3
 

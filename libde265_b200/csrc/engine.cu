@@ -368,7 +368,7 @@ struct b200_engine {
   int intra_i_grid = 64;        // grid cap of k_intra for such pictures: the DAG is at most ~160 tasks wide, 64 CTAs (512 warps) cover it and leave the other SMs to the P/B pictures (0: one CTA per SM; B200_INTRA_I_GRID)
   unsigned int *intra_err = nullptr, *intra_err_host = nullptr;  // k_intra gave up a dependency wait (device word; mapped host copy)
   unsigned long long spin_limit_ns = 2000000000ull;              // B200_INTRA_SPIN_LIMIT_MS
-  int intra_ctas = 2, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
+  int intra_ctas = 3, poll_ns = 256;  // k_intra: persistent CTAs per SM, back-off cap of the flag polling (B200_INTRA_CTAS / B200_POLL_NS)
   int region = 16;  // luma size of an intra region task (16 or 8; B200_REGION overrides)
   // B200_TIMELINE=<file>: a CUDA event before and after every launch; the intervals of all streams (ms since the first launch)
   // are appended to the file at b200_engine_sync / destroy: which kernels of which pictures really overlap (tools/timeline.py)
@@ -443,6 +443,9 @@ struct PicLayout {
   size_t off[14] = {}, total = 0, raw_total = 0, unit_cap = 0;
   uint32_t ref_mask = 0;  // slots the picture's PUs read
   int n_tiles = 0, n_batches = 0, n_a = 0, n_aw = 0, n_a8 = 0, n_b = 0, n_task = 0;
+  bool direct = false;                   // B200_PIC_RECORDS_PINNED: raw sections are uploaded from raw_src (the caller's arrays)
+  const void* raw_src[14] = {};
+  size_t raw_sz[14] = {};
   int intra_levels = 0, intra_width = 0;  // tickets in DAG-level order: number of levels, tasks in the widest level (0: anti-diagonal order)
   bool run_deblock = false, run_sao = false, has_scaling = false;
   b200_pic_params params{};
@@ -798,11 +801,18 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
     ra.pend[2] = ra.pend[1] + cw4 * ch4;
     ra.pend_w[0] = dp.w4;
     ra.pend_w[1] = ra.pend_w[2] = (int)cw4;
+    ra.mark_list = nullptr;
+    ra.n_mark = 0;
+    if (L.n_b > 0) CU(cudaMemsetAsync(cx.sync_buf, 0, 256 + (size_t)dp.w4 * dp.h4 + 2 * cw4 * ch4, st));  // ticket + pending flags
     if (L.n_a > 0) {
       ra.list = (const uint32_t*)(dbase + off[3]);
       ra.n_list = L.n_a;
       ra.n_listw = L.n_aw;
       ra.n_list8 = L.n_a8;
+      if (L.n_b > 0) {  // k_residual also sets the pending flags of the intra TUs
+        ra.mark_list = (const uint32_t*)(dbase + off[4]);
+        ra.n_mark = L.n_b;
+      }
       const int items = L.n_aw + (L.n_a8 + 3) / 4 + (L.n_a - L.n_aw - L.n_a8 + 31) / 32;
       TL("residual", (k_residual<P><<<std::min((items + RC_WARPS - 1) / RC_WARPS, en->num_sms * 4), RC_THREADS, 0, st>>>(dp, ra)));
       en->launches++;
@@ -818,8 +828,10 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
       }
       ra.list = (const uint32_t*)(dbase + off[4]);
       ra.n_list = L.n_b;
-      CU(cudaMemsetAsync(cx.sync_buf, 0, 256 + (size_t)dp.w4 * dp.h4 + 2 * cw4 * ch4, st));
-      TL("mark", (k_mark_pending<<<(L.n_b + 255) / 256, 256, 0, st>>>(ra)));
+      if (L.n_a == 0) {
+        TL("mark", (k_mark_pending<<<(L.n_b + 255) / 256, 256, 0, st>>>(ra)));
+        en->launches++;
+      }
       ra.task_start = (const uint32_t*)(dbase + off[13]);
       ra.n_task = L.n_task;
       int grid = (L.n_task + RC_WARPS - 1) / RC_WARPS;
@@ -832,7 +844,7 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
         cap = std::min(cap, std::max(4, (int)(((long long)L.intra_width * en->intra_width_pct / 100 + RC_WARPS - 1) / RC_WARPS)));
       if (grid > cap) grid = cap;
       TL("intra", (k_intra<P><<<grid, RC_THREADS, sizeof(IntraSmem<P>), st>>>(dp, ra)));
-      en->launches += 2;
+      en->launches++;
       if (trace_dev) {
         std::vector<unsigned long long> h(4 * (size_t)L.n_task);
         CU(cudaStreamSynchronize(st));
@@ -865,9 +877,13 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
   if (run_sao) {
     uint16_t* avail = (uint16_t*)(cx.sync_buf + sync_sao_offset(L.params));
     fa.sao_avail = avail;
-    TL("sao_prep", (k_sao_prep<<<(2 * dp.wctb * dp.hctb + 127) / 128, 128, 0, st>>>(dp, fa, avail)));
+    const bool sao8 = sizeof(P) == 1 && dp.log2ctb >= 5 && !en->sao_legacy;
+    if (!sao8) {  // k_sao8 derives the neighbour masks itself
+      TL("sao_prep", (k_sao_prep<<<(2 * dp.wctb * dp.hctb + 127) / 128, 128, 0, st>>>(dp, fa, avail)));
+      en->launches++;
+    }
     dim3 grid((dp.w / 8 + 127) / 128, dp.h, dp.chroma ? 3 : 1);
-    if (sizeof(P) == 1 && dp.log2ctb >= 5 && !en->sao_legacy) {  // byte-parallel kernel: a warp per CTB part (kernels_filter.cuh)
+    if (sao8) {  // byte-parallel kernel: a warp per CTB part (kernels_filter.cuh)
       Sao8Layout lay;
       lay.n_ctb = dp.wctb * dp.hctb;
       const int S = 1 << dp.log2ctb, rows_l = (32 >> (dp.log2ctb - 4)) * SAO8_R, rows_c = (32 >> (dp.log2ctb - 5)) * SAO8_R;
@@ -878,7 +894,7 @@ static int launch_picture(b200_engine* en, PipeCtx& cx, const PicLayout& L, cons
     } else {
       TL("sao", (k_sao<P><<<grid, 128, 0, st>>>(dp, fa)));
     }
-    en->launches += 2;
+    en->launches++;
   }
   if (en->timing) CU(cudaEventRecord(en->ev[5], st));
   CU(cudaGetLastError());
@@ -928,6 +944,10 @@ static int plan_begin(b200_engine* en, const b200_picture* pic, PicLayout* L, si
   size_t total = 0;
   for (int i : k_raw_sections) { L->off[i] = total; total += align_up(sz[i], 256); }
   L->raw_total = total;
+  L->direct = (p.flags & B200_PIC_RECORDS_PINNED) != 0;
+  const void* src[14] = {pic->pus, pic->weights, pic->tus, nullptr, nullptr, pic->coeffs, pic->slices, pic->ctbs, pic->bs_map, pic->qp_map, pic->nofilt_map,
+                         pic->scaling_factors, nullptr, nullptr};
+  for (int i : k_raw_sections) { L->raw_src[i] = src[i]; L->raw_sz[i] = sz[i]; }
   // upper bound of the lists: every TU in one list, one task per TU; MC units cannot outnumber 4x8 blocks unless PUs overlap
   L->unit_cap = ((size_t)w4 * h4 / 2 + 64 + 8 * MCT_MAX_TILES) * 3 / 2 + 64;  // + the padding of the class-pure batches + the batch table
   *cap_total = total + 3 * align_up(sizeof(uint32_t) * ((size_t)pic->n_tu + 1), 256) + align_up(sizeof(uint32_t) * L->unit_cap, 256) + 256;
@@ -1406,7 +1426,8 @@ static int plan_and_pack(b200_engine* en, const b200_picture* pic, PicLayout* L,
       if (rc_pu[part]) err_pu[part] = g_err;  // the worker's thread-local message
     });
   }
-  for (int part = 0; part < 3; part++) en->prun([=] { pack_raw(pic, *L, hb, part); });
+  if (!L->direct)
+    for (int part = 0; part < 3; part++) en->prun([=] { pack_raw(pic, *L, hb, part); });
   en->pwait();
   for (int part = 0; part < PLAN_TU_PARTS; part++)
     if (rc_tv[part]) return set_err(rc_tv[part], "%s", err_tv[part].c_str());
@@ -1615,7 +1636,13 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
   cudaStream_t st = cx.stream;
   en->ev = en->timing ? &en->tev[(size_t)(en->tcount % TIMING_RING) * 7] : nullptr;
   if (en->timing) CU(cudaEventRecord(en->ev[0], st));
-  if (upload_from) CU(cudaMemcpyAsync(dbase, upload_from, L.total, cudaMemcpyHostToDevice, st));  // records first: overlaps the waits below
+  if (upload_from && L.direct) {  // raw record arrays straight from the caller's page-locked memory, the planner's lists from the staging buffer
+    for (int i : k_raw_sections)
+      if (L.raw_sz[i]) CU(cudaMemcpyAsync(dbase + L.off[i], L.raw_src[i], L.raw_sz[i], cudaMemcpyHostToDevice, st));
+    if (L.total > L.raw_total) CU(cudaMemcpyAsync(dbase + L.raw_total, upload_from + L.raw_total, L.total - L.raw_total, cudaMemcpyHostToDevice, st));
+  } else if (upload_from) {
+    CU(cudaMemcpyAsync(dbase, upload_from, L.total, cudaMemcpyHostToDevice, st));  // records first: overlaps the waits below
+  }
   if (prof) tseg[1] = now();
   rc = order_before(en, k, L, dst_phys);
   if (rc) return rc;
@@ -1837,9 +1864,10 @@ static int async_start(b200_engine* en)
   AsyncState* as = new (std::nothrow) AsyncState();
   if (!as) return set_err(B200_ERR_NOMEM, "out of memory");
   en->async = as;
-  // one planner takes ~3.5 ms of one core per 4K picture: half of the cores this process may use (affinity mask and cgroup quota:
-  // exceeding the quota gets the whole process throttled), at most 12 (B200_ASYNC_THREADS overrides)
-  int n = std::max(2, std::min(12, host_cores() / 2));
+  // one planner takes ~4 ms of one core per 4K picture: the cores this process may use (affinity mask and cgroup quota: exceeding
+  // the quota gets the whole process throttled) minus four for the caller, the sequencer and the CUDA driver's threads, at most 16
+  // (B200_ASYNC_THREADS overrides)
+  int n = std::max(2, std::min(16, host_cores() - 4));
   if (const char* e = getenv("B200_ASYNC_THREADS")) n = std::max(1, std::min(32, atoi(e)));
   as->depth = std::min(B200_ASYNC_DEPTH, n + 8);
   if (const char* e = getenv("B200_ASYNC_QUEUE")) as->depth = std::max(1, std::min(B200_ASYNC_DEPTH, atoi(e)));
@@ -1959,7 +1987,9 @@ extern "C" int b200_engine_prepare_picture(b200_engine* en, const b200_picture* 
   if (!pp) return set_err(B200_ERR_NOMEM, "out of memory");
   PipeCtx& cx = en->ctx[0];
   StagingSet& ss = en->stage_pool[en->next_stage++ % B200_STAGE_SETS];
-  int rc = plan_and_pack(en, pic, &pp->L, ss, nullptr);
+  b200_picture staged = *pic;
+  staged.params.flags &= ~B200_PIC_RECORDS_PINNED;  // a prepared picture keeps its own device copy of everything
+  int rc = plan_and_pack(en, &staged, &pp->L, ss, nullptr);
   if (rc) { delete pp; return rc; }
   cudaError_t e = cudaMalloc(&pp->dev, pp->L.total);
   if (e == cudaSuccess) e = cudaMemcpyAsync(pp->dev, ss.host, pp->L.total, cudaMemcpyHostToDevice, cx.stream);

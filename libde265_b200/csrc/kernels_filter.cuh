@@ -447,7 +447,24 @@ __global__ void __launch_bounds__(SAO8_WARPS * 32) k_sao8(DevPic pic, FilterArgs
   const int cls = (int)(w0 >> (40 + 2 * c)) & 3;
   const int hx0 = (cls == 1) ? 0 : (cls == 3) ? 1 : -1;  // neighbour a = (x + hx0, y + vy0), b = (x - hx0, y - vy0)
   const int vy0 = (cls == 0) ? 0 : -1;
-  const unsigned m = edge ? a.sao_avail[(c ? pic.wctb * pic.hctb : 0) + ctb] : 0;
+  // which of the 8 neighbouring CTBs edge classification may read (k_sao_prep's rule, sao.cc:125-190): lane l < 9 tests the
+  // neighbour (l % 3 - 1, l / 3 - 1), one ballot gives the mask — no separate launch in front of this kernel
+  unsigned m = 0;
+  if (edge) {
+    bool ok = false;
+    if (lane < 9) {
+      const int nx = cx + lane % 3 - 1, ny = cy + lane / 3 - 1;
+      if (nx >= 0 && ny >= 0 && nx < pic.wctb && ny < pic.hctb) {
+        const int ctb_addr = (int)slice_at(pic, a, min(xC, pic.w - 1), min(yC, pic.h - 1)).slice_addr_rs;  // component coordinates (sao.cc:49)
+        const b200_ctb_info& cn = a.ctbs[nx + ny * pic.wctb];
+        const b200_slice_info& sn = a.slices[cn.slice_idx];
+        ok = !((int)sn.slice_addr_rs < ctb_addr && !(sl.flags & B200_SLICE_LF_ACROSS_SLICES)) &&
+             !((int)sn.slice_addr_rs > ctb_addr && !(sn.flags & B200_SLICE_LF_ACROSS_SLICES)) &&
+             !(!(pic.flags & B200_PIC_LF_ACROSS_TILES) && cn.tile_id != (uint16_t)(w0 >> 16));
+      }
+    }
+    m = __ballot_sync(0xffffffffu, ok) & 0x1FFu;
+  }
   const int pos = (c == 0) ? (int)(w0 >> 48) & 0xFF : (c == 1) ? (int)(w0 >> 56) : (int)(w1 & 0xFF);
   const uint32_t pos4 = (uint32_t)(pos & 31) * 0x01010101u;
 

@@ -5,7 +5,7 @@
 //
 // Work split.  The host cuts every PU into TILES of at most 16x16 luma samples (+ the co-located 8x8 Cb/Cr samples) and sorts
 // them into 8 classes (wide: more than 8 columns | bi-predicted | tall: more than 8 rows); a BATCH is 8 tiles of one class.
-// Persistent CTAs of 128 threads take batches; inside a batch all threads run over FLAT task lists, so lanes stay busy for
+// Persistent CTAs of MCT_THREADS compute threads (+ one producer warp) take batches; inside a batch all threads run over FLAT task lists, so lanes stay busy for
 // every PU size and nothing in a task body depends on the PU shape except two uniform loop bounds:
 //   stage   16 producer threads (one per tile and list) decode the PU records and issue one 2-D TMA box (48 bytes x 26 rows,
 //           luma) and one 3-D TMA box (32 bytes x 14 rows x {Cb, Cr}) per used reference list into shared memory, completion
@@ -33,7 +33,9 @@
 
 #define MCT_HD __host__ __device__ __forceinline__
 
-#define MCT_THREADS 128
+#ifndef MCT_THREADS
+#define MCT_THREADS 192                  // compute threads per CTA (warps 0..MCT_THREADS/32-1); one more warp is the producer. 576 pass-1 and 192 pass-2 tasks per big batch: 3 + 1 full rounds (128: 57.6 us, 192: 54.5 us, 256: 55.2 us per 4K B picture)
+#endif
 #ifndef MCT_TLS
 #define MCT_TLS 32                       // tile-list items per batch with the small boxes (a power of two); half as many with the big ones
 #endif
@@ -130,13 +132,18 @@ MCT_HD MctGeom mct_geom(int cls)
   return g;
 }
 
+#ifndef MCT_DB
+#define MCT_DB 1  // window buffers: 2 = the producer fetches a whole batch ahead (the boxes of batch n+1 land while batch n is computed).
+                  // Measured (4K B picture): 1 buffer x 3 CTAs/SM 57.9 us; 2 buffers x 2 CTAs/SM 61.5-62.2 us; 2 buffers of 16 items x
+                  // 3 CTAs/SM 61.3 us — the second buffer costs a resident CTA and buys nothing: 1 stays the default
+#endif
 struct MctShared {
-  alignas(128) uint8_t win[MCT_WIN_BYTES];
+  alignas(128) uint8_t win[MCT_DB][MCT_WIN_BYTES];
   alignas(16) uint32_t interm[MCT_INT_WORDS];
   MctTile info[2][MCT_MAX_TILES];
   MctGeom geom[2];
   alignas(16) Mc8Tables tab;
-  alignas(8) unsigned long long bar, bar_empty;
+  alignas(8) unsigned long long bar[2], bar_empty[2];
 };
 
 // ---- portable forms of the packed-integer instructions (host emulation) ----
@@ -516,7 +523,7 @@ struct MctMaps {
 
 __device__ __forceinline__ uint32_t mct_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Warp roles: warps 0-3 (MCT_THREADS threads) compute; warp 4 is the PRODUCER: it decodes the next batch's tiles (two dependent
+// Warp roles: the first MCT_THREADS / 32 warps compute; the last warp is the PRODUCER: it decodes the next batch's tiles (two dependent
 // global loads per tile: tile word -> PU record) while the compute warps work, waits until pass 1 has consumed the current windows
 // (`empty` mbarrier), publishes the tile info and issues the TMA boxes (`full` mbarrier: 32 arrivals + the boxes' bytes).
 #define MCT_CTA_THREADS (MCT_THREADS + 32)
@@ -540,10 +547,15 @@ __global__ void __launch_bounds__(MCT_CTA_THREADS) k_inter_pred_tma(DevPic pic, 
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.tab);
     for (int i = tid; i < (int)(sizeof(Mc8Tables) / 4); i += MCT_CTA_THREADS) dst[i] = src[i];
   }
-  const uint32_t full = mct_smem(&sm.bar), empty = mct_smem(&sm.bar_empty);
+  // full[b]: the windows + tile info of the batches with (it & 1) == b; empty: one arrival per batch when its windows (MCT_DB == 1:
+  // after pass 1) resp. its windows AND tile info (MCT_DB == 2: after pass 2) are free
+  // (one barrier per batch parity: a parity wait must never see its barrier two phases ahead)
+  const uint32_t full0 = mct_smem(&sm.bar[0]), full1 = mct_smem(&sm.bar[1]), empty0 = mct_smem(&sm.bar_empty[0]), empty1 = mct_smem(&sm.bar_empty[1]);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(MCT_MAX_TL));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0), "r"(MCT_MAX_TL));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full1), "r"(MCT_MAX_TL));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty1), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -562,8 +574,12 @@ __global__ void __launch_bounds__(MCT_CTA_THREADS) k_inter_pred_tma(DevPic pic, 
       const int tile = g.nl == 2 ? (lane >> 1) : lane, s = g.nl == 2 ? (lane & 1) : 0;
       if (lane < g.ntl) bx = mct_decode_tile(tiles[(bw & 0x0FFFFFFF) + tile], s, pus, wts, maps.valid_slots, pic, &mine);
       const int mi = bx.active ? maps.index_of_slot[bx.slot] : -1;
-      // the windows (and info[it & 1], last read in pass 2 of batch it-2) are free once pass 1 of the previous batch is done
-      if (it > 0) mct_mbar_wait(empty, (it - 1) & 1);
+      const uint32_t full = (it & 1) ? full1 : full0;
+      uint8_t* win = sm.win[MCT_DB == 2 ? (it & 1) : 0];
+      // MCT_DB == 1: the windows (and info[it & 1], last read in pass 2 of batch it-2) are free once pass 1 of batch it-1 is done;
+      // MCT_DB == 2: window buffer and info of parity it & 1 are free once pass 2 of batch it-2 is done — a whole batch of lookahead
+      if (MCT_DB == 2) { if (it > 1) mct_mbar_wait((it & 1) ? empty1 : empty0, ((it >> 1) - 1) & 1); }  // batch it-2 = previous use of this parity
+      else if (it > 0) mct_mbar_wait(((it - 1) & 1) ? empty1 : empty0, ((it - 1) >> 1) & 1);
       MctTile* dst = &sm.info[it & 1][tile];
       if (lane < g.ntl) {
         if (s == 0) {  // slot-0 lane owns the common fields; with two lists the slot-1 lane adds its own
@@ -582,12 +598,12 @@ __global__ void __launch_bounds__(MCT_CTA_THREADS) k_inter_pred_tma(DevPic pic, 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the windows were read through the generic proxy in pass 1
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                         mct_smem(sm.win + lane * g.lw_slot)),
+                         mct_smem(win + lane * g.lw_slot)),
                      "l"(&maps.luma[k][mi]), "r"(bx.lx + B200_PAD_X), "r"(bx.ly + B200_PAD_Y - skew), "r"(full)
                      : "memory");
         if (has_chroma)
           asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                           mct_smem(sm.win + g.cw_off + lane * g.cw_slot)),
+                           mct_smem(win + g.cw_off + lane * g.cw_slot)),
                        "l"(&maps.chroma[k][mi]), "r"(bx.cx + B200_PAD_CX), "r"(bx.cy + B200_PAD_CY - skew), "r"(0), "r"(full)
                        : "memory");
       } else if (lane < MCT_MAX_TL) {
@@ -600,21 +616,23 @@ __global__ void __launch_bounds__(MCT_CTA_THREADS) k_inter_pred_tma(DevPic pic, 
   // ================= compute warps =================
   int it = 0;
   for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x, it++) {
-    mct_mbar_wait(full, it & 1);  // this batch's windows and tile info
+    mct_mbar_wait((it & 1) ? full1 : full0, (it >> 1) & 1);  // this batch's windows and tile info
+    const uint8_t* win = sm.win[MCT_DB == 2 ? (it & 1) : 0];
     const MctTile* info = sm.info[it & 1];
     const MctGeom g = sm.geom[it & 1];
     const int n1 = g.n1l + (has_chroma ? g.n1c : 0), n2 = g.n2l + (has_chroma ? g.n2c : 0);
     for (int t = tid; t < n1; t += MCT_THREADS) {  // one flat list: luma tasks, then chroma tasks
-      if (t < g.n1l) mct_pass1_luma(t, g, info, sm.win, sm.interm, sm.tab);
-      else mct_pass1_chroma(t - g.n1l, g, info, sm.win, sm.interm, sm.tab);
+      if (t < g.n1l) mct_pass1_luma(t, g, info, win, sm.interm, sm.tab);
+      else mct_pass1_chroma(t - g.n1l, g, info, win, sm.interm, sm.tab);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(MCT_THREADS) : "memory");
-    if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty) : "memory");  // the windows are free: the producer fetches ahead
+    if (MCT_DB == 1 && tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((it & 1) ? empty1 : empty0) : "memory");  // the windows are free: the producer fetches ahead
     for (int t = tid; t < n2; t += MCT_THREADS) {
       if (t < g.n2l) mct_pass2_luma(t, g, info, sm.interm, sm.tab, pic.cur[0], pic.pitch[0]);
       else mct_pass2_chroma(t - g.n2l, g, info, sm.interm, sm.tab, pic.cur[1], pic.cur[2], pic.pitch[1]);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(MCT_THREADS) : "memory");
+    if (MCT_DB == 2 && tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((it & 1) ? empty1 : empty0) : "memory");  // buffer + info of this parity are free
   }
 }
 #endif  // __CUDACC__

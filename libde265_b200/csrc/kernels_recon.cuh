@@ -45,6 +45,8 @@ struct ReconArgs {
   unsigned long long* trace;  // optional [n_task][4]: globaltimer at claim, cycles waiting, cycles working, #TUs (debug)
   uint8_t* pend[3];           // per plane, one byte per 4x4 samples: 1 = covered by an intra TU that is not finished
   int pend_w[3];
+  const uint32_t* mark_list;  // k_residual: intra TU indices whose pending flags it sets on the way (k_mark_pending's work), or null
+  int n_mark;
   unsigned int* err;          // k_intra: set (task index + 1) when a dependency wait exceeded spin_limit_ns: records whose avail bits name
   unsigned int* err_host;     //          units of LATER tasks (or of the task itself) can never be satisfied; err_host = mapped host copy
   unsigned long long spin_limit_ns;
@@ -578,6 +580,14 @@ __global__ void __launch_bounds__(RC_THREADS) k_residual(DevPic pic, ReconArgs a
   __shared__ ResidualSmem sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < (int)(sizeof(ResTables) / 4); i += RC_THREADS) reinterpret_cast<uint32_t*>(&sm.tb)[i] = reinterpret_cast<const uint32_t*>(&c_res)[i];
+  // the intra DAG's pending flags (k_intra runs after this kernel): one launch less per picture than a separate k_mark_pending
+  for (int i = blockIdx.x * RC_THREADS + tid; i < args.n_mark; i += gridDim.x * RC_THREADS) {
+    const b200_tu tu = args.tus[args.mark_list[i]];
+    const int c = tu.cidx, n4u = 1 << (tu.log2_size - 2);
+    uint8_t* p = args.pend[c] + (tu.y >> 2) * args.pend_w[c] + (tu.x >> 2);
+    for (int j = 0; j < n4u; j++)
+      for (int k = 0; k < n4u; k++) p[j * args.pend_w[c] + k] = 1;
+  }
   __syncthreads();
   const int n4 = args.n_list - args.n_listw - args.n_list8;
   const int Ww = args.n_listw, W8 = (args.n_list8 + 3) >> 2, W4 = (n4 + 31) >> 5;

@@ -65,22 +65,22 @@ extern "C" __attribute__((visibility("default"))) int mct_emulate(const b200_pic
     const MctGeom g = mct_geom(cls);
     if (g.ntiles != MCT_CLASS_TILES(cls) || first + g.ntiles > n_tiles) return -1;
     MctTile* info = sm.info[it & 1];
-    memset(sm.win, 0xAB, sizeof(sm.win));  // poison: stale data must never matter
+    memset(sm.win[0], 0xAB, sizeof(sm.win[0]));  // poison: stale data must never matter
     memset(sm.interm, 0xCD, sizeof(sm.interm));
     for (int tid = 0; tid < g.ntl; tid++) {  // the producer threads
       const int tile = g.nl == 2 ? (tid >> 1) : tid, s = g.nl == 2 ? (tid & 1) : 0;
       const MctBox bx = mct_decode_tile(tiles[first + tile], s, pic->pus, pic->weights, valid, dp, &info[tile]);
       if (!bx.active) continue;
       const int skew = tid & 3;
-      pad[bx.slot][0].box(sm.win + tid * g.lw_slot, bx.lx + B200_PAD_X, bx.ly + B200_PAD_Y - skew, g.lw_pitch, g.small ? MCT_LWS_ROWS : MCT_LWB_ROWS);
+      pad[bx.slot][0].box(sm.win[0] + tid * g.lw_slot, bx.lx + B200_PAD_X, bx.ly + B200_PAD_Y - skew, g.lw_pitch, g.small ? MCT_LWS_ROWS : MCT_LWB_ROWS);
       if (CW)
         for (int c = 0; c < 2; c++)
-          pad[bx.slot][1 + c].box(sm.win + g.cw_off + tid * g.cw_slot + c * g.cw_plane, bx.cx + B200_PAD_CX, bx.cy + B200_PAD_CY - skew, g.cw_pitch,
+          pad[bx.slot][1 + c].box(sm.win[0] + g.cw_off + tid * g.cw_slot + c * g.cw_plane, bx.cx + B200_PAD_CX, bx.cy + B200_PAD_CY - skew, g.cw_pitch,
                                   g.small ? MCT_CWS_ROWS : MCT_CWB_ROWS);
     }
-    for (int t = 0; t < g.n1l; t++) mct_pass1_luma(t, g, info, sm.win, sm.interm, sm.tab);
+    for (int t = 0; t < g.n1l; t++) mct_pass1_luma(t, g, info, sm.win[0], sm.interm, sm.tab);
     if (CW)
-      for (int t = 0; t < g.n1c; t++) mct_pass1_chroma(t, g, info, sm.win, sm.interm, sm.tab);
+      for (int t = 0; t < g.n1c; t++) mct_pass1_chroma(t, g, info, sm.win[0], sm.interm, sm.tab);
     for (int t = 0; t < g.n2l; t++) mct_pass2_luma(t, g, info, sm.interm, sm.tab, dp.cur[0], dp.pitch[0]);
     if (CW)
       for (int t = 0; t < g.n2c; t++) mct_pass2_chroma(t, g, info, sm.interm, sm.tab, dp.cur[1], dp.cur[2], dp.pitch[1]);

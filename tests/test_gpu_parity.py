@@ -350,6 +350,48 @@ def test_unsatisfiable_intra_dependencies_are_reported_not_hung(monkeypatch):
     e.close()
 
 
+def test_records_uploaded_straight_from_pinned_arrays(eng, oracle_mod):
+    """B200_PIC_RECORDS_PINNED: the engine uploads the raw record arrays from the caller's page-locked memory (no staging copy);
+    same pictures as through the staging path, synchronous and asynchronous submission."""
+    lib = eng.lib
+    W, H = 320, 192
+    base = [synth.make_picture(W, H, "I", seed=71, dst_slot=0), synth.make_picture(W, H, "P", seed=72, dst_slot=1, ref_slots=(0,)),
+            synth.make_picture(W, H, "B", seed=73, dst_slot=2, ref_slots=(0, 1), weighted=True)]
+    orc = oracle_mod.Oracle()
+    expect = []
+    for p in base:
+        orc.reconstruct(p)
+        expect.append(orc.read_slot(p.params.dst_slot, p.params))
+    orc.close()
+    blocks = []
+
+    def pinned_copy(a):
+        if a is None or not len(a):
+            return a
+        ptr = lib.b200_host_alloc(a.nbytes)
+        assert ptr
+        blocks.append(ptr)
+        out = np.frombuffer((C.c_uint8 * a.nbytes).from_address(ptr), dtype=a.dtype, count=len(a))
+        out[:] = a
+        return out
+
+    pics = []
+    for p in base:
+        q = synth.SynthPicture(p.params, *[pinned_copy(getattr(p, n)) for n in ("pus", "weights", "tus", "coeffs", "slices", "ctbs", "bs_map", "qp_map", "nofilt_map")])
+        q.c.params.flags |= capi.PIC_RECORDS_PINNED
+        pics.append(q)
+    for use_async in (False, True):
+        e = Engine(0)
+        for q in pics:
+            (e.submit_async if use_async else e.submit)(q)
+        e.sync()
+        for q, x in zip(pics, expect):
+            assert_same(e.read_slot(q.params.dst_slot, q.params), x, f"pinned records, async={use_async}")
+        e.close()
+    for ptr in blocks:
+        lib.b200_host_free(ptr)
+
+
 def test_empty_picture(eng, oracle_mod):
     """No PUs and no TUs: every stage must cope with empty work lists (samples no record covers keep the slot's
     content; with SAO on they would come from the scratch surface, which only a malformed stream can expose)."""

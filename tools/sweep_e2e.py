@@ -18,6 +18,8 @@ seq, key_slot, gen_s = bench.build_workload(W, H, 8, seed0=1000)
 ref0 = synth.random_planes(W, H, 8, 7)
 outs = [[torch.empty((H, W), dtype=torch.uint8).pin_memory(), torch.empty((H // 2, W // 2), dtype=torch.uint8).pin_memory(),
          torch.empty((H // 2, W // 2), dtype=torch.uint8).pin_memory()] for _ in range(8)]
+if not os.environ.get("B200_E2E_PAGEABLE"):
+    print("records pinned:", bench.pin_records(seq, torch), flush=True)
 for setting in (sys.argv[1:] or [""]):
     env = dict(kv.split("=", 1) for kv in setting.split() if "=" in kv)
     for k, v in env.items():
