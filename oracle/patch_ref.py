@@ -20,6 +20,18 @@ def sub_once(text, pattern, repl, what):
     return new
 
 
+def write_new(path, text):
+    """Write a patched copy.  A stale symlink of the same name (left by an earlier run that did not patch this file yet) must be
+    removed first: open(..., "w") would follow it and write into the reference tree."""
+    if os.path.islink(path):
+        os.remove(path)
+    real = os.path.realpath(path)
+    if real.startswith("/root/reference"):
+        raise SystemExit(f"patch_ref.py: refusing to write into the reference tree ({real})")
+    with open(path, "w") as f:
+        f.write(text)
+
+
 def main():
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(__file__), "_ref", "patched")
@@ -54,7 +66,7 @@ def main():
         r"\1  b200_hook_pcm(tctx, x0, y0, w, h, cIdx);\n",
         "read_pcm_samples_internal",
     )
-    open(os.path.join(dst, "slice.cc"), "w").write(t)
+    write_new(os.path.join(dst, "slice.cc"), t)
 
     # --- motion.cc: generate_inter_prediction_samples ---
     t = open(os.path.join(src, "motion.cc")).read()
@@ -65,7 +77,7 @@ def main():
         r"\1  if (b200_hook_inter_pred(ctx, shdr, img, xC + xB, yC + yB, nPbW, nPbH, vi)) return;\n",
         "generate_inter_prediction_samples",
     )
-    open(os.path.join(dst, "motion.cc"), "w").write(t)
+    write_new(os.path.join(dst, "motion.cc"), t)
 
     # --- decctx.cc: post-processing filters -> picture done ---
     t = open(os.path.join(src, "decctx.cc")).read()
@@ -90,7 +102,7 @@ def main():
         r"\1  b200_hook_unavailable_reference(this, img);\n\2",
         "generate_unavailable_reference_picture",
     )
-    open(os.path.join(dst, "decctx.cc"), "w").write(t)
+    write_new(os.path.join(dst, "decctx.cc"), t)
 
     # --- de265.cc: the deferred read-back is awaited when the picture is handed to the application ---
     t = open(os.path.join(src, "de265.cc")).read()
@@ -101,12 +113,12 @@ def main():
         r"\1    b200_hook_wait_image(ctx, img);\n\2",
         "de265_peek_next_picture",
     )
-    open(os.path.join(dst, "de265.cc"), "w").write(t)
+    write_new(os.path.join(dst, "de265.cc"), t)
 
     # --- de265.h: the acceleration level ---
     t = open(os.path.join(src, "de265.h")).read()
     t = sub_once(t, r"(  de265_acceleration_NEON = 80,\n)", r"\1  de265_acceleration_B200 = 200, // reconstruction on a B200 GPU (libde265_hooks.h)\n", "de265_acceleration enum")
-    open(os.path.join(dst, "de265.h"), "w").write(t)
+    write_new(os.path.join(dst, "de265.h"), t)
 
     # --- decctx.h: per-context hook state ---
     t = open(os.path.join(src, "decctx.h")).read()
@@ -116,7 +128,7 @@ def main():
         r"\1  void* b200_state = nullptr; // B200 reconstruction backend (libde265_hooks.h)\n",
         "base_context member",
     )
-    open(os.path.join(dst, "decctx.h"), "w").write(t)
+    write_new(os.path.join(dst, "decctx.h"), t)
     print("patched:", dst)
 
 
