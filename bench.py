@@ -476,7 +476,7 @@ def run_config(name, eng, torch, dist, stream, a, rank, local_rank, world, headl
 
     def roof(k):
         launches_per_step = max(1, {"inter_pred": n_inter, "recon": 32, "deblock": 64, "sao": 32}[k])
-        return {"kernel": {"inter_pred": mc_kernel, "recon": "k_residual+k_mark_pending+k_intra", "deblock": "k_deblock<V>+<H>", "sao": "k_sao_prep+k_sao"}[k],
+        return {"kernel": {"inter_pred": mc_kernel, "recon": "k_residual+k_intra", "deblock": "k_deblock<V>+<H>", "sao": "k_sao8" if bd == 8 else "k_sao_prep+k_sao<u16>"}[k],
                 "bound": "hbm", "achieved": per_stage[k]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_stage[k]["frac"],
                 "traffic": traffic.get(k) if name == "main_ra_4k" else None, "peak_source": peak_src,
                 "avg_launch_ms": round(per_stage[k]["ms_per_step"] / launches_per_step, 5),
@@ -564,7 +564,10 @@ def main():
     head = run_config(a.config, eng, torch, dist, stream, a, rank, local_rank, world, True)
     leg_res = {}
     for leg in legs:
-        try:
+        try:  # every leg on a fresh engine: surface pool, staging sizes and stream state of one format must not leak into the next
+            eng.close()
+            eng = Engine(local_rank)
+            stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
             leg_res[leg] = run_config(leg, eng, torch, dist, stream, a, rank, local_rank, world, False)
         except Exception as e:  # a leg never takes the headline down
             leg_res[leg] = {"error": str(e)[:300]}

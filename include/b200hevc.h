@@ -238,6 +238,12 @@ B200_API int  b200_engine_submit_picture(b200_engine*, const b200_picture*);
 B200_API int  b200_engine_submit_picture_async(b200_engine*, const b200_picture*);
 /* Blocks until everything queued has been issued to the GPU (not until the GPU has finished: see b200_engine_sync). */
 B200_API int  b200_engine_flush(b200_engine*);
+/* Tickets: every queued command (picture, read-back) gets the next number.  b200_engine_last_ticket returns the one queued last;
+ * b200_engine_wait_ticket returns when every command up to the ticket has been issued — from then on the record arrays of those
+ * pictures are no longer read by the engine's host side (a recorder with a ring of buffers waits for the ticket of the picture
+ * that used a buffer last, not for the whole queue).  b200_engine_wait_slot only waits for the commands that touch its slot. */
+B200_API unsigned long long b200_engine_last_ticket(b200_engine*);
+B200_API int  b200_engine_wait_ticket(b200_engine*, unsigned long long ticket);
 
 /* Prepared pictures: validate + upload the records ONCE and keep them resident in HBM; running a prepared
  * picture only launches the kernels (bench.py `value`: inputs already resident when the timed region starts;

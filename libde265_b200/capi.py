@@ -118,7 +118,7 @@ EXPORTS = [
     "b200_engine_slot_device_planes", "b200_engine_enable_timing", "b200_engine_last_timing",
     "b200_engine_launch_count", "b200_engine_stream", "b200_engine_prepare_picture", "b200_engine_run_prepared",
     "b200_engine_free_prepared", "b200_engine_timing_sum", "b200_engine_set_streams", "b200_engine_join", "b200_plan_picture_host", "b200_last_error",
-    "b200_engine_wait_slot", "b200_host_alloc", "b200_host_free", "b200_engine_submit_picture_async", "b200_engine_flush",
+    "b200_engine_wait_slot", "b200_host_alloc", "b200_host_free", "b200_engine_submit_picture_async", "b200_engine_flush", "b200_engine_last_ticket", "b200_engine_wait_ticket",
     "b200_abi_version",
     "b200_rec_create", "b200_rec_destroy", "b200_rec_begin_picture", "b200_rec_add_slice", "b200_rec_add_weights",
     "b200_rec_add_pu", "b200_rec_add_tu", "b200_rec_set_ctb", "b200_rec_bs_map", "b200_rec_qp_map",
@@ -169,6 +169,9 @@ def load(path=None):
     lib.b200_engine_sync.argtypes = [vp]
     lib.b200_engine_submit_picture_async.argtypes = [vp, C.POINTER(Picture)]
     lib.b200_engine_flush.argtypes = [vp]
+    lib.b200_engine_last_ticket.argtypes = [vp]
+    lib.b200_engine_last_ticket.restype = C.c_ulonglong
+    lib.b200_engine_wait_ticket.argtypes = [vp, C.c_ulonglong]
     lib.b200_engine_wait_slot.argtypes = [vp, C.c_int]
     lib.b200_host_alloc.argtypes = [C.c_size_t]
     lib.b200_host_alloc.restype = vp

@@ -317,6 +317,7 @@ struct AsyncState;
 struct b200_engine {
   int device = 0;
   std::atomic<size_t> stage_cap_hint{0};
+  std::mutex issue_m;  // held by the asynchronous sequencer while it issues a command (it mutates the slot / stream state b200_engine_wait_slot reads)
   AsyncState* async = nullptr;  // b200_engine_submit_picture_async: planner threads + the in-order sequencer (created on first use)
   PipeCtx ctx[B200_MAX_CTX];
   // Record staging: pinned host buffer + device arena per picture in flight, handed out round-robin whatever stream the picture
@@ -1740,6 +1741,7 @@ struct AsyncCmd {
   int slot = 0;
   void* planes[3] = {nullptr, nullptr, nullptr};
   size_t strides[3] = {0, 0, 0};
+  unsigned long long seq = 0;  // ticket: position in submission order (1, 2, ...)
 };
 struct AsyncState {
   std::mutex m;
@@ -1753,6 +1755,8 @@ struct AsyncState {
   bool stop = false;
   int first_rc = B200_OK;
   std::string first_err;
+  unsigned long long enq_seq = 0, done_seq = 0;          // tickets: queued last / issued last
+  unsigned long long slot_seq[B200_MAX_SLOTS] = {};      // ticket of the last queued command that writes or reads the slot
 };
 #define B200_ASYNC_DEPTH 32  // queued PICTURES; < B200_STAGE_SETS: a staging set is never handed out again before its previous picture was launched
 
@@ -1826,17 +1830,20 @@ static void async_sequencer(b200_engine* en)
     }
     if (en->host_prof) ts[1] = prof_now();
     int rc = cmd->rc;
-    if (cmd->kind == 0) {
-      if (!rc) {
-        const int k = pick_ctx(en, cmd->L.ref_mask, cmd->L.params.dst_slot);
-        rc = run_layout(en, k, cmd->L, cmd->ss->dev, cmd->ss->host);
+    {
+      std::lock_guard<std::mutex> issue(en->issue_m);
+      if (cmd->kind == 0) {
         if (!rc) {
-          cudaEventRecord(cmd->ss->done, en->ctx[k].stream);
-          cmd->ss->in_flight = true;
+          const int k = pick_ctx(en, cmd->L.ref_mask, cmd->L.params.dst_slot);
+          rc = run_layout(en, k, cmd->L, cmd->ss->dev, cmd->ss->host);
+          if (!rc) {
+            cudaEventRecord(cmd->ss->done, en->ctx[k].stream);
+            cmd->ss->in_flight = true;
+          }
         }
+      } else {
+        rc = read_slot_async_now(en, cmd->slot, cmd->planes, cmd->strides);
       }
-    } else {
-      rc = read_slot_async_now(en, cmd->slot, cmd->planes, cmd->strides);
     }
     if (en->host_prof && en->host_skip > 0) {
       if (cmd->kind == 0) en->host_skip--;  // B200_HOST_PROF_SKIP: warm-up pictures (first-use allocations) stay out of the profile
@@ -1851,6 +1858,7 @@ static void async_sequencer(b200_engine* en)
       if (rc && !as->first_rc) { as->first_rc = rc; as->first_err = cmd->err.empty() ? std::string(g_err) : cmd->err; }
       as->q.pop_front();
       if (cmd->kind == 0) as->n_pictures--;
+      as->done_seq = cmd->seq;
     }
     delete cmd;
     as->cv_space.notify_all();
@@ -1900,6 +1908,20 @@ static int async_flush(b200_engine* en)
   return rc;
 }
 
+// Blocks until every command up to `ticket` has been issued (its records are no longer read by the host side).
+static int async_wait_ticket(b200_engine* en, unsigned long long ticket)
+{
+  AsyncState* as = en->async;
+  if (!as) return B200_OK;
+  std::unique_lock<std::mutex> lk(as->m);
+  as->cv_space.wait(lk, [&] { return as->done_seq >= ticket; });
+  const int rc = as->first_rc;
+  if (rc) set_err(rc, "%s", as->first_err.c_str());
+  as->first_rc = B200_OK;
+  as->first_err.clear();
+  return rc;
+}
+
 static void async_stop(b200_engine* en)
 {
   AsyncState* as = en->async;
@@ -1926,6 +1948,9 @@ static int async_enqueue(b200_engine* en, AsyncCmd* cmd)
     as->cv_space.wait(lk, [&] { return as->n_pictures < as->depth && as->q.size() < 4 * B200_ASYNC_DEPTH; });
     as->q.push_back(cmd);
     if (cmd->kind == 0) as->n_pictures++;
+    cmd->seq = ++as->enq_seq;
+    const int slot = cmd->kind == 0 ? (int)cmd->pic.params.dst_slot : cmd->slot;
+    if (slot >= 0 && slot < B200_MAX_SLOTS) as->slot_seq[slot] = cmd->seq;
   }
   if (cmd->kind == 0) as->cv_plan.notify_one();
   as->cv_seq.notify_all();
@@ -1944,6 +1969,19 @@ extern "C" int b200_engine_submit_picture_async(b200_engine* en, const b200_pict
   cmd->pic = *pic;  // the record ARRAYS must stay valid until b200_engine_flush / _sync returns
   cmd->ss = &en->stage_pool[en->next_stage++ % B200_STAGE_SETS];
   return async_enqueue(en, cmd);
+}
+
+extern "C" unsigned long long b200_engine_last_ticket(b200_engine* en)
+{
+  if (!en || !en->async) return 0;
+  std::lock_guard<std::mutex> lk(en->async->m);
+  return en->async->enq_seq;
+}
+
+extern "C" int b200_engine_wait_ticket(b200_engine* en, unsigned long long ticket)
+{
+  if (!en) return set_err(B200_ERR_INVALID, "null engine");
+  return async_wait_ticket(en, ticket);
 }
 
 extern "C" int b200_engine_flush(b200_engine* en)
@@ -2145,17 +2183,30 @@ extern "C" int b200_engine_wait_slot(b200_engine* en, int slot)
 {
   if (!en || slot < 0 || slot >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(en->device));
-  { const int frc = async_flush(en); if (frc) return frc; }
-  for (int ph = 0; ph < B200_MAX_PHYS; ph++) {
-    // the surface that carries the name, and surfaces that carried it before a later picture took the name elsewhere: a
-    // read-back requested from them may still be in flight
-    const bool current = en->lmap[slot] == ph;
-    if (!current && !(en->owner[ph] < 0 && en->last_owner[ph] == slot)) continue;
-    SlotSync& ss = en->ssync[ph];
-    if (current && ss.writer >= 0) CU(cudaEventSynchronize(ss.written));
-    for (int c = 0; c < B200_MAX_CTX; c++)
-      if (ss.read_pending[c]) CU(cudaEventSynchronize(ss.read[c]));
+  if (en->async) {  // not a flush: only the commands that touch this slot (later pictures may still be with the planners)
+    unsigned long long t;
+    {
+      std::lock_guard<std::mutex> lk(en->async->m);
+      t = en->async->slot_seq[slot];
+    }
+    const int frc = async_wait_ticket(en, t);
+    if (frc) return frc;
   }
+  std::vector<cudaEvent_t> evs;
+  {
+    std::lock_guard<std::mutex> issue(en->issue_m);  // the sequencer may be issuing later pictures
+    for (int ph = 0; ph < B200_MAX_PHYS; ph++) {
+      // the surface that carries the name, and surfaces that carried it before a later picture took the name elsewhere: a
+      // read-back requested from them may still be in flight
+      const bool current = en->lmap[slot] == ph;
+      if (!current && !(en->owner[ph] < 0 && en->last_owner[ph] == slot)) continue;
+      SlotSync& ss = en->ssync[ph];
+      if (current && ss.writer >= 0) evs.push_back(ss.written);
+      for (int c = 0; c < B200_MAX_CTX; c++)
+        if (ss.read_pending[c]) evs.push_back(ss.read[c]);
+    }
+  }
+  for (cudaEvent_t e : evs) CU(cudaEventSynchronize(e));
   return check_intra_err(en);
 }
 

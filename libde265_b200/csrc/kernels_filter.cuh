@@ -381,7 +381,7 @@ struct Sao8Layout {
   int n_ctb, ipl, ipc;  // items (warps) per luma / chroma CTB
 };
 
-__global__ void __launch_bounds__(SAO8_WARPS * 32) k_sao8(DevPic pic, FilterArgs a, Sao8Layout lay)
+__global__ void __launch_bounds__(SAO8_WARPS * 32, 4) k_sao8(DevPic pic, FilterArgs a, Sao8Layout lay)
 {
   const int lane = threadIdx.x & 31;
   int item = blockIdx.x * SAO8_WARPS + (threadIdx.x >> 5);

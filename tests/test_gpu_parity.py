@@ -87,13 +87,16 @@ def test_real_intra_stream_end_to_end(b200lib, name):
     assert n == exp["pictures"] and md.hexdigest() == exp["md5_of_all_planes_in_output_order"]
 
 
-@pytest.mark.parametrize("lag", [0, 1])
+@pytest.mark.parametrize("lag,queued", [(0, False), (1, False), (1, True)])
 @pytest.mark.skipif(oracle_lib.ref_path("libde265_hooked.so") is None, reason="oracle/_ref not shipped")
-def test_girlshy_through_the_acceleration_code(b200lib, lag):
+def test_girlshy_through_the_acceleration_code(b200lib, monkeypatch, lag, queued):
     """The drop-in switch itself: de265_set_parameter_int(ctx, DE265_DECODER_PARAM_ACCELERATION_CODE, de265_acceleration_B200)
     on a libde265 built with the binding of INTEGRATION.md — no sink, no Python in the data path: the decoder owns a B200 engine,
     submits every picture asynchronously at picture end and awaits the read-back when the picture is handed out.  Golden md5 of
-    scripts/ci-run.sh:91-92, with the dec265 loop (lag 0) and with pictures fetched one de265_decode call late (lag 1)."""
+    scripts/ci-run.sh:91-92, with the dec265 loop (lag 0) and with pictures fetched one de265_decode call late (lag 1); `queued`:
+    the backend queues the pictures (b200_engine_submit_picture_async, ring of recorders, tickets) instead of planning them in the hook."""
+    if queued:
+        monkeypatch.setenv("B200_HOOK_ASYNC", "1")
     dec = de265.Decoder(oracle_lib.ref_path("libde265_hooked.so"))
     dec.select_b200()
     md = hashlib.md5()
