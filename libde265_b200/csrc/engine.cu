@@ -336,6 +336,7 @@ struct b200_engine {
   int owner[B200_MAX_PHYS];       // physical surface -> name it currently carries, -1: free (may still have readers in flight)
   int last_owner[B200_MAX_PHYS];  // the name it carried last (b200_engine_wait_slot also waits for reads of a renamed-away surface)
   bool rename = true;
+  uint64_t pool_geom = 0;  // format of the last picture issued (run_layout)
   int intra_width_pct = 0;  // off: warps beyond the DAG's width still pay (they run the dependency-free part of later levels ahead: measured)
   bool sao_legacy = false;  // B200_SAO_LEGACY=1: k_sao for 8-bit pictures too
   uint64_t n_renamed = 0;
@@ -1610,6 +1611,19 @@ static int run_layout(b200_engine* en, int k, const PicLayout& L, uint8_t* dbase
     const Surface& s = en->slot[en->lmap[i]];
     if (s.valid && s.w == p.width && s.h == p.height && s.chroma == p.chroma_format_idc && s.bd_y == p.bit_depth_luma && s.bd_c == p.bit_depth_chroma)
       for (int c = 0; c < 3; c++) refs.plane[i][c] = s.plane[c];
+  }
+  {
+    // Format change (new SPS): drain, then drop every surface that carries no name — surfaces of another format cannot be reused
+    // as they are, and converting them one rename at a time (free + allocate, each a device-wide synchronisation) was measured
+    // to leave the second format at 75 % of its speed for a long time.
+    const uint64_t geom = (uint64_t)p.width | ((uint64_t)p.height << 16) | ((uint64_t)p.chroma_format_idc << 32) |
+                          ((uint64_t)bytes_per_sample(p.bit_depth_luma) << 34) | ((uint64_t)bytes_per_sample(p.bit_depth_chroma) << 36);
+    if (en->pool_geom && en->pool_geom != geom) {
+      for (int c = 0; c < B200_MAX_CTX; c++) CU(cudaStreamSynchronize(en->ctx[c].stream));
+      for (int ph = 0; ph < B200_MAX_PHYS; ph++)
+        if (en->owner[ph] < 0 && en->slot[ph].plane[0] && !same_geometry(en->slot[ph], p)) surface_free(en->slot[ph]);
+    }
+    en->pool_geom = geom;
   }
   int dst_phys = phys_for_write(en, p.dst_slot, k, p);
   if (dst_phys < 0) {  // first use of the name with every surface taken: cannot happen (B200_MAX_PHYS > B200_MAX_SLOTS), but stay safe

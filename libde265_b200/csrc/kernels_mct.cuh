@@ -43,7 +43,7 @@
 #define MCT_MAX_TL MCT_TLS
 #define MCT_MAX_TILES MCT_TLS            // tiles per batch (small, uni-predicted)
 #define MCT_WIN_BYTES (MCT_TLS * 1280)   // window region: TLS/2 x (1280 + 896) big  |  TLS x (640 + 640) small
-#define MCT_INT_WORDS (MCT_TLS * 200)    // intermediate region: TLS/2 x (240 + 144) big  |  TLS x (100 + 100) small
+#define MCT_INT_WORDS (MCT_TLS * 200)    // intermediate region: TLS/2 x (244 + 148) big  |  TLS x (100 + 100) small
 // big boxes (tiles wider or taller than 8): luma 48 bytes x 26 rows (16-byte aligned origin + up to 15 + 23 columns; 23 rows + up
 // to 3 rows of bank skew), chroma 32 bytes x 14 rows x {Cb, Cr}
 #define MCT_LWB_PITCH 48
@@ -127,7 +127,9 @@ MCT_HD MctGeom mct_geom(int cls)
   } else {
     g.lw_pitch = MCT_LWB_PITCH; g.lw_slot = MCT_LWB_SLOT; g.cw_off = MCT_TLS / 2 * MCT_LWB_SLOT; g.cw_pitch = MCT_CWB_PITCH;
     g.cw_plane = MCT_CWB_PITCH * MCT_CWB_ROWS; g.cw_slot = MCT_CWB_SLOT;
-    g.li_pitch = 20; g.li_words = 240; g.ci_off = MCT_TLS / 2 * 240; g.ci_pitch = 12; g.ci_plane = 72; g.ci_words = 144;
+    // slot strides of 244 / 148 words (= 20 mod 32): the 8 lanes of a 16-byte store phase, one slot each, hit 8 different bank groups
+    // (240 / 144 = 16 mod 32 put them on two)
+    g.li_pitch = 20; g.li_words = 244; g.ci_off = MCT_TLS / 2 * 244; g.ci_pitch = 12; g.ci_plane = 72; g.ci_words = 148;
   }
   return g;
 }
