@@ -41,6 +41,8 @@ GOP_REFS = {8: (0, None), 4: (0, 8), 2: (0, 4), 6: (4, 8), 1: (0, 2), 3: (2, 4),
 # referenced or read out, so a new picture never waits for readers of the picture it overwrites (no WAR stalls), and the
 # assignment repeats every two intra periods: the workload is 64 prepared pictures, a step alternates between its halves.
 KEY_SLOTS, REFB_SLOTS, NONREF_SLOTS = 8, 8, 16
+if os.environ.get("B200_TIGHT_DPB"):  # experiment: the smallest DPB the GOP structure allows (7 slots, every slot reused at once): the
+    KEY_SLOTS, REFB_SLOTS, NONREF_SLOTS = 2, 3, 2  # WAR / WAW hazards the engine's slot renaming removes (tools/sweep_bench.py)
 STEP_VARIANTS = 2
 
 

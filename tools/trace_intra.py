@@ -38,3 +38,15 @@ for c in range(3):
         m = (plane == c) & (cnt == k)
         print(f" plane {c} TUs/task {k:2d}: n={m.sum():6d} work mean {work[m].mean()/clk:7.2f} us  (log2 of first TU: {np.bincount(lg[m]).tolist()})")
 print("sum of work / 1e3:", work.sum() / clk / 1e3, "ms  => with", 148 * 3 * 8, "warps:", work.sum() / clk / 1e3 / (148 * 3 * 8), "ms")
+# ticket-order view (tickets are in DAG-level order): when are the tasks of each slice of the ticket range claimed / finished?
+idx = np.arange(n)
+base = t0.min()
+print("ticket range   claim us (p50,max)   end us (p50,max)   wait us mean   work us mean   TUs")
+for a, b in [(i * n // 10, (i + 1) * n // 10) for i in range(10)]:
+    sl = slice(a, b)
+    print(f" {a:6d}-{b:6d}   {np.percentile(t0[sl]-base,50)/1e3:7.1f} {float((t0[sl]-base).max())/1e3:7.1f}   {np.percentile(end[sl]-base,50)/1e3:7.1f} {float((end[sl]-base).max())/1e3:7.1f}   "
+          f"{wait[sl].mean()/clk:7.2f}   {work[sl].mean()/clk:7.2f}   {cnt[sl].sum()}")
+late = np.argsort(end)[-12:]
+print("last tasks to finish: ticket, claim us, wait us, work us, TUs, plane")
+for i in late:
+    print(f"  {i:6d} {float(t0[i]-base)/1e3:8.1f} {wait[i]/clk:8.1f} {work[i]/clk:8.1f} {cnt[i]:3d} {plane[i]}")
