@@ -440,43 +440,50 @@ __device__ void tu_intra_large(const b200_tu& tu, const P* gsrc, int gstride, P*
   P* b1 = b1mem + 2 * 32 + 2;
   const int total = 4 * nT + 1;
   // ---- gather + substitution (intrapred.h:529-674); scan index s: 0 -> border[-2nT], 2nT -> border[0], 4nT -> border[2nT]
+  // All (up to 129) neighbour samples are requested FIRST — up to five independent loads per lane, one L2 round trip — and the
+  // availability scan / substitution then runs on registers.  (The loads used to sit inside the two chunk loops, each chunk's
+  // ballot waiting for its load: ten dependent round trips per large TU, ~8 us of the task's dependent latency.)
   {
-    int carry = -1;  // value of the last sample of the previous chunk after substitution
+    constexpr int MAXC = 5;  // ceil((4 * 32 + 1) / 32)
+    int v[MAXC];
+    bool av[MAXC];
+#pragma unroll
+    for (int c5 = 0; c5 < MAXC; c5++) {
+      const int s = 32 * c5 + lane, i = s - 2 * nT;
+      av[c5] = false;
+      v[c5] = 0;
+      if (s < total) {
+        const P* addr;
+        if (i < 0) { const int r = -i - 1; av[c5] = (avail >> (r >> 2)) & 1; addr = gsrc - 1 + r * gstride; }
+        else if (i == 0) { av[c5] = (avail >> B200_AVAIL_CORNER_BIT) & 1; addr = gsrc - 1 - gstride; }
+        else { const int c = i - 1; av[c5] = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; addr = gsrc + c - gstride; }
+        if (av[c5]) v[c5] = (int)__ldcg(addr);
+      }
+    }
     // first available sample in scan order (firstValue)
     int first_val = 1 << (bd - 1);
     bool any = false;
-    for (int base = 0; base < total; base += 32) {
-      const int s = base + lane, i = s - 2 * nT;
-      bool av = false;
-      int v = 0;
-      if (s < total) {
-        if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = (int)__ldcg(gsrc - 1 + r * gstride); }
-        else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = (int)__ldcg(gsrc - 1 - gstride); }
-        else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = (int)__ldcg(gsrc + c - gstride); }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, av);
-      if (!any && m) { first_val = __shfl_sync(0xffffffffu, v, __ffs(m) - 1); any = true; }
+#pragma unroll
+    for (int c5 = 0; c5 < MAXC; c5++) {
+      const unsigned m = __ballot_sync(0xffffffffu, av[c5]);
+      if (!any && m) { first_val = __shfl_sync(0xffffffffu, v[c5], __ffs(m) - 1); any = true; }
     }
     if (!any) {
       for (int s = lane; s < total; s += 32) b0[s - 2 * nT] = (P)(1 << (bd - 1));
     } else {
-      carry = first_val;
-      for (int base = 0; base < total; base += 32) {
-        const int s = base + lane, i = s - 2 * nT;
-        bool av = false;
-        int v = 0;
-        if (s < total) {
-          if (i < 0) { const int r = -i - 1; av = (avail >> (r >> 2)) & 1; if (av) v = (int)__ldcg(gsrc - 1 + r * gstride); }
-          else if (i == 0) { av = (avail >> B200_AVAIL_CORNER_BIT) & 1; if (av) v = (int)__ldcg(gsrc - 1 - gstride); }
-          else { const int c = i - 1; av = (avail >> (B200_AVAIL_TOP_BIT0 + (c >> 2))) & 1; if (av) v = (int)__ldcg(gsrc + c - gstride); }
+      int carry = first_val;  // value of the last sample of the previous chunk after substitution
+#pragma unroll
+      for (int c5 = 0; c5 < MAXC; c5++) {
+        if (32 * c5 < total) {  // warp-uniform
+          const int s = 32 * c5 + lane, i = s - 2 * nT;
+          const unsigned m = __ballot_sync(0xffffffffu, av[c5]);
+          const unsigned below = m & ((2u << lane) - 1u);  // available lanes <= this one
+          const int src = below ? 31 - __clz(below) : 0;
+          const int sv = __shfl_sync(0xffffffffu, v[c5], src);
+          const int outv = below ? sv : carry;
+          if (s < total) b0[i] = (P)outv;
+          carry = __shfl_sync(0xffffffffu, outv, 31);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, av);
-        const unsigned below = m & ((2u << lane) - 1u);  // available lanes <= this one
-        const int src = below ? 31 - __clz(below) : 0;
-        const int sv = __shfl_sync(0xffffffffu, v, src);
-        const int outv = below ? sv : carry;
-        if (s < total) b0[i] = (P)outv;
-        carry = __shfl_sync(0xffffffffu, outv, 31);
       }
     }
   }
@@ -664,7 +671,7 @@ __device__ __forceinline__ void dep_units_of(const b200_tu& tu, int rx, int ry, 
 }
 
 template <typename P>
-__global__ void __launch_bounds__(RC_THREADS) k_intra(DevPic pic, ReconArgs args)
+__global__ void __launch_bounds__(RC_THREADS, 3) k_intra(DevPic pic, ReconArgs args)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   IntraSmem<P>& sm = *reinterpret_cast<IntraSmem<P>*>(smem_raw);
