@@ -560,6 +560,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    if world > 1:  # the ranks of one node share its cores: split the host-side threads of the engines between them
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        cores = effective_cores()[0]
+        os.environ.setdefault("B200_ASYNC_THREADS", str(max(2, (cores - 2 * local_world) // local_world)))
+        os.environ.setdefault("B200_HOST_THREADS", str(max(2, min(8, cores // local_world))))
     eng = Engine(local_rank)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
 

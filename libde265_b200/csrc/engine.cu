@@ -366,8 +366,8 @@ struct b200_engine {
   long long slot_depth[B200_MAX_SLOTS] = {}, tail_depth[B200_MAX_CTX] = {}, key_depth = 0;  // pick_ctx: dependency depths
   // one intra task per plane and region in every picture (default).  B200_INTRA_SPLIT=0: pictures with inter prediction merge the
   // planes of a region into one task — fewer tasks, but each runs its segments in sequence (three dependent L2 round trips);
-  // measured with tickets in level order and 3 CTAs per SM: 4K B picture k_intra 0.25 ms split vs 0.28-1.4 ms (unstable) merged,
-  // bench 3382 vs 3210 frames/s
+  // measured with tickets in level order and 3 CTAs per SM: 4K B picture k_intra 0.25 ms split vs 0.28 ms merged, bench 3382 vs 3210
+  // frames/s
   bool intra_split_planes = true;
   bool sched_rr = false;        // B200_SCHED=rr: plain round-robin placement (A/B measurements)
   int n_ind = 2, next_ind = 0, ind_run = 0;  // streams for pictures that read no reference (intra pictures), used round-robin (B200_IND_STREAMS)
