@@ -13,6 +13,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <exception>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -1897,18 +1898,27 @@ static int async_start(b200_engine* en)
   if (const char* e = getenv("B200_ASYNC_THREADS")) n = std::max(1, std::min(32, atoi(e)));
   as->depth = std::min(B200_ASYNC_DEPTH, n + 8);
   if (const char* e = getenv("B200_ASYNC_QUEUE")) as->depth = std::max(1, std::min(B200_ASYNC_DEPTH, atoi(e)));
-  for (int i = 0; i < n; i++) {
-    b200_engine* sh = new b200_engine();  // no CUDA state: only the planner's scratch and the flags the planner reads
-    sh->device = en->device;
-    sh->region = en->region;
-    sh->mc_legacy = en->mc_legacy;
-    sh->intra_split_planes = en->intra_split_planes;
-    sh->intra_level_order = en->intra_level_order;
-    sh->helper = &en->pool;
-    as->shadows.push_back(sh);
-    as->planners.emplace_back(async_planner, en, sh);
+  try {  // thread creation may throw (resource limits): no exception leaves the C ABI
+    as->sequencer = std::thread(async_sequencer, en);
+    for (int i = 0; i < n; i++) {
+      b200_engine* sh = new b200_engine();  // no CUDA state: only the planner's scratch and the flags the planner reads
+      sh->device = en->device;
+      sh->region = en->region;
+      sh->mc_legacy = en->mc_legacy;
+      sh->intra_split_planes = en->intra_split_planes;
+      sh->intra_level_order = en->intra_level_order;
+      sh->helper = &en->pool;
+      as->shadows.push_back(sh);
+      as->planners.emplace_back(async_planner, en, sh);
+    }
+  } catch (const std::exception& ex) {
+    if (as->planners.empty() || !as->sequencer.joinable()) {  // nothing usable: tear down what exists
+      async_stop(en);
+      return set_err(B200_ERR_NOMEM, "asynchronous submission: cannot start threads (%s)", ex.what());
+    }
+    // fewer planners than asked for still work
+    as->depth = std::min(as->depth, (int)as->planners.size() + 8);
   }
-  as->sequencer = std::thread(async_sequencer, en);
   return B200_OK;
 }
 
@@ -1932,6 +1942,7 @@ static int async_wait_ticket(b200_engine* en, unsigned long long ticket)
   AsyncState* as = en->async;
   if (!as) return B200_OK;
   std::unique_lock<std::mutex> lk(as->m);
+  if (ticket > as->enq_seq) ticket = as->enq_seq;  // a ticket that was never handed out: everything queued so far
   as->cv_space.wait(lk, [&] { return as->done_seq >= ticket; });
   const int rc = as->first_rc;
   if (rc) set_err(rc, "%s", as->first_err.c_str());
@@ -1952,7 +1963,7 @@ static void async_stop(b200_engine* en)
   as->cv_plan.notify_all();
   as->cv_seq.notify_all();
   for (auto& t : as->planners) t.join();
-  as->sequencer.join();
+  if (as->sequencer.joinable()) as->sequencer.join();
   for (b200_engine* sh : as->shadows) delete sh;
   delete as;
   en->async = nullptr;

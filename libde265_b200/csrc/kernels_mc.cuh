@@ -5,7 +5,7 @@
 //
 // Work split: the host cuts every PU into tiles of at most 16x16 luma samples (+ the co-located
 // 8x8 Cb/Cr samples); one warp owns one tile, four warps per CTA.  Per list the warp runs the
-// horizontal pass straight from the reference plane (clamped coordinates = motion.cc:147-153) into a
+// horizontal pass straight from the (border-padded) reference plane into a
 // per-warp shared-memory int16 strip, then the vertical pass + weighting from shared memory, and
 // writes the predicted samples with 4-sample (luma) / 2-sample (chroma) vector stores.
 #pragma once
@@ -35,28 +35,57 @@ __device__ __forceinline__ int weight_sample(int a, int b, const WeightParams& w
   return clip_bd(v, bd);
 }
 
-template <typename P, int NT>
+template <typename P, int NT, bool PADDED = false>
 __device__ __forceinline__ void mc_hpass(int16_t* strip, const uint8_t* ref, int pitch, int pw, int ph, int x_int, int y_int,
                                          int x_frac, int y_frac, int tw, int th, int bd, int lane, const int8_t* taps_h)
 {
+  if (!PADDED) {  // plain buffers (the per-block DSP table, dsp_table.cuh): every coordinate clamped as motion.cc:147-153 does
+    constexpr int TWMAX = (NT == 8) ? MC_TILE : MC_TILE / 2;
+    constexpr int BEFORE = (NT == 8) ? 3 : 1;
+    const int before = y_frac ? BEFORE : 0;
+    const int nrows = th + (y_frac ? NT - 1 : 0);
+    const int shift1 = bd - 8;
+    for (int idx = lane; idx < nrows * TWMAX; idx += B200_WARP) {
+      const int r = idx / TWMAX, c = idx % TWMAX;
+      if (c >= tw) continue;
+      const int ya = clip3i(0, ph - 1, y_int + r - before);
+      const P* row = row_ptr<P>(ref, pitch, ya);
+      int v;
+      if (x_frac == 0) {
+        v = row[clip3i(0, pw - 1, x_int + c)];
+      } else {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < NT; k++) sum += taps_h[k] * (int)row[clip3i(0, pw - 1, x_int + c + k - BEFORE)];
+        v = sum >> shift1;
+      }
+      strip[r * TWMAX + c] = (int16_t)v;
+    }
+    return;
+  }
   // Rows [-before, th+after) when a vertical filter follows, else th rows.  Strip row stride = TWMAX.
+  // The reference surfaces carry a replicated border (engine.cu), so the coordinate clamping of motion.cc:147-153 is done ONCE per
+  // tile: the window of (tw + NT - 1) x (th + NT - 1) samples is moved to the border's rim when the motion vector points further
+  // out (same samples), and the taps read it without any per-sample clamp.
   constexpr int TWMAX = (NT == 8) ? MC_TILE : MC_TILE / 2;
   constexpr int BEFORE = (NT == 8) ? 3 : 1;
-  const int before = y_frac ? BEFORE : 0;
+  constexpr int PADX = (NT == 8) ? B200_PAD_X : B200_PAD_CX, PADY = (NT == 8) ? B200_PAD_Y : B200_PAD_CY;
+  constexpr int WIN = TWMAX + NT - 1;
+  const int wx = clip3i(-PADX, pw + PADX - WIN, x_int - BEFORE), wy = clip3i(-PADY, ph + PADY - WIN, y_int - BEFORE);
+  const int r0 = y_frac ? 0 : BEFORE;  // first window row the strip needs
   const int nrows = th + (y_frac ? NT - 1 : 0);
   const int shift1 = bd - 8;
   for (int idx = lane; idx < nrows * TWMAX; idx += B200_WARP) {
     const int r = idx / TWMAX, c = idx % TWMAX;
     if (c >= tw) continue;
-    const int ya = clip3i(0, ph - 1, y_int + r - before);
-    const P* row = row_ptr<P>(ref, pitch, ya);
+    const P* row = row_ptr<P>(ref, pitch, wy + r0 + r) + wx + c;
     int v;
     if (x_frac == 0) {
-      v = row[clip3i(0, pw - 1, x_int + c)];
+      v = row[BEFORE];
     } else {
       int sum = 0;
 #pragma unroll
-      for (int k = 0; k < NT; k++) sum += taps_h[k] * (int)row[clip3i(0, pw - 1, x_int + c + k - BEFORE)];
+      for (int k = 0; k < NT; k++) sum += taps_h[k] * (int)row[k];
       v = sum >> shift1;
     }
     strip[r * TWMAX + c] = (int16_t)v;
@@ -109,14 +138,14 @@ __global__ void __launch_bounds__(128) k_inter_pred(DevPic pic, RefTable refs, c
     const int mvx = pu.mv[l][0], mvy = pu.mv[l][1];
     xf[l] = mvx & 3; yf[l] = mvy & 3;
     int16_t* strip = s_strip[warp][l];
-    mc_hpass<P, 8>(strip, ry, pic.pitch[0], pic.w, pic.h, x0 + (mvx >> 2), y0 + (mvy >> 2), xf[l], yf[l], tw, th, pic.bd_y, lane, k_qpel[xf[l]]);
+    mc_hpass<P, 8, true>(strip, ry, pic.pitch[0], pic.w, pic.h, x0 + (mvx >> 2), y0 + (mvy >> 2), xf[l], yf[l], tw, th, pic.bd_y, lane, k_qpel[xf[l]]);
     if (has_chroma) {
       // 4:2:0: chroma mv in eighth samples = luma mv (motion.cc:196-206)
       xfc[l] = mvx & 7; yfc[l] = mvy & 7;
       const int xi = (x0 >> 1) + (mvx >> 3), yi = (y0 >> 1) + (mvy >> 3);
-      mc_hpass<P, 4>(strip + MC_LUMA_ROWS * MC_TILE, refs.plane[slot][1], pic.pitch[1], pic.cw, pic.ch, xi, yi, xfc[l], yfc[l], cwd, chh,
+      mc_hpass<P, 4, true>(strip + MC_LUMA_ROWS * MC_TILE, refs.plane[slot][1], pic.pitch[1], pic.cw, pic.ch, xi, yi, xfc[l], yfc[l], cwd, chh,
                      pic.bd_c, lane, k_epel[xfc[l]]);
-      mc_hpass<P, 4>(strip + MC_LUMA_ROWS * MC_TILE + MC_CH_ROWS * (MC_TILE / 2), refs.plane[slot][2], pic.pitch[2], pic.cw, pic.ch, xi, yi,
+      mc_hpass<P, 4, true>(strip + MC_LUMA_ROWS * MC_TILE + MC_CH_ROWS * (MC_TILE / 2), refs.plane[slot][2], pic.pitch[2], pic.cw, pic.ch, xi, yi,
                      xfc[l], yfc[l], cwd, chh, pic.bd_c, lane, k_epel[xfc[l]]);
     }
   }
