@@ -118,6 +118,17 @@ def pin_records(seq, torch):
     return True
 
 
+def unpin_records(seq, torch):
+    """Undo pin_records: page-locked memory is a shared resource of the host (later legs and the decoder's own page-locked picture
+    planes were measured to slow down with gigabytes of it registered)."""
+    rt = torch.cuda.cudart()
+    for ptr in list(_PINNED):
+        rt.cudaHostUnregister(ptr)
+        del _PINNED[ptr]
+    for p in seq:
+        p.c.params.flags &= ~capi_flags().PIC_RECORDS_PINNED
+
+
 def capi_flags():
     from libde265_b200 import capi
     return capi
@@ -445,6 +456,8 @@ def run_config(name, eng, torch, dist, stream, a, rank, local_rank, world, headl
     eng.sync()
     ms_e2e = timed(step_e2e, steps)
     eng.sync()
+    if pinned:
+        unpin_records(seq, torch)
     for h in prepared:
         eng.free_prepared(h)
     if rank != 0:
