@@ -346,36 +346,7 @@ __global__ void __launch_bounds__(128) k_sao(DevPic pic, FilterArgs a)
 #define SAO8_R 2
 #define SAO8_WARPS 8
 
-__device__ __forceinline__ uint32_t sao8_rep(uint32_t x)  // 0xFF in every byte whose bit 7 is set
-{
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(r) : "r"(x));
-  return r;
-}
-__device__ __forceinline__ uint32_t sao8_lt(uint32_t x, uint32_t y)  // byte mask: x < y (unsigned)
-{
-  const uint32_t d = (x | 0x80808080u) - (y & 0x7F7F7F7Fu);
-  return sao8_rep((~x & y) | (~(x ^ y) & ~d));
-}
-__device__ __forceinline__ uint32_t sao8_eq_small(uint32_t k, uint32_t cst)  // byte mask: k == cst, for bytes < 0x80
-{
-  const uint32_t z = k ^ cst;
-  return ~sao8_rep(z + 0x7F7F7F7Fu);  // bit 7 set <=> byte nonzero
-}
-__device__ __forceinline__ uint32_t sao8_apply(uint32_t s, uint32_t pos, uint32_t neg)  // clip(s + pos - neg, 0, 255) per byte; pos, neg < 128
-{
-  // saturating add: low 7 bits with carry into bit 7, then the true bit 7; overflow <=> s's bit 7 set and the sum's clear
-  const uint32_t t = ((s & 0x7F7F7F7Fu) + pos) ^ (s & 0x80808080u);
-  const uint32_t a = t | sao8_rep(s & ~t);
-  // saturating subtract: (a | 0x80) - neg never borrows; bit 7 of u <=> low7(a) >= neg
-  const uint32_t u = (a | 0x80808080u) - neg;
-  const uint32_t hi = sao8_rep(a), ok = sao8_rep(u);
-  return (hi & u) | (~hi & ok & u & 0x7F7F7F7Fu);
-}
-__device__ __forceinline__ uint32_t sao8_mask4(unsigned bits)  // 4 bits -> 4 byte masks
-{
-  return sao8_rep((((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0x80u);
-}
+#include "sao8_swar.cuh"
 
 struct Sao8Layout {
   int n_ctb, ipl, ipc;  // items (warps) per luma / chroma CTB
