@@ -28,3 +28,31 @@ def test_dpb_slot_policy_has_no_hazards_and_is_periodic():
             assert d not in holder or poc - holder[d] >= 16, f"POC {poc} overwrites POC {holder[d]} too early"
             holder[d] = poc
         poc_base += 32 * bench.STEP_VARIANTS
+
+
+def test_tight_dpb_variant_still_references_the_right_pictures(monkeypatch):
+    """B200_TIGHT_DPB=1 (the slot-renaming experiment of tools/sweep_bench.py): 7 slots, every slot reused as early as the GOP
+    structure allows — references must still hold the pictures the GOP names, and the assignment must stay periodic."""
+    import importlib
+    monkeypatch.setenv("B200_TIGHT_DPB", "1")
+    tight = importlib.reload(bench)
+    try:
+        assert (tight.KEY_SLOTS, tight.REFB_SLOTS, tight.NONREF_SLOTS) == (2, 3, 2)
+        seq, key_slot, _ = tight.build_workload(64, 64, 8)
+        holder = {key_slot: 0}
+        poc_base = 0
+        for rep in range(3):
+            for p in seq:
+                poc = poc_base + p.params.poc
+                g, off = divmod(p.params.poc - 1, 8)
+                off += 1
+                r0, r1 = tight.GOP_REFS[off]
+                want = {poc_base + g * 8 + r0} | ({poc_base + g * 8 + r1} if r1 is not None else set())
+                refs = {int(s) for s in p.pus["ref_slot"].ravel() if s >= 0} if len(p.pus) else set()
+                assert {holder[s] for s in refs} <= want, f"POC {poc}: a reference slot holds the wrong picture"
+                assert p.params.dst_slot not in refs
+                holder[p.params.dst_slot] = poc
+            poc_base += 32 * tight.STEP_VARIANTS
+    finally:
+        monkeypatch.delenv("B200_TIGHT_DPB")
+        importlib.reload(bench)
