@@ -231,8 +231,10 @@ B200_API int  b200_engine_submit_picture(b200_engine*, const b200_picture*);
 
 /* Asynchronous submission: queues the picture and returns; planner threads validate / plan / pack whole pictures in parallel and one
  * sequencer thread issues them to the GPU in submission order, exactly as b200_engine_submit_picture would (same stream placement,
- * same results).  The record ARRAYS the picture points to must stay valid until b200_engine_flush (or _sync, _read_slot, _wait_slot)
- * returns; the b200_picture struct itself is copied.  b200_engine_read_slot_async calls are queued behind the pictures submitted
+ * same results).  The record ARRAYS the picture points to must stay valid until the picture has been issued: until b200_engine_flush,
+ * _sync or _read_slot returns, or b200_engine_wait_ticket of the picture's ticket, or b200_engine_wait_slot of its OWN destination slot
+ * (with B200_PIC_RECORDS_PINNED: until the picture has been reconstructed, i.e. _sync / _wait_slot); the b200_picture struct itself is
+ * copied.  b200_engine_read_slot_async calls are queued behind the pictures submitted
  * before them.  Errors of queued pictures (malformed records) are reported by the next flush / sync: the picture is skipped.
  * For hosts that produce pictures faster than one thread can plan them (parallel parsers, cached records, bench.py e2e). */
 B200_API int  b200_engine_submit_picture_async(b200_engine*, const b200_picture*);
