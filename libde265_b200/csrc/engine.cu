@@ -311,7 +311,7 @@ struct SlotSync {
 #define PLAN_INTRA_PARTS 8
 struct IntraPart {
   uint32_t i0 = 0, i1 = 0, task_base = 0;
-  std::vector<uint32_t> intra_idx, task_of, task_first, diag_cnt, diag_off, fill;
+  std::vector<uint32_t> intra_idx, task_of, task_first, task_cell, diag_cnt, diag_off, fill;  // task_cell: region cell x | y << 12 | cells per side << 24 | plane << 28
 };
 
 struct AsyncState;
@@ -967,38 +967,51 @@ static int plan_pus_part(b200_engine* en, const b200_picture* pic, int part, uin
 {
   const b200_pic_params& p = pic->params;
   std::vector<uint32_t>& tiles = en->pu_tiles[part];
-  tiles.clear();
+  // at most 16 tiles (64x64 PU) per record: written through a raw pointer, trimmed at the end (no per-tile capacity check)
+  tiles.resize((size_t)(i1 - i0) * 16);
+  uint32_t* out = tiles.data();
   uint32_t ref_mask = 0;
-  size_t* count = en->pu_count[part];
-  for (int c = 0; c < 8; c++) count[c] = 0;
+  size_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool wide = p.bit_depth_luma > 8;  // same rule as the launch_picture<P> dispatch
+  const bool legacy = en->mc_legacy;
+  const unsigned pw = p.width, ph = p.height;
+  const uint32_t n_weights = pic->n_weights;
+  const b200_pu* pus = pic->pus;
   for (uint32_t i = i0; i < i1; i++) {
-    const b200_pu& pu = pic->pus[i];
-    if (pu.w == 0 || pu.h == 0 || pu.w > 64 || pu.h > 64 || (pu.w & 3) || (pu.h & 3) || (pu.x & 3) || (pu.y & 3) ||
-        pu.x + pu.w > p.width || pu.y + pu.h > p.height)
+    const b200_pu& pu = pus[i];
+    const unsigned w = pu.w, h = pu.h;
+    if (w - 1u > 63u || h - 1u > 63u || ((w | h | pu.x | pu.y) & 3u) || pu.x + w > pw || pu.y + h > ph)
       return set_err(B200_ERR_INVALID, "PU %u out of range", i);
-    if ((pu.flags & B200_PU_WEIGHTED) && pu.wt_idx >= pic->n_weights) return set_err(B200_ERR_INVALID, "PU %u weight index", i);
+    if ((pu.flags & B200_PU_WEIGHTED) && pu.wt_idx >= n_weights) return set_err(B200_ERR_INVALID, "PU %u weight index", i);
     if (pu.ref_slot[0] >= B200_MAX_SLOTS || pu.ref_slot[1] >= B200_MAX_SLOTS) return set_err(B200_ERR_INVALID, "PU %u reference slot", i);
-    if (!(pu.flags & (B200_PU_PRED_L0 | B200_PU_PRED_L1))) continue;
-    if ((pu.flags & B200_PU_PRED_L0) && pu.ref_slot[0] >= 0) ref_mask |= 1u << pu.ref_slot[0];
-    if ((pu.flags & B200_PU_PRED_L1) && pu.ref_slot[1] >= 0) ref_mask |= 1u << pu.ref_slot[1];
+    const unsigned l0 = pu.flags & B200_PU_PRED_L0, l1 = pu.flags & B200_PU_PRED_L1;
+    if (!(l0 | l1)) continue;
+    if (l0 && pu.ref_slot[0] >= 0) ref_mask |= 1u << pu.ref_slot[0];
+    if (l1 && pu.ref_slot[1] >= 0) ref_mask |= 1u << pu.ref_slot[1];
     if (wide) {  // 16-bit path: <= 16x16 tiles, one warp each (kernels_mc.cuh)
-      for (int ty = 0; ty * MC_TILE < pu.h; ty++)
-        for (int tx = 0; tx * MC_TILE < pu.w; tx++) tiles.push_back(i | ((uint32_t)tx << 20) | ((uint32_t)ty << 22));
-    } else if (en->mc_legacy) {  // first-generation 8-bit path: <= 8x16 units, one quarter-warp each (kernels_mc8.cuh)
-      for (int uy = 0; uy * MC8_UH < pu.h; uy++)
-        for (int ux = 0; ux * MC8_UW < pu.w; ux++) tiles.push_back(MC8_UNIT(i, ux, uy));
+      for (unsigned ty = 0; ty * MC_TILE < h; ty++)
+        for (unsigned tx = 0; tx * MC_TILE < w; tx++) *out++ = i | (tx << 20) | (ty << 22);
+    } else if (legacy) {  // first-generation 8-bit path: <= 8x16 units, one quarter-warp each (kernels_mc8.cuh)
+      tiles.resize((size_t)(out - tiles.data()));  // (rare debug path: up to 32 units per PU, keep the simple form)
+      for (unsigned uy = 0; uy * MC8_UH < h; uy++)
+        for (unsigned ux = 0; ux * MC8_UW < w; ux++) tiles.push_back(MC8_UNIT(i, ux, uy));
+      const size_t used = tiles.size();
+      tiles.resize(used + (size_t)(i1 - i - 1) * 32 + 32);
+      out = tiles.data() + used;
     } else {     // 8-bit path: <= 16x16 tiles with their class (kernels_mct.cuh), sorted into class-pure batches by the merge
-      const int bi = ((pu.flags & B200_PU_PRED_L0) && (pu.flags & B200_PU_PRED_L1)) ? MCT_CLASS_BI : 0;
-      for (int ty = 0; ty * 16 < pu.h; ty++)
-        for (int tx = 0; tx * 16 < pu.w; tx++) {
-          const int tw = std::min(16, pu.w - 16 * tx), th = std::min(16, pu.h - 16 * ty);
-          const int cls = bi | (tw > 8 ? MCT_CLASS_WIDE : 0) | (th > 8 ? MCT_CLASS_TALL : 0);
-          tiles.push_back(MCT_TILE_WORD(i, tx, ty, cls));
+      const unsigned bi = (l0 && l1) ? MCT_CLASS_BI : 0;
+      for (unsigned ty = 0; ty * 16 < h; ty++) {
+        const unsigned tall = (h - 16 * ty > 8) ? MCT_CLASS_TALL : 0;
+        for (unsigned tx = 0; tx * 16 < w; tx++) {
+          const unsigned cls = bi | tall | ((w - 16 * tx > 8) ? MCT_CLASS_WIDE : 0);
+          *out++ = MCT_TILE_WORD(i, tx, ty, cls);
           count[cls]++;
         }
+      }
     }
   }
+  tiles.resize((size_t)(out - tiles.data()));
+  for (int c = 0; c < 8; c++) en->pu_count[part][c] = count[c];
   en->pu_ref_mask[part] = ref_mask;
   return B200_OK;
 }
@@ -1044,14 +1057,22 @@ static int plan_pus_merge(b200_engine* en, const b200_picture* pic, PicLayout* L
 // TU validation + the k_residual work classes for the TU range [i0, i1) into the part's own lists (two parts run on pool
 // threads; plan_and_pack concatenates them).  Classes: warp per TU (16x16, 32x32, PCM) | quarter-warp per 8x8 | lane per 4x4.
 #define PLAN_TU_PARTS PLAN_INTRA_PARTS  // validation and the intra task formation share one pass over a range of TUs
-// One TU record against the picture; B200_OK or the error (message set).
-static inline int tu_check(const b200_pic_params& p, const b200_picture* pic, uint32_t i, const b200_tu& tu)
+// One TU record against the picture; B200_OK or the error (message set).  `dims`: plane sizes per cIdx (0 when the plane does not exist).
+struct TuDims { int pw[3], ph[3]; };
+static inline TuDims tu_dims(const b200_pic_params& p)
 {
-  const int nT = 1 << tu.log2_size;
-  const int pw = tu.cidx ? p.width / 2 : p.width, ph = tu.cidx ? p.height / 2 : p.height;
-  if (tu.log2_size < 2 || tu.log2_size > 5 || tu.cidx > 2 || (tu.cidx && !p.chroma_format_idc) || tu.x + nT > pw || tu.y + nT > ph ||
-      (tu.x & 3) || (tu.y & 3) || (tu.x & (nT - 1)) || (tu.y & (nT - 1)))
-    return set_err(B200_ERR_INVALID, "TU %u out of range", i);
+  TuDims d;
+  d.pw[0] = p.width; d.ph[0] = p.height;
+  d.pw[1] = d.pw[2] = p.chroma_format_idc ? p.width / 2 : 0;
+  d.ph[1] = d.ph[2] = p.chroma_format_idc ? p.height / 2 : 0;
+  return d;
+}
+static inline int tu_check(const TuDims& d, const b200_picture* pic, uint32_t i, const b200_tu& tu)
+{
+  const unsigned l2 = tu.log2_size, c = tu.cidx;
+  if (l2 - 2u > 3u || c > 2u) return set_err(B200_ERR_INVALID, "TU %u out of range", i);
+  const int nT = 1 << l2, pw = d.pw[c], ph = d.ph[c];
+  if (tu.x + nT > pw || tu.y + nT > ph || ((tu.x | tu.y) & (nT - 1))) return set_err(B200_ERR_INVALID, "TU %u out of range", i);  // nT >= 4: also the 4-sample grid
   if ((size_t)tu.coeff_off + tu.n_coeff > pic->n_coeff || tu.n_coeff > nT * nT) return set_err(B200_ERR_INVALID, "TU %u coefficient range", i);
   if ((tu.flags & B200_TU_PCM) && tu.n_coeff != nT * nT) return set_err(B200_ERR_INVALID, "PCM TU %u sample count", i);
   if (tu.flags & B200_TU_INTRA) {
@@ -1115,20 +1136,26 @@ static int plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_d
   ip.intra_idx.clear();
   ip.task_of.clear();
   ip.task_first.clear();
+  ip.task_cell.clear();
   ip.diag_cnt.assign((size_t)n_diag, 0);
   // Pictures with inter prediction have few, scattered intra blocks: the per-task overhead of k_intra dominates there, so the
   // small TUs of ALL planes of a region form one task (luma, then Cb, then Cr) when they are at most 16; intra pictures keep
   // one task per plane (three shorter dependency chains side by side).
   const bool merged = pic->n_pu > 0 && !en->intra_split_planes;
   const int lg_region = en->region == 16 ? 4 : 3;
+  const TuDims dims = tu_dims(p);
   long long cur_key[3] = {-1, -1, -1};
   uint32_t cur_task[3] = {0, 0, 0};
   uint32_t run[48];  // merged mode: the small intra TUs of the current region (at most 16 + 4 + 4, sized generously)
   int n_run = 0;
   long long run_key = -1;
   auto new_task = [&](uint32_t first_tu) {
+    const b200_tu& ft = pic->tus[first_tu];
     ip.task_first.push_back(first_tu);
-    ip.diag_cnt[plan_diag_of(p, pic->tus[first_tu])]++;
+    ip.diag_cnt[plan_diag_of(p, ft)]++;
+    const uint32_t sh = ft.cidx ? 1 : 0;  // what plan_intra_levels needs of the task, kept here so that pass reads no TU record
+    const uint32_t R = std::max(1u, ((1u << ft.log2_size) << sh) >> lg_region);
+    ip.task_cell.push_back((((uint32_t)ft.x << sh) >> lg_region) | ((((uint32_t)ft.y << sh) >> lg_region) << 12) | (R << 24) | ((uint32_t)ft.cidx << 28));
     return (uint32_t)ip.task_first.size() - 1;
   };
   auto flush_run = [&]() {
@@ -1153,7 +1180,7 @@ static int plan_intra_A(b200_engine* en, const b200_picture* pic, int k, int n_d
   };
   for (uint32_t i = ip.i0; i < ip.i1; i++) {
     const b200_tu& tu = pic->tus[i];
-    if (const int rc = tu_check(p, pic, i, tu)) return rc;
+    if (const int rc = tu_check(dims, pic, i, tu)) return rc;
     if (!(tu.flags & B200_TU_INTRA)) {
       if (tu.flags & (B200_TU_CBF | B200_TU_PCM)) {
         if ((tu.flags & B200_TU_PCM) || tu.log2_size > 3) la.push_back(i);
@@ -1239,11 +1266,10 @@ static void plan_intra_levels(b200_engine* en, const b200_picture* pic, PicLayou
   for (int k = 0; k < PLAN_INTRA_PARTS; k++) {
     const IntraPart& ip = en->ipart[k];
     for (size_t t = 0; t < ip.task_first.size(); t++) {
-      const b200_tu& tu = pic->tus[ip.task_first[t]];
-      const int sh = tu.cidx ? 1 : 0;
-      const int cx = (tu.x << sh) >> lg, cy = (tu.y << sh) >> lg;
-      const int R = std::max(1, ((1 << tu.log2_size) << sh) >> lg);  // cells per side: 1 (region task) or the large TU's size
-      uint32_t* map = en->cell_level[per_plane ? tu.cidx : 0].data();
+      const uint32_t tc = ip.task_cell[t];
+      const int cx = (int)(tc & 0xfff), cy = (int)((tc >> 12) & 0xfff);
+      const int R = (int)((tc >> 24) & 0xf);  // cells per side: 1 (region task) or the large TU's size
+      uint32_t* map = en->cell_level[per_plane ? (tc >> 28) : 0].data();
       uint32_t lvl = 0;
       if (cx > 0)
         for (int y = std::max(cy - 1, 0); y < std::min(cy + 2 * R, ch); y++) lvl = std::max(lvl, map[(size_t)y * cw + cx - 1]);
