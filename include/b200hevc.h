@@ -292,12 +292,12 @@ B200_API int  b200_engine_timing_sum(b200_engine*, float ms[6], int* n_pictures,
 /* Number of kernels this engine has launched so far (bench.py "gpu_launches"). */
 B200_API uint64_t b200_engine_launch_count(const b200_engine*);
 
-/* Picture-level pipelining.  The engine issues pictures round-robin onto `n` CUDA streams (default 8, 1..12;
- * environment B200_STREAMS overrides the default) and orders them with per-slot events: a picture waits for the
- * writers of the slots it references and for all earlier readers / writers of its destination slot, so pictures
- * that do not depend on each other overlap on the GPU, in the spirit of libde265 decoding several images at once
- * (decctx.h:334 image_units, WPP/frame-parallel slice threads).  Results do not depend on n.  While per-stage
- * timing is enabled all pictures go to stream 0. */
+/* Picture-level pipelining.  The engine issues pictures onto `n` CUDA streams (default 8, 1..12; environment B200_STREAMS overrides
+ * the default) plus two more for pictures that read no reference, placed by dependency depth, and orders them with per-surface
+ * events: a picture waits for the writers of the slots it references; a destination slot that earlier pictures still read or write
+ * is renamed to an idle surface, so only true dependencies order pictures and pictures that do not depend on each
+ * other overlap on the GPU, in the spirit of libde265 decoding several images at once (decctx.h:334 image_units, WPP /
+ * frame-parallel slice threads).  Results do not depend on n.  While per-stage timing is enabled all pictures go to stream 0. */
 B200_API int  b200_engine_set_streams(b200_engine*, int n);
 /* Raw CUDA stream handle (cudaStream_t) of stream 0 so callers can bracket with their own events ... */
 B200_API void* b200_engine_stream(b200_engine*);
